@@ -1,0 +1,118 @@
+/* rovr_b200.h — C ABI of the B200-native ROVR hot path (librovr_b200.so).
+ *
+ * The reference (arjvik/Reinformcement-Optimized-Video-Reconstruction) has NO native code and no
+ * FFI: its boundary is the Python nn.Module surface. This header is therefore a
+ * new design: one plain-C entry point per fused operator and direction, bound from Python with
+ * ctypes by the drop-in modules. Each declaration cites the reference lines whose arithmetic it
+ * replaces.
+ *
+ * Conventions
+ *   - every pointer is a raw CUDA device pointer (tensor.data_ptr()); the caller allocates all
+ *     outputs and workspaces; nothing here allocates or synchronises;
+ *   - activations are NHWC bf16; `*_ld` is the channel stride of one pixel in elements, so a
+ *     pointer may address a channel slice of a wider (concat) buffer; slices start on multiples
+ *     of 8 channels and ld is a multiple of 8;
+ *   - parameters and parameter gradients are fp32 in the PyTorch layouts of the reference
+ *     state_dict (Conv2d [Cout][Cin][kh][kw], ConvTranspose2d [Cin][Cout][kh][kw]);
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return 0 on success, negative on error; rovr_last_error() describes the last failure on the
+ *     calling thread. There is no CPU fallback: without an sm_100 device every compute call fails.
+ */
+#ifndef ROVR_B200_H
+#define ROVR_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int rovr_abi_version(void);
+const char* rovr_last_error(void);
+/* 0 if the current device is sm_100 (B200); negative otherwise. */
+int rovr_device_check(void);
+/* last mbarrier-timeout code recorded by a kernel (0 = none); debugging aid. */
+int rovr_hang_code(unsigned int* code);
+
+/* ---- layout packing ------------------------------------------------------------------------
+ * cat of up to three NCHW fp32 tensors along C, converted to NHWC bf16 padded to cpad channels.
+ * Replaces torch.cat + rearrange 'b n c h w -> b (n c) h w' (rovr/local_net.py:48-49) and
+ * torch.cat([x, context], 1) (rovr/policy_net_1.py:88). */
+int rovr_pack_nchw_to_nhwc(const float* s0, int c0, const float* s1, int c1, const float* s2, int c2,
+                           void* dst, int B, int H, int W, int cpad, void* stream);
+int rovr_unpack_nhwc_to_nchw(const void* src, int ld, float* dst, int B, int H, int W, int C,
+                             void* stream);
+
+/* ---- weight repacking (fp32 parameter -> bf16 K-major GEMM operand) ------------------------- */
+/* Conv2d 3x3 weight [Cout][Cin][3][3] -> [Cout][9][cin_pad] */
+int rovr_repack_conv3x3_fprop(const float* w, void* wk, int Cout, int Cin, int cin_pad, void* stream);
+/* Conv2d 3x3 weight -> [cin_pad][9][Cout] (rows >= Cin are zero) for the data gradient */
+int rovr_repack_conv3x3_dgrad(const float* w, void* wk, int Cout, int Cin, int cin_pad, void* stream);
+/* ConvTranspose2d 2x2 weight [Cin][Cout][2][2] -> [4*Cout][Cin] (row = q*Cout+co, q = 2*ky+kx) */
+int rovr_repack_convT2x2_fprop(const float* w, void* wk, int Cin, int Cout, void* stream);
+/* ConvTranspose2d 2x2 weight -> [Cin][4*Cout] */
+int rovr_repack_convT2x2_dgrad(const float* w, void* wk, int Cin, int Cout, void* stream);
+
+/* ---- Conv2d 3x3, padding 1 (+bias, +ReLU) ---------------------------------------------------
+ * Replaces nn.Conv2d(k=3,p=1) + F.relu: rovr/local_net.py:12-18,26,31,36,52-68;
+ * rovr/policy_net_1.py:19-47,61-81; rovr/policy_net_2.py:42-54. Cin, Cout multiples of 16. */
+int rovr_conv3x3_fprop(const void* x, int x_ld, const void* wk, const float* bias, void* y, int y_ld,
+                       int B, int H, int W, int Cin, int Cout, int relu, void* stream);
+/* dx = conv3x3^T(dy); if mask != NULL, dx *= (mask > 0) (ReLU of the producer of x). */
+int rovr_conv3x3_dgrad(const void* dy, int dy_ld, const void* wk_d, void* dx, int dx_ld,
+                       const void* mask, int mask_ld, int B, int H, int W, int Cin, int Cout,
+                       void* stream);
+size_t rovr_conv3x3_wgrad_workspace(int B, int H, int W, int Cin, int Cout);
+/* dw[Cout][cin_keep][3][3] (fp32) = sum_pixels dy (x) x_shifted; Cin is the padded channel count
+ * of x, cin_keep <= Cin the true one. */
+int rovr_conv3x3_wgrad(const void* dy, int dy_ld, const void* x, int x_ld, float* dw, int B, int H,
+                       int W, int Cin, int cin_keep, int Cout, void* ws, size_t ws_bytes,
+                       void* stream);
+
+/* ---- ConvTranspose2d k=2 s=2 (+bias, +ReLU), H and W are the INPUT resolution ---------------
+ * Replaces nn.ConvTranspose2d(k=2,s=2) + F.relu: rovr/local_net.py:24,29,34,58,62,66;
+ * rovr/policy_net_1.py:32,37,42,67-77. y is written pixel-shuffled straight into its (concat)
+ * destination: the torch.cat of rovr/local_net.py:59,63,67 never materialises. */
+int rovr_convT2x2_fprop(const void* x, int x_ld, const void* wk, const float* bias, void* y, int y_ld,
+                        int B, int H, int W, int Cin, int Cout, int relu, void* stream);
+int rovr_convT2x2_dgrad(const void* dy, int dy_ld, const void* wk_d, void* dx, int dx_ld,
+                        const void* mask, int mask_ld, int B, int H, int W, int Cin, int Cout,
+                        void* stream);
+size_t rovr_convT2x2_wgrad_workspace(int B, int H, int W, int Cin, int Cout);
+int rovr_convT2x2_wgrad(const void* dy, int dy_ld, const void* x, int x_ld, float* dw, int B, int H,
+                        int W, int Cin, int Cout, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- plain GEMM on the same engine: y[M][N] = x[M][K] . wk[N][K]^T + bias (bf16 in, bf16 or fp32 out)
+ * Replaces nn.Linear / 1x1 convolutions on bf16 activations. K multiple of 16, N multiple of 16. */
+int rovr_gemm_bf16(const void* x, int x_ld, const void* wk, const float* bias, void* y_bf16,
+                   float* y_f32, int y_ld, int M, int N, int K, int relu, void* stream);
+
+/* ---- max pooling -----------------------------------------------------------------------------
+ * nn.MaxPool2d: rovr/local_net.py:21,53-55; rovr/policy_net_1.py:29; rovr/policy_net_2.py:45-58. */
+int rovr_maxpool_fwd(const void* x, int x_ld, void* y, int y_ld, int B, int H, int W, int C, int kh,
+                     int kw, int sh, int sw, void* stream);
+/* gx = [relu_mask: (x > 0) *] (gskip + maxpool_backward(gp)); gskip may be NULL. */
+int rovr_maxpool_bwd(const void* x, int x_ld, const void* gp, int gp_ld, const void* gskip, int gs_ld,
+                     void* gx, int gx_ld, int B, int H, int W, int C, int kh, int kw, int sh, int sw,
+                     int relu_mask, void* stream);
+
+/* ---- LocalNet tail: conv8 1x1 (64->3) + sigmoid (+ fused L2 loss) ------------------------------
+ * rovr/local_net.py:39,71; nn.MSELoss of rovr/train_local_net_unet.py:90,107.
+ * out: NCHW fp32 [B][3][H][W]. If target != NULL, *loss = mean((out-target)^2) (ws >= 4*ceil(B*H*W/256)). */
+size_t rovr_tail_workspace(int B, int H, int W);
+int rovr_tail_fwd(const void* y7, const float* w8, const float* b8, float* out, const float* target,
+                  float* loss, void* ws, size_t ws_bytes, int B, int H, int W, void* stream);
+/* g7 (NHWC bf16, ld 64), dw8[3][64], db8[3]. dL/dout = gout (NCHW fp32, may be NULL) +
+ * mse_scale * (*gloss) * (out - target) when target != NULL (mse_scale = 2 / numel; gloss is the
+ * device scalar dL/dloss, NULL = 1). */
+int rovr_tail_bwd(const void* y7, const float* w8, const float* out, const float* gout,
+                  const float* target, float mse_scale, const float* gloss, void* g7, float* dw8,
+                  float* db8, void* ws, size_t ws_bytes, int B, int H, int W, void* stream);
+
+/* ---- bias gradient: out[c] = sum over pixels of g[pixel][c]; C even, C <= 512 ------------------ */
+size_t rovr_colsum_workspace(int C);
+int rovr_colsum(const void* g, int ld, long long npix, int C, float* out, void* ws, size_t ws_bytes,
+                void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROVR_B200_H */

@@ -1,0 +1,419 @@
+"""CPU oracle for the ROVR hot path — TEST INFRASTRUCTURE ONLY.
+
+A plain PyTorch fp32 *functional* restatement of the reference networks' arithmetic, written
+from the reference's forward() bodies (each function cites the lines it follows). It is the
+checker the CUDA path is compared against; nothing under oracle/ is ever imported by the product
+package. Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import it.
+
+Pinning: the reference ships no tests, golden vectors or fixtures, so the
+oracle is pinned against the reference itself: tests/golden/make_golden.py imports the unmodified
+reference classes from /root/reference/rovr in the build container, loads the deterministic
+weights of `make_state_dict` into them, and stores their outputs / gradients under
+tests/golden/*.npz. tests/test_oracle_golden.py checks this file against those fixtures.
+Third-party arithmetic: torch.nn.functional (torch 2.11.0 in this image; the reference pins
+nothing) and torchvision.models.resnet50 (0.26.0) for the frame extractor.
+
+The functions take a `state_dict`-style mapping of tensors so that the same weights can be fed
+to the reference classes, to this oracle and to the B200 modules.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+# ------------------------------------------------------------------------------------------------
+# deterministic weights (shared by the golden generator, the oracle tests and the GPU tests)
+# ------------------------------------------------------------------------------------------------
+# LocalNetworkUNetNorm: registration order of rovr/local_net.py:12-39
+LOCALNET_SPEC = [
+    ("conv1", "conv3", 9, 64), ("bn1", "bn", 64), ("conv2", "conv3", 64, 128), ("bn2", "bn", 128),
+    ("conv3", "conv3", 128, 256), ("bn3", "bn", 256), ("conv4", "conv3", 256, 512), ("bn4", "bn", 512),
+    ("upconv1", "up2", 512, 256), ("bn_up1", "bn", 256), ("conv5", "conv3", 512, 256), ("bn5", "bn", 256),
+    ("upconv2", "up2", 256, 128), ("bn_up2", "bn", 128), ("conv6", "conv3", 256, 128), ("bn6", "bn", 128),
+    ("upconv3", "up2", 128, 64), ("bn_up3", "bn", 64), ("conv7", "conv3", 128, 64), ("bn7", "bn", 64),
+    ("conv8", "conv1", 64, 3),
+]
+# PolicyNetwork1UNet: rovr/policy_net_1.py:19-57 (fc_final appended per is_critic)
+PN1_SPEC = [
+    ("conv1", "conv3", 6, 32), ("bn1", "bn", 32), ("conv2", "conv3", 32, 64), ("bn2", "bn", 64),
+    ("conv3", "conv3", 64, 128), ("bn3", "bn", 128), ("conv4", "conv3", 128, 256), ("bn4", "bn", 256),
+    ("upconv1", "up2", 256, 128), ("bn_up1", "bn", 128), ("conv5", "conv3", 256, 128), ("bn5", "bn", 128),
+    ("upconv2", "up2", 128, 64), ("bn_up2", "bn", 64), ("conv6", "conv3", 128, 64), ("bn6", "bn", 64),
+    ("upconv3", "up2", 64, 32), ("bn_up3", "bn", 32), ("conv7", "conv3", 64, 32), ("bn7", "bn", 32),
+    ("conv8", "conv1", 32, 3), ("bn8", "bn", 3), ("conv9", "conv1", 3, 1), ("bn9", "bn", 1),
+]
+# PolicyNetwork2UNet: rovr/policy_net_2.py:27-69 (Sequential indices)
+PN2_SPEC = [
+    ("context_conv.0", "conv3", 3, 128), ("context_conv.3", "conv3", 128, 256),
+    ("context_conv.6", "conv3", 256, 512),
+    ("video_conv.0", "conv3", 1, 64), ("video_conv.1", "bn", 64),
+    ("video_conv.4", "conv3", 64, 128), ("video_conv.5", "bn", 128),
+    ("video_conv.8", "conv3", 128, 256), ("video_conv.9", "bn", 256),
+    ("video_conv.12", "conv3", 256, 512), ("video_conv.13", "bn", 512),
+    ("final_fc.0", "linear", 2048, 1024), ("final_fc.1", "linear", 1024, 512),
+    ("final_fc.2", "linear", 512, 256), ("final_fc.3", "linear", 256, 64),
+]
+
+
+def _fill(gen, shape, bound):
+    return (torch.rand(shape, generator=gen, dtype=torch.float32) * 2.0 - 1.0) * bound
+
+
+def state_dict_from_spec(spec, seed, gain=1.0, bn_affine_noise=True):
+    """Deterministic fp32 weights for a layer spec. Conv/linear ~ U(-k, k), k = gain*sqrt(3/fan_in)
+    (variance-preserving, so activations stay O(1) through the U-Net); BatchNorm affine slightly
+    perturbed around (1, 0) so that its gradients are exercised."""
+    gen = torch.Generator().manual_seed(seed)
+    sd = {}
+    for item in spec:
+        name, kind = item[0], item[1]
+        if kind == "conv3":
+            cin, cout = item[2], item[3]
+            k = gain * math.sqrt(3.0 / (cin * 9))
+            sd[name + ".weight"] = _fill(gen, (cout, cin, 3, 3), k)
+            sd[name + ".bias"] = _fill(gen, (cout,), 0.1)
+        elif kind == "conv1":
+            cin, cout = item[2], item[3]
+            k = gain * math.sqrt(3.0 / cin)
+            sd[name + ".weight"] = _fill(gen, (cout, cin, 1, 1), k)
+            sd[name + ".bias"] = _fill(gen, (cout,), 0.1)
+        elif kind == "up2":
+            cin, cout = item[2], item[3]
+            k = gain * math.sqrt(3.0 / cin)
+            sd[name + ".weight"] = _fill(gen, (cin, cout, 2, 2), k)
+            sd[name + ".bias"] = _fill(gen, (cout,), 0.1)
+        elif kind == "linear":
+            cin, cout = item[2], item[3]
+            k = gain * math.sqrt(3.0 / cin)
+            sd[name + ".weight"] = _fill(gen, (cout, cin), k)
+            sd[name + ".bias"] = _fill(gen, (cout,), 0.1)
+        elif kind == "bn":
+            c = item[2]
+            if bn_affine_noise:
+                sd[name + ".weight"] = 1.0 + _fill(gen, (c,), 0.2)
+                sd[name + ".bias"] = _fill(gen, (c,), 0.2)
+            else:
+                sd[name + ".weight"] = torch.ones(c)
+                sd[name + ".bias"] = torch.zeros(c)
+            sd[name + ".running_mean"] = torch.zeros(c)
+            sd[name + ".running_var"] = torch.ones(c)
+            sd[name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+        else:
+            raise ValueError(kind)
+    return sd
+
+
+def localnet_state_dict(seed=0):
+    return state_dict_from_spec(LOCALNET_SPEC, seed, gain=math.sqrt(2.0), bn_affine_noise=False)
+
+
+def pn1_state_dict(seed=0, is_critic=False):
+    sd = state_dict_from_spec(PN1_SPEC, seed, gain=math.sqrt(2.0))
+    extra = state_dict_from_spec([("fc_final", "linear", 400, 1 if is_critic else 25)], seed + 1000)
+    sd.update(extra)
+    return sd
+
+
+def pn2_state_dict(seed=0, is_critic=False):
+    sd = state_dict_from_spec(PN2_SPEC, seed, gain=math.sqrt(2.0))
+    extra = state_dict_from_spec([("final_fc.4", "linear", 64, 1 if is_critic else 20)], seed + 1000)
+    sd.update(extra)
+    return sd
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic masked-video inputs (mask geometry mirrors rovr/video_ds.py:19,62-87)
+# ------------------------------------------------------------------------------------------------
+def synthetic_localnet_batch(B, H, W, seed=1234):
+    """frame [B,3,H,W], context [B,2,3,H,W], target [B,3,H,W] in [0,1], fp32, CPU.
+
+    A clip is a smooth random field translated a little per frame so that neighbouring frames
+    correlate; frame f and its two predecessors are corrupted by a zeroed box (150x100 at 256^2,
+    scaled with resolution) whose position follows the raster scan of rovr/video_ds.py:62-87;
+    target = clean frame f-1 (rovr/train_local_net_unet.py:44-52)."""
+    gen = torch.Generator().manual_seed(seed)
+    base = torch.rand((B, 3, 16, 16), generator=gen)
+    big = F.interpolate(base, size=(H + 8, W + 8), mode="bilinear", align_corners=False)
+    fidx = torch.randint(2, 25, (B,), generator=gen)
+    bw, bh = max(1, (150 * W) // 256), max(1, (100 * H) // 256)
+
+    def frame_at(b, n):
+        dx, dy = int(n) % 8, (int(n) // 3) % 8
+        clean = big[b, :, dy:dy + H, dx:dx + W]
+        mask = torch.ones((1, H, W))
+        x0 = ((int(n) % 8) * 32 * W) // 256
+        y0 = ((int(n) // 8) * (256 // 3) * H) // 256
+        mask[:, y0:min(H, y0 + bh), x0:min(W, x0 + bw)] = 0.0
+        return clean, clean * mask
+
+    frames, ctx, tgt = [], [], []
+    for b in range(B):
+        f = int(fidx[b])
+        _, cf = frame_at(b, f)
+        clean_m, cm = frame_at(b, f - 1)
+        _, cn = frame_at(b, f - 2)
+        frames.append(cf)
+        ctx.append(torch.stack([cn, cm], 0))
+        tgt.append(clean_m)
+    return (torch.stack(frames).contiguous(), torch.stack(ctx).contiguous(),
+            torch.stack(tgt).contiguous())
+
+
+# ------------------------------------------------------------------------------------------------
+# LocalNet
+# ------------------------------------------------------------------------------------------------
+def localnet_forward(sd, x, context):
+    """rovr/local_net.py:46-72. BatchNorm layers are registered (:13-37) but never applied."""
+    b = x.shape[0]
+    # :48-49  cat along a new frame axis, then fold (frame, channel) -> channel: [x | ctx0 | ctx1]
+    h = torch.cat([x[:, None], context], dim=1).reshape(b, 9, x.shape[2], x.shape[3])
+
+    def conv(name, t):
+        return F.relu(F.conv2d(t, sd[name + ".weight"], sd[name + ".bias"], padding=1))
+
+    def up(name, t):
+        return F.relu(F.conv_transpose2d(t, sd[name + ".weight"], sd[name + ".bias"], stride=2))
+
+    e1 = conv("conv1", h)                                   # :52
+    e2 = conv("conv2", F.max_pool2d(e1, 2))                 # :53
+    e3 = conv("conv3", F.max_pool2d(e2, 2))                 # :54
+    e4 = conv("conv4", F.max_pool2d(e3, 2))                 # :55
+    d = conv("conv5", torch.cat([up("upconv1", e4), e3], 1))  # :58-60  (order: [up, skip])
+    d = conv("conv6", torch.cat([up("upconv2", d), e2], 1))   # :62-64
+    d = conv("conv7", torch.cat([up("upconv3", d), e1], 1))   # :66-68
+    return torch.sigmoid(F.conv2d(d, sd["conv8.weight"], sd["conv8.bias"]))  # :71
+
+
+LOCALNET_LIVE = [n + s for n in ["conv1", "conv2", "conv3", "conv4", "upconv1", "conv5", "upconv2",
+                                 "conv6", "upconv3", "conv7", "conv8"] for s in (".weight", ".bias")]
+
+
+def localnet_step(sd, x, context, target):
+    """One training step's arithmetic, rovr/train_local_net_unet.py:102-107,115 restricted to the
+    named path: y = net(x, ctx); loss = MSELoss()(y, target); loss.backward() (no LPIPS — it is a
+    third-party package that is not part of the path — and no optimizer). Returns y, loss, grads."""
+    leaf = {k: (v.clone().requires_grad_(True) if k in LOCALNET_LIVE else v) for k, v in sd.items()}
+    y = localnet_forward(leaf, x, context)
+    loss = F.mse_loss(y, target)
+    loss.backward()
+    return y.detach(), loss.detach(), {k: leaf[k].grad for k in LOCALNET_LIVE}
+
+
+# ------------------------------------------------------------------------------------------------
+# Policy network 1
+# ------------------------------------------------------------------------------------------------
+def _bn_train(sd, name, t, eps=1e-5):
+    """Train-mode BatchNorm2d (batch statistics, biased variance for normalisation). Running-stat
+    updates are returned by pn*_running_stats, not applied here."""
+    return F.batch_norm(t, None, None, sd[name + ".weight"], sd[name + ".bias"], True, 0.0, eps)
+
+
+def pn1_unet(sd, x):
+    """rovr/policy_net_1.py:60-84: LocalNet-shaped U-Net at half width with BN after every conv."""
+    def cbr(conv, bn, t, pad=1):
+        return F.relu(_bn_train(sd, bn, F.conv2d(t, sd[conv + ".weight"], sd[conv + ".bias"], padding=pad)))
+
+    def ubr(up, bn, t):
+        return F.relu(_bn_train(sd, bn, F.conv_transpose2d(t, sd[up + ".weight"], sd[up + ".bias"], stride=2)))
+
+    e1 = cbr("conv1", "bn1", x)
+    e2 = cbr("conv2", "bn2", F.max_pool2d(e1, 2))
+    e3 = cbr("conv3", "bn3", F.max_pool2d(e2, 2))
+    e4 = cbr("conv4", "bn4", F.max_pool2d(e3, 2))
+    d = cbr("conv5", "bn5", torch.cat([ubr("upconv1", "bn_up1", e4), e3], 1))
+    d = cbr("conv6", "bn6", torch.cat([ubr("upconv2", "bn_up2", d), e2], 1))
+    d = cbr("conv7", "bn7", torch.cat([ubr("upconv3", "bn_up3", d), e1], 1))
+    d = cbr("conv8", "bn8", d, pad=0)                                  # :80
+    d = cbr("conv9", "bn9", F.max_pool2d(d, 2), pad=0)                 # :81
+    return F.max_pool2d(d, 2)                                          # :82
+
+
+def pn1_compute_logits(sd, image, context):
+    """rovr/policy_net_1.py:86-94: flatten 400, per-sample standardise (unbiased std, NO eps), fc."""
+    feat = pn1_unet(sd, torch.cat([image, context], dim=1)).flatten(1)
+    feat = (feat - feat.mean(dim=1, keepdim=True)) / feat.std(dim=1, keepdim=True)
+    return F.linear(feat, sd["fc_final.weight"], sd["fc_final.bias"])
+
+
+def gumbel_softmax_with_noise(logits, tau, expo):
+    """F.gumbel_softmax(hard=False, dim=1) with the Exp(1) draw made explicit:
+    gumbels = -log(expo); softmax((logits + gumbels) / tau). torch's implementation draws
+    `torch.empty_like(logits).exponential_()` from the device's global generator."""
+    return F.softmax((logits - expo.log()) / tau, dim=1)
+
+
+def pn1_forward(sd, image, context, is_critic, expo=None):
+    """rovr/policy_net_1.py:96-105. Actor: valid for b == 1 only (mean(dim=1) has no keepdim)."""
+    logits = pn1_compute_logits(sd, image, context)
+    if is_critic:
+        return logits.squeeze(1)
+    logits = (logits - logits.mean(dim=1)) / (logits.std(dim=(1,), keepdim=True) + 0.1)
+    probs = gumbel_softmax_with_noise(logits, 0.5, expo)
+    mx = probs.max(dim=1)
+    return mx.indices, mx.values.log()
+
+
+def pn1_logprob(sd, image, context, action, expo):
+    """rovr/policy_net_1.py:107-114: gumbel-softmax on the UN-standardised logits, gather, log."""
+    logits = pn1_compute_logits(sd, image, context)
+    probs = gumbel_softmax_with_noise(logits, 0.5, expo)
+    return probs.gather(1, action[:, None]).log().squeeze(1)
+
+
+# ------------------------------------------------------------------------------------------------
+# Policy network 2
+# ------------------------------------------------------------------------------------------------
+def pn2_video_conv(sd, image):
+    """rovr/policy_net_2.py:41-60: 4 x [conv3x3 + BN + ReLU + pool] on [b,1,160,160] -> [b,1024]."""
+    def cbr(i, t):
+        c, b = f"video_conv.{i}", f"video_conv.{i + 1}"
+        return F.relu(_bn_train(sd, b, F.conv2d(t, sd[c + ".weight"], sd[c + ".bias"], padding=1)))
+
+    t = F.max_pool2d(cbr(0, image), 8, 8)
+    t = F.max_pool2d(cbr(4, t), 4, 4)
+    t = F.max_pool2d(cbr(8, t), 1, 1)
+    t = cbr(12, t)
+    t = F.max_pool2d(t, 2, (2, 1))
+    t = F.max_pool2d(t, 2, (2, 2))
+    return t.flatten(1)
+
+
+def pn2_final_fc(sd, v):
+    """rovr/policy_net_2.py:63-69,71-79: five Linear layers with no activation between them."""
+    for i in range(5):
+        v = F.linear(v, sd[f"final_fc.{i}.weight"], sd[f"final_fc.{i}.bias"])
+    return v
+
+
+def pn2_masked_logits(sd, stacked, target):
+    """rovr/policy_net_2.py:110-124: zero the target column(s), then (l - mean) / (std + .1) where
+    mean(dim=1) has NO keepdim — for b == 20 it subtracts the mean of row j from column j;
+    reproduced as written."""
+    logits = pn2_final_fc(sd, stacked)
+    idx = target.to(torch.int64).squeeze(1)
+    logits = logits.scatter(1, idx, 0.0)
+    return (logits - logits.mean(dim=1)) / (logits.std(dim=(1,), keepdim=True) + 0.1)
+
+
+def pn2_forward(sd, image, context, target, is_critic, extra=None, expo=None):
+    """rovr/policy_net_2.py:81-108."""
+    if is_critic:
+        image = image[:, None]
+    stacked = torch.cat([pn2_video_conv(sd, image), context.squeeze(1)], dim=1)
+    if extra is not None:
+        return pn2_masked_logits(sd, stacked, target)
+    if not is_critic:
+        logits = pn2_masked_logits(sd, stacked, target)
+        probs = gumbel_softmax_with_noise(logits, 0.7, expo)
+        top = torch.topk(probs, k=2, dim=1)
+        return top.indices, top.values.log().sum(1) / 2 + 0.69314
+    mean = stacked.mean(dim=0, keepdim=True)
+    std = stacked.std(dim=0, keepdim=True)
+    return pn2_final_fc(sd, (stacked - mean) / (std + 0.001)).squeeze(1)
+
+
+def pn2_logprob(sd, image, context, target, action, expo):
+    """rovr/policy_net_2.py:127-141."""
+    stacked = torch.cat([pn2_video_conv(sd, image[:, None]), context.squeeze(1)], dim=1)
+    logits = pn2_final_fc(sd, stacked).scatter(1, target.to(torch.int64), 0.0)
+    probs = gumbel_softmax_with_noise(logits, 0.7, expo)
+    pair = (probs[:, :, None] * probs[:, None, :]).flatten(1)
+    flat_action = action[:, 0] * probs.shape[1] + action[:, 1]
+    return pair.gather(1, flat_action[:, None]).log().sum(1) / 2 + 0.69314
+
+
+def bn_running_update(x, running_mean, running_var, momentum=0.1):
+    """What train-mode BatchNorm2d does to its buffers: unbiased variance, momentum 0.1."""
+    mean = x.mean(dim=(0, 2, 3))
+    var = x.var(dim=(0, 2, 3), unbiased=True)
+    return (1 - momentum) * running_mean + momentum * mean, (1 - momentum) * running_var + momentum * var
+
+
+# ------------------------------------------------------------------------------------------------
+# common_layers blocks
+# ------------------------------------------------------------------------------------------------
+def layer_norm(sd, name, t):
+    return F.layer_norm(t, (t.shape[-1],), sd[name + ".weight"], sd[name + ".bias"])
+
+
+def mha(sd, name, q, kv, num_heads):
+    """nn.MultiheadAttention(batch_first=True), eval-mode (dropout inactive): packed in-proj
+    [3E, E], per-head softmax(QK^T / sqrt(d)) V, out-proj. Returns the attention output only."""
+    E = q.shape[-1]
+    w, b = sd[name + ".in_proj_weight"], sd[name + ".in_proj_bias"]
+    Q = F.linear(q, w[:E], b[:E])
+    K = F.linear(kv, w[E:2 * E], b[E:2 * E])
+    V = F.linear(kv, w[2 * E:], b[2 * E:])
+    B, S, _ = Q.shape
+    T = K.shape[1]
+    d = E // num_heads
+    Q = Q.view(B, S, num_heads, d).transpose(1, 2)
+    K = K.view(B, T, num_heads, d).transpose(1, 2)
+    V = V.view(B, T, num_heads, d).transpose(1, 2)
+    att = torch.softmax(Q @ K.transpose(-1, -2) / math.sqrt(d), dim=-1)
+    o = (att @ V).transpose(1, 2).reshape(B, S, E)
+    return F.linear(o, sd[name + ".out_proj.weight"], sd[name + ".out_proj.bias"])
+
+
+def self_attention_block(sd, prefix, x, num_heads):
+    """rovr/common_layers.py:54-64: x = LN(x); x = x + MHA(x, x, x) (residual on the normalised x)."""
+    x = layer_norm(sd, prefix + "layer_norm", x)
+    return x + mha(sd, prefix + "attention", x, x, num_heads)
+
+
+def cross_attention_block(sd, prefix, x, enc, num_heads):
+    """rovr/common_layers.py:66-78."""
+    x = layer_norm(sd, prefix + "layer_norm", x)
+    enc = layer_norm(sd, prefix + "layer_norm_encoder_output", enc)
+    return x + mha(sd, prefix + "attention", x, enc, num_heads)
+
+
+def feed_forward_block(sd, prefix, x):
+    """rovr/common_layers.py:80-92: LN -> fc1 (E -> E/4) -> exact GELU -> (dropout) -> fc2."""
+    x = layer_norm(sd, prefix + "layer_norm", x)
+    h = F.gelu(F.linear(x, sd[prefix + "fc1.weight"], sd[prefix + "fc1.bias"]))
+    return F.linear(h, sd[prefix + "fc2.weight"], sd[prefix + "fc2.bias"])
+
+
+def encoder_block(sd, prefix, x, num_heads):
+    """rovr/common_layers.py:94-104."""
+    x = x + self_attention_block(sd, prefix + "attention.", x, num_heads)
+    return x + feed_forward_block(sd, prefix + "feed_forward.", x)
+
+
+def decoder_block(sd, prefix, x, enc, num_heads):
+    """rovr/common_layers.py:106-118."""
+    x = x + self_attention_block(sd, prefix + "attention.", x, num_heads)
+    x = x + cross_attention_block(sd, prefix + "cross_attention.", x, enc, num_heads)
+    return x + feed_forward_block(sd, prefix + "feed_forward.", x)
+
+
+def image_positional_encoding(sd, prefix, x, num_image_patches):
+    """rovr/common_layers.py:7-25: Linear(1, P^2 C) applied to arange(n^2), added to x."""
+    pos = torch.arange(num_image_patches ** 2, dtype=torch.float32)[:, None]
+    return x + F.linear(pos, sd[prefix + "positional_encoder.weight"], sd[prefix + "positional_encoder.bias"])[None]
+
+
+def context_positional_encoding(sd, prefix, x, num_context_patches, num_context):
+    """rovr/common_layers.py:27-52."""
+    pp = torch.arange(num_context_patches ** 2, dtype=torch.float32)[:, None]
+    cp = torch.arange(num_context, dtype=torch.float32)[:, None]
+    patch = F.linear(pp, sd[prefix + "patch_positional_encoder.weight"], sd[prefix + "patch_positional_encoder.bias"])
+    ctx = F.linear(cp, sd[prefix + "context_positional_encoder.weight"], sd[prefix + "context_positional_encoder.bias"])
+    table = (patch[None, :, :] + ctx[:, None, :]).reshape(1, -1, patch.shape[-1])
+    return x + table
+
+
+# ------------------------------------------------------------------------------------------------
+# ActionLSTM
+# ------------------------------------------------------------------------------------------------
+def action_lstm_step(sd, action, new_tensor, hx, cx):
+    """rovr/action_lstm.py:19-38: LSTMCell(3 + 2304, hidden) + Linear(hidden, 19200) -> [b,3,80,80]."""
+    inp = torch.cat([action.float() / 48, new_tensor.flatten(1)], dim=1)
+    gates = F.linear(inp, sd["lstm.weight_ih"], sd["lstm.bias_ih"]) + F.linear(hx, sd["lstm.weight_hh"], sd["lstm.bias_hh"])
+    i, f, g, o = gates.chunk(4, dim=1)
+    cx = torch.sigmoid(f) * cx + torch.sigmoid(i) * torch.tanh(g)
+    hx = torch.sigmoid(o) * torch.tanh(cx)
+    out = F.linear(hx, sd["fc.weight"], sd["fc.bias"]).view(-1, 3, 80, 80)
+    return out, hx, cx

@@ -1,0 +1,87 @@
+"""ctypes binding of librovr_b200.so (include/rovr_b200.h).
+
+There is deliberately no fallback: if the library is missing the import raises, and if the device
+is not an sm_100 GPU every compute call raises RuntimeError with the library's error text.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librovr_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing. Build it with `python __graft_entry__.py build` "
+        "(nvcc, sm_100a). The ROVR B200 path has no CPU or PyTorch fallback."
+    )
+
+lib = ctypes.CDLL(LIB_PATH)
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_f = ctypes.c_float
+_sz = ctypes.c_size_t
+_ll = ctypes.c_longlong
+
+# name -> (restype, argtypes); must list every symbol declared in include/rovr_b200.h
+SIGNATURES = {
+    "rovr_abi_version": (_i, []),
+    "rovr_last_error": (ctypes.c_char_p, []),
+    "rovr_device_check": (_i, []),
+    "rovr_hang_code": (_i, [ctypes.POINTER(ctypes.c_uint)]),
+    "rovr_pack_nchw_to_nhwc": (_i, [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p]),
+    "rovr_unpack_nhwc_to_nchw": (_i, [_p, _i, _p, _i, _i, _i, _i, _p]),
+    "rovr_repack_conv3x3_fprop": (_i, [_p, _p, _i, _i, _i, _p]),
+    "rovr_repack_conv3x3_dgrad": (_i, [_p, _p, _i, _i, _i, _p]),
+    "rovr_repack_convT2x2_fprop": (_i, [_p, _p, _i, _i, _p]),
+    "rovr_repack_convT2x2_dgrad": (_i, [_p, _p, _i, _i, _p]),
+    "rovr_conv3x3_fprop": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_conv3x3_dgrad": (_i, [_p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_conv3x3_wgrad_workspace": (_sz, [_i, _i, _i, _i, _i]),
+    "rovr_conv3x3_wgrad": (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "rovr_convT2x2_fprop": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_convT2x2_dgrad": (_i, [_p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_convT2x2_wgrad_workspace": (_sz, [_i, _i, _i, _i, _i]),
+    "rovr_convT2x2_wgrad": (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "rovr_gemm_bf16": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "rovr_maxpool_fwd": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_maxpool_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_tail_workspace": (_sz, [_i, _i, _i]),
+    "rovr_tail_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _p]),
+    "rovr_tail_bwd": (_i, [_p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _p]),
+    "rovr_colsum_workspace": (_sz, [_i]),
+    "rovr_colsum": (_i, [_p, _i, _ll, _i, _p, _p, _sz, _p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here == header/library mismatch
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+class RovrError(RuntimeError):
+    pass
+
+
+def last_error():
+    return lib.rovr_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise RovrError(f"{what or 'librovr_b200'} failed (rc={rc}): {last_error()}")
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point and raise on a non-zero status."""
+    check(getattr(lib, name)(*args), name)
+
+
+def require_device():
+    check(lib.rovr_device_check(), "rovr_device_check")
+
+
+def hang_code():
+    c = ctypes.c_uint(0)
+    lib.rovr_hang_code(ctypes.byref(c))
+    return c.value

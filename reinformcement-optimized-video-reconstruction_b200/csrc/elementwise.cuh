@@ -1,0 +1,417 @@
+// elementwise.cuh — the HBM-bound kernels around the tensor-core engine: layout packing, max
+// pooling (forward / backward fused with the skip-gradient add and ReLU mask), the 1x1-conv +
+// sigmoid + L2-loss tail of LocalNet and its backward, per-channel column sums (bias gradients)
+// and weight repacking. All are coalesced 16-byte-vector kernels; reductions are two-stage and
+// deterministic (no float atomics).
+#pragma once
+#include "ptx.cuh"
+
+namespace rovr {
+
+// ---------------------------------------------------------------------------------------------
+// NCHW fp32 (up to 3 source tensors, channel-concatenated) -> NHWC bf16 padded to cpad channels.
+// Reference: the input pack of LocalNet, rovr/local_net.py:48-49 (cat + 'b n c h w -> b (n c) h w'),
+// and torch.cat([x, context], 1) of rovr/policy_net_1.py:88.
+// ---------------------------------------------------------------------------------------------
+struct PackSrc {
+  const float* ptr[3];
+  int ch[3];
+  int nsrc;
+};
+__global__ void pack_nchw_to_nhwc_kernel(PackSrc src, __nv_bfloat16* __restrict__ dst, int B,
+                                         int HW, int cpad) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * HW) return;
+  const int b = static_cast<int>(i / HW);
+  const int px = static_cast<int>(i - static_cast<long long>(b) * HW);
+  __nv_bfloat16* o = dst + i * cpad;
+  int c = 0;
+  for (int s = 0; s < src.nsrc; ++s) {
+    const float* base = src.ptr[s] + (static_cast<long long>(b) * src.ch[s]) * HW + px;
+    for (int k = 0; k < src.ch[s]; ++k) o[c++] = __float2bfloat16_rn(__ldg(base + static_cast<long long>(k) * HW));
+  }
+  for (; c < cpad; ++c) o[c] = __float2bfloat16_rn(0.f);
+}
+
+// NHWC bf16 (ld) -> NCHW fp32, used to hand results back at the module boundary.
+__global__ void unpack_nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int ld,
+                                           float* __restrict__ dst, int B, int HW, int C) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * HW) return;
+  const int b = static_cast<int>(i / HW);
+  const int px = static_cast<int>(i - static_cast<long long>(b) * HW);
+  for (int c = 0; c < C; ++c)
+    dst[(static_cast<long long>(b) * C + c) * HW + px] = __bfloat162float(src[i * ld + c]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Max pooling, NHWC bf16, 8 channels (16 B) per thread. Reference: nn.MaxPool2d,
+// rovr/local_net.py:21,53-55; rovr/policy_net_1.py:29; rovr/policy_net_2.py:45-58.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void max8(uint4& a, const uint4& b) {
+  __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pa[j] = __hmax2(pa[j], pb[j]);
+}
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld,
+                                   __nv_bfloat16* __restrict__ y, int y_ld, int B, int H, int W,
+                                   int C, int kh, int kw, int sh, int sw_, int Ho, int Wo) {
+  const int c8 = C >> 3;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = static_cast<long long>(B) * Ho * Wo * c8;
+  if (i >= n) return;
+  const int cv = static_cast<int>(i % c8);
+  long long r = i / c8;
+  const int ox = static_cast<int>(r % Wo);
+  r /= Wo;
+  const int oy = static_cast<int>(r % Ho);
+  const int b = static_cast<int>(r / Ho);
+  const __nv_bfloat16* xb = x + ((static_cast<long long>(b) * H + oy * sh) * W + ox * sw_) * x_ld + cv * 8;
+  uint4 m = __ldg(reinterpret_cast<const uint4*>(xb));
+  for (int dy = 0; dy < kh; ++dy)
+    for (int dx = 0; dx < kw; ++dx) {
+      if (dy == 0 && dx == 0) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + (static_cast<long long>(dy) * W + dx) * x_ld));
+      max8(m, v);
+    }
+  *reinterpret_cast<uint4*>(y + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * y_ld + cv * 8) = m;
+}
+
+// Backward for non-overlapping windows (stride == kernel, H % kh == 0, W % kw == 0): one thread
+// owns one window x 8 channels, routes the pooled gradient to the first maximum in row-major scan
+// order (ATen's rule), adds the skip-connection gradient arriving at the same tensor, and applies
+// the ReLU mask of the pooled tensor (x > 0). This is the fused form of
+//   g_x = relu'(x) * (g_skip + maxpool_backward(g_pool))
+// that autograd evaluates for x1/x2/x3 of rovr/local_net.py:52-68.
+__global__ void maxpool_bwd_tiled_kernel(const __nv_bfloat16* __restrict__ x, int x_ld,
+                                         const __nv_bfloat16* __restrict__ gp, int gp_ld,
+                                         const __nv_bfloat16* __restrict__ gskip, int gs_ld,
+                                         __nv_bfloat16* __restrict__ gx, int gx_ld, int B, int H,
+                                         int W, int C, int kh, int kw, int relu_mask) {
+  const int c8 = C >> 3;
+  const int Ho = H / kh, Wo = W / kw;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = static_cast<long long>(B) * Ho * Wo * c8;
+  if (i >= n) return;
+  const int cv = static_cast<int>(i % c8);
+  long long r = i / c8;
+  const int ox = static_cast<int>(r % Wo);
+  r /= Wo;
+  const int oy = static_cast<int>(r % Ho);
+  const int b = static_cast<int>(r / Ho);
+  const long long pix0 = (static_cast<long long>(b) * H + oy * kh) * W + ox * kw;
+  const uint4 gv = __ldg(reinterpret_cast<const uint4*>(
+      gp + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * gp_ld + cv * 8));
+  const __nv_bfloat16* g8 = reinterpret_cast<const __nv_bfloat16*>(&gv);
+  float best[8];
+  int arg[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+  for (int dy = 0; dy < kh; ++dy)
+    for (int dx = 0; dx < kw; ++dx) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (pix0 + static_cast<long long>(dy) * W + dx) * x_ld + cv * 8));
+      const __nv_bfloat16* v8 = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float f = __bfloat162float(v8[j]);
+        if (f > best[j]) { best[j] = f; arg[j] = dy * kw + dx; }
+      }
+    }
+  for (int dy = 0; dy < kh; ++dy)
+    for (int dx = 0; dx < kw; ++dx) {
+      const long long pix = pix0 + static_cast<long long>(dy) * W + dx;
+      uint4 sk = make_uint4(0, 0, 0, 0);
+      if (gskip) sk = __ldg(reinterpret_cast<const uint4*>(gskip + pix * gs_ld + cv * 8));
+      const __nv_bfloat16* s8 = reinterpret_cast<const __nv_bfloat16*>(&sk);
+      // re-read this element's own value (L1 hit) for the ReLU mask
+      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + pix * x_ld + cv * 8));
+      const __nv_bfloat16* x8 = reinterpret_cast<const __nv_bfloat16*>(&xv);
+      uint4 o;
+      __nv_bfloat16* o8 = reinterpret_cast<__nv_bfloat16*>(&o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float g = __bfloat162float(s8[j]);
+        if (arg[j] == dy * kw + dx) g += __bfloat162float(g8[j]);
+        if (relu_mask && !(__bfloat162float(x8[j]) > 0.f)) g = 0.f;
+        o8[j] = __float2bfloat16_rn(g);
+      }
+      *reinterpret_cast<uint4*>(gx + pix * gx_ld + cv * 8) = o;
+    }
+}
+
+// Generic (possibly overlapping / ragged) backward: one thread per input element vector, gathers
+// from every window that contains it. Only used on the tiny 5x5 maps of PolicyNetwork2UNet.
+__global__ void maxpool_bwd_generic_kernel(const __nv_bfloat16* __restrict__ x, int x_ld,
+                                           const __nv_bfloat16* __restrict__ gp, int gp_ld,
+                                           __nv_bfloat16* __restrict__ gx, int gx_ld, int B, int H,
+                                           int W, int C, int kh, int kw, int sh, int sw_, int Ho,
+                                           int Wo, int relu_mask) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = static_cast<long long>(B) * H * W * C;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % C);
+  long long r = i / C;
+  const int xx = static_cast<int>(r % W);
+  r /= W;
+  const int yy = static_cast<int>(r % H);
+  const int b = static_cast<int>(r / H);
+  float g = 0.f;
+  for (int oy = 0; oy < Ho; ++oy) {
+    if (yy < oy * sh || yy >= oy * sh + kh) continue;
+    for (int ox = 0; ox < Wo; ++ox) {
+      if (xx < ox * sw_ || xx >= ox * sw_ + kw) continue;
+      float best = -INFINITY;
+      int ay = 0, ax = 0;
+      for (int dy = 0; dy < kh; ++dy)
+        for (int dx = 0; dx < kw; ++dx) {
+          const float f = __bfloat162float(
+              x[((static_cast<long long>(b) * H + oy * sh + dy) * W + ox * sw_ + dx) * x_ld + c]);
+          if (f > best) { best = f; ay = oy * sh + dy; ax = ox * sw_ + dx; }
+        }
+      if (ay == yy && ax == xx)
+        g += __bfloat162float(gp[((static_cast<long long>(b) * Ho + oy) * Wo + ox) * gp_ld + c]);
+    }
+  }
+  const long long pix = (static_cast<long long>(b) * H + yy) * W + xx;
+  if (relu_mask && !(__bfloat162float(x[pix * x_ld + c]) > 0.f)) g = 0.f;
+  gx[pix * gx_ld + c] = __float2bfloat16_rn(g);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LocalNet tail: conv8 (1x1, 64 -> 3) + sigmoid, output NCHW fp32; optional fused L2 loss.
+// Reference: rovr/local_net.py:39,71 and nn.MSELoss of rovr/train_local_net_unet.py:90,107.
+// One thread per pixel: 128 B of y7 in, 3 coalesced plane stores out.
+// ---------------------------------------------------------------------------------------------
+constexpr int TAIL_C = 64;
+__global__ void tail_fwd_kernel(const __nv_bfloat16* __restrict__ y7, const float* __restrict__ w8,
+                                const float* __restrict__ b8, float* __restrict__ out,
+                                const float* __restrict__ target, float* __restrict__ loss_partial,
+                                int B, int HW) {
+  __shared__ float sw[3 * TAIL_C + 3];
+  __shared__ float sred[32];
+  for (int i = threadIdx.x; i < 3 * TAIL_C + 3; i += blockDim.x)
+    sw[i] = i < 3 * TAIL_C ? w8[i] : b8[i - 3 * TAIL_C];
+  __syncthreads();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float se = 0.f;
+  if (i < static_cast<long long>(B) * HW) {
+    const int b = static_cast<int>(i / HW);
+    const int px = static_cast<int>(i - static_cast<long long>(b) * HW);
+    float a0 = sw[3 * TAIL_C], a1 = sw[3 * TAIL_C + 1], a2 = sw[3 * TAIL_C + 2];
+    const uint4* xp = reinterpret_cast<const uint4*>(y7 + i * TAIL_C);
+#pragma unroll
+    for (int v = 0; v < TAIL_C / 8; ++v) {
+      const uint4 q = __ldg(xp + v);
+      const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lo = bf16_lo(wds[j]), hi = bf16_hi(wds[j]);
+        const int c = v * 8 + 2 * j;
+        a0 = fmaf(lo, sw[c], a0);            a0 = fmaf(hi, sw[c + 1], a0);
+        a1 = fmaf(lo, sw[TAIL_C + c], a1);   a1 = fmaf(hi, sw[TAIL_C + c + 1], a1);
+        a2 = fmaf(lo, sw[2 * TAIL_C + c], a2); a2 = fmaf(hi, sw[2 * TAIL_C + c + 1], a2);
+      }
+    }
+    const float y0 = 1.f / (1.f + expf(-a0)), y1 = 1.f / (1.f + expf(-a1)), y2 = 1.f / (1.f + expf(-a2));
+    const long long o = static_cast<long long>(b) * 3 * HW + px;
+    out[o] = y0;
+    out[o + HW] = y1;
+    out[o + 2ll * HW] = y2;
+    if (target) {
+      const float d0 = y0 - target[o], d1 = y1 - target[o + HW], d2 = y2 - target[o + 2ll * HW];
+      se = d0 * d0 + d1 * d1 + d2 * d2;
+    }
+  }
+  if (loss_partial) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = se;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v = threadIdx.x < (blockDim.x >> 5) ? sred[threadIdx.x] : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (threadIdx.x == 0) loss_partial[blockIdx.x] = v;
+    }
+  }
+}
+
+// sum a vector of per-block partials in a fixed order -> out[0] = scale * sum
+__global__ void sum_partials_kernel(const float* __restrict__ partial, int n, float scale,
+                                    float* __restrict__ out) {
+  __shared__ float sred[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? sred[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) out[0] = v * scale;
+  }
+}
+
+// Tail backward. gz_k = g_k * y_k (1 - y_k) with g_k = gout_k (if given) + mse_scale * gloss *
+// (y_k - t_k) (if a fused L2 target is given; mse_scale = 2 / numel, gloss = dL/dloss on device); g7[c] = (sum_k w8[k][c] gz_k) * (y7[c] > 0);
+// dW8[k][c] = sum_p gz_k y7[c]; db8[k] = sum_p gz_k. Per-block partials [grid][3*64+3].
+constexpr int TAILB_THREADS = 256;
+constexpr int TAILB_PIX_PER_THREAD = 8;
+__global__ void __launch_bounds__(TAILB_THREADS)
+tail_bwd_kernel(const __nv_bfloat16* __restrict__ y7, const float* __restrict__ w8,
+                const float* __restrict__ yout, const float* __restrict__ gout,
+                const float* __restrict__ target, float mse_scale,
+                const float* __restrict__ gloss, __nv_bfloat16* __restrict__ g7,
+                float* __restrict__ partial, int B, int HW) {
+  __shared__ float sw[3 * TAIL_C];
+  __shared__ float sacc[3 * TAIL_C + 3];
+  for (int i = threadIdx.x; i < 3 * TAIL_C; i += blockDim.x) sw[i] = w8[i];
+  for (int i = threadIdx.x; i < 3 * TAIL_C + 3; i += blockDim.x) sacc[i] = 0.f;
+  const float lscale = mse_scale * (gloss ? __ldg(gloss) : 1.f);
+  __syncthreads();
+  // Each warp handles 32 consecutive pixels per iteration; lane l accumulates dW for channels
+  // (2l, 2l+1) of all three outputs over the warp's pixels via shuffles of gz.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long npix = static_cast<long long>(B) * HW;
+  const long long base = (static_cast<long long>(blockIdx.x) * (TAILB_THREADS / 32) + warp) * 32ll * TAILB_PIX_PER_THREAD;
+  float dw[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  float db[3] = {0.f, 0.f, 0.f};
+  for (int it = 0; it < TAILB_PIX_PER_THREAD; ++it) {
+    const long long i = base + static_cast<long long>(it) * 32 + lane;
+    float gz[3] = {0.f, 0.f, 0.f};
+    const bool ok = i < npix;
+    if (ok) {
+      const int b = static_cast<int>(i / HW);
+      const int px = static_cast<int>(i - static_cast<long long>(b) * HW);
+      const long long o = static_cast<long long>(b) * 3 * HW + px;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float y = yout[o + static_cast<long long>(k) * HW];
+        float g = 0.f;
+        if (gout) g = gout[o + static_cast<long long>(k) * HW];
+        if (target) g += lscale * (y - target[o + static_cast<long long>(k) * HW]);
+        gz[k] = g * y * (1.f - y);
+        db[k] += gz[k];
+      }
+      // own pixel: g7 row
+      const uint4* xp = reinterpret_cast<const uint4*>(y7 + i * TAIL_C);
+      uint4* gp = reinterpret_cast<uint4*>(g7 + i * TAIL_C);
+#pragma unroll
+      for (int v = 0; v < TAIL_C / 8; ++v) {
+        const uint4 q = __ldg(xp + v);
+        const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = v * 8 + 2 * j;
+          float lo = gz[0] * sw[c] + gz[1] * sw[TAIL_C + c] + gz[2] * sw[2 * TAIL_C + c];
+          float hi = gz[0] * sw[c + 1] + gz[1] * sw[TAIL_C + c + 1] + gz[2] * sw[2 * TAIL_C + c + 1];
+          if (!(bf16_lo(wds[j]) > 0.f)) lo = 0.f;
+          if (!(bf16_hi(wds[j]) > 0.f)) hi = 0.f;
+          ow[j] = pack_bf16x2(lo, hi);
+        }
+        gp[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+    }
+    // dW: for each of the 32 pixels of this warp iteration, lane l reads channels (2l,2l+1).
+    const long long wbase = base + static_cast<long long>(it) * 32;
+    for (int s = 0; s < 32; ++s) {
+      const float z0 = __shfl_sync(0xffffffffu, gz[0], s);
+      const float z1 = __shfl_sync(0xffffffffu, gz[1], s);
+      const float z2 = __shfl_sync(0xffffffffu, gz[2], s);
+      const long long pi = wbase + s;
+      if (pi < npix) {
+        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(y7 + pi * TAIL_C) + lane);
+        const float lo = bf16_lo(u), hi = bf16_hi(u);
+        dw[0][0] = fmaf(z0, lo, dw[0][0]); dw[0][1] = fmaf(z0, hi, dw[0][1]);
+        dw[1][0] = fmaf(z1, lo, dw[1][0]); dw[1][1] = fmaf(z1, hi, dw[1][1]);
+        dw[2][0] = fmaf(z2, lo, dw[2][0]); dw[2][1] = fmaf(z2, hi, dw[2][1]);
+      }
+    }
+  }
+  // block reduction in a fixed order: warps take turns adding into shared memory
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) db[k] += __shfl_xor_sync(0xffffffffu, db[k], o);
+  for (int w = 0; w < TAILB_THREADS / 32; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        sacc[k * TAIL_C + 2 * lane] += dw[k][0];
+        sacc[k * TAIL_C + 2 * lane + 1] += dw[k][1];
+        if (lane == 0) sacc[3 * TAIL_C + k] += db[k];
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < 3 * TAIL_C + 3; i += blockDim.x)
+    partial[static_cast<long long>(blockIdx.x) * (3 * TAIL_C + 3) + i] = sacc[i];
+}
+
+// out[j] = sum_{r < nrows} partial[r][j]   (fixed order), optional accumulate into out
+__global__ void reduce_rows_kernel(const float* __restrict__ partial, int nrows, int row_stride,
+                                   int ncols, float* __restrict__ out, int accumulate) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ncols) return;
+  float s = 0.f;
+  for (int r = 0; r < nrows; ++r) s += partial[static_cast<long long>(r) * row_stride + j];
+  out[j] = accumulate ? out[j] + s : s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Column sums of an NHWC bf16 tensor (bias gradients): stage 1 writes [grid][C] partials.
+// blockDim = 256: thread t owns channel pair (t % (C/2)) of pixel lane (t / (C/2)).
+// ---------------------------------------------------------------------------------------------
+__global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ g, int ld, long long npix,
+                                      int C, float* __restrict__ partial) {
+  extern __shared__ float ssum[];  // [blockDim.x * 2]
+  const int c2 = C >> 1;
+  const int pl = threadIdx.x / c2;          // pixel lane
+  const int cp = threadIdx.x - pl * c2;     // channel pair
+  const int plane = blockDim.x / c2;        // pixel lanes per block
+  float s0 = 0.f, s1 = 0.f;
+  if (pl < plane) {
+    for (long long px = static_cast<long long>(blockIdx.x) * plane + pl; px < npix;
+         px += static_cast<long long>(gridDim.x) * plane) {
+      const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(g + px * ld) + cp);
+      s0 += bf16_lo(u);
+      s1 += bf16_hi(u);
+    }
+  }
+  ssum[2 * threadIdx.x] = s0;
+  ssum[2 * threadIdx.x + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < c2) {
+    float a = 0.f, b = 0.f;
+    for (int l = 0; l < plane; ++l) {
+      a += ssum[2 * (l * c2 + threadIdx.x)];
+      b += ssum[2 * (l * c2 + threadIdx.x) + 1];
+    }
+    partial[static_cast<long long>(blockIdx.x) * C + 2 * threadIdx.x] = a;
+    partial[static_cast<long long>(blockIdx.x) * C + 2 * threadIdx.x + 1] = b;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight repack: dst[i0][i1][i2] (bf16, dense) = src[i0*s0 + i1*s1 + i2*s2] (fp32) for i2 < v2,
+// i0 < v0, else 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void repack_weights_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                      int d0, int d1, int d2, long long s0, long long s1,
+                                      long long s2, int v0, int v2) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = static_cast<long long>(d0) * d1 * d2;
+  if (i >= n) return;
+  const int i2 = static_cast<int>(i % d2);
+  const int i1 = static_cast<int>((i / d2) % d1);
+  const int i0 = static_cast<int>(i / (static_cast<long long>(d1) * d2));
+  float v = 0.f;
+  if (i2 < v2 && i0 < v0) v = src[i0 * s0 + i1 * s1 + i2 * s2];
+  dst[i] = __float2bfloat16_rn(v);
+}
+
+}  // namespace rovr

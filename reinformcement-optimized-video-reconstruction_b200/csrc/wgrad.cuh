@@ -1,0 +1,239 @@
+// wgrad.cuh — weight-gradient contractions on tcgen05 with MN-major operands.
+//
+//     P[slice][m][t][c] = sum_{pixels p in slice}  A[p][m] * B_t[p][c]
+//
+// A is the un-shifted NHWC bf16 tensor (dy for Conv2d 3x3, x for ConvTranspose2d), B_t the other
+// tensor read at tap offset t (x shifted by the 3x3 tap / dy at the 2x2 sub-pixel). The reduction
+// index is the pixel, which in NHWC is the *strided* dimension, so both operands are fed to the
+// tensor core as MN-major tiles: a TMA box of [kp pixels][blk channels] lands in shared memory as
+// kp rows of `sw` bytes and is described to tcgen05.mma with the MN-major flag — no transposed
+// copy of any activation is ever written to HBM.
+//
+// Work split: a CTA owns one accumulator group (128 rows of m, a tap group, a channel chunk of
+// c — at most 512 TMEM columns) and a contiguous slice of pixel tiles (split-K). Partial sums go
+// to an fp32 workspace and are combined in a fixed order by wgrad_reduce_kernel, so the gradient
+// is bitwise reproducible run to run.
+//
+// Reference semantics: autograd of nn.Conv2d / nn.ConvTranspose2d weights,
+// rovr/local_net.py:12-39 (layers) as driven by rovr/train_local_net_unet.py:115 (backward()).
+#pragma once
+#include "ptx.cuh"
+
+namespace rovr {
+
+constexpr int WG_MAX_STAGES = 6;
+constexpr int WG_THREADS = 192;
+
+struct WgradParams {
+  int boxM[4];   // pixel tile extents (rows per K-step kp = prod, multiple of 16, <= 128)
+  int ntile[4];  // pixel tiles per dim
+  int kp;        // rows reserved per block (>= prod(boxM), multiple of 16)
+  int blk;       // channels per block = sw/2 (16/32/64)
+  int a_blocks;  // A blocks loaded per group (M = 128 rows reserved)
+  int m_chunks;  // number of 128-row chunks of m
+  int m_total;   // valid m
+  int taps_total;          // T
+  int taps_per_group;      // taps handled by one CTA
+  int tap_groups;
+  int tap_off[9][4];
+  int c_total;             // valid c (multiple of blk)
+  int c_blocks_per_group;  // B channel blocks per tap in one CTA
+  int c_groups;
+  int n_slices;
+  int k_tiles;             // total pixel tiles
+  int stages;
+  int tmem_cols;
+  float* partial;          // [n_slices][m_total][taps_total][c_total]
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int sw = p.blk * 2;
+  const uint32_t blk_bytes = static_cast<uint32_t>(p.kp) * sw;
+  const int m_blocks = 128 / p.blk;  // blocks reserved for A so that M = 128 is addressable
+  const int nblk = p.taps_per_group * p.c_blocks_per_group;
+  const uint32_t a_bytes = static_cast<uint32_t>(m_blocks) * blk_bytes;
+  const uint32_t stage_bytes = a_bytes + static_cast<uint32_t>(nblk) * blk_bytes;
+  const int rows = p.boxM[0] * p.boxM[1] * p.boxM[2] * p.boxM[3];
+  const uint32_t tx_bytes = static_cast<uint32_t>(p.a_blocks + nblk) * rows * sw;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  uint64_t* empty_bar = full_bar + WG_MAX_STAGES;
+  uint64_t* done_bar = empty_bar + WG_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  // group / slice decode
+  int g = blockIdx.x;
+  const int slice = g % p.n_slices;
+  g /= p.n_slices;
+  const int cg = g % p.c_groups;
+  g /= p.c_groups;
+  const int tg = g % p.tap_groups;
+  g /= p.tap_groups;
+  const int mc = g;  // m chunk
+  const int kt0 = static_cast<int>((static_cast<long long>(p.k_tiles) * slice) / p.n_slices);
+  const int kt1 = static_cast<int>((static_cast<long long>(p.k_tiles) * (slice + 1)) / p.n_slices);
+  const int t_first = tg * p.taps_per_group;
+  const int n_cols = nblk * p.blk;
+
+  // Rows of a block that TMA never writes (kp > rows) and A blocks that are never loaded must
+  // read as zero / be harmless: zero the whole staging area once.
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = static_cast<int>((static_cast<size_t>(p.stages) * stage_bytes) >> 4);
+    for (int i = threadIdx.x; i < n16; i += WG_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kt = kt0; kt < kt1; ++kt) {
+        int org[4];
+        int r = kt;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          org[j] = (r % p.ntile[j]) * p.boxM[j];
+          r /= p.ntile[j];
+        }
+        mbar_wait(&empty_bar[s], ph ^ 1u, 0x500u + s);
+        uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
+        mbar_expect_tx(&full_bar[s], tx_bytes);
+        for (int i = 0; i < p.a_blocks; ++i)
+          tma_load_5d(&tmA, &full_bar[s], st + static_cast<size_t>(i) * blk_bytes,
+                      mc * 128 + i * p.blk, org[0], org[1], org[2], org[3]);
+        for (int tl = 0; tl < p.taps_per_group; ++tl) {
+          const int t = t_first + tl;
+          for (int j = 0; j < p.c_blocks_per_group; ++j) {
+            const int c0 = (cg * p.c_blocks_per_group + j) * p.blk;
+            tma_load_5d(&tmB, &full_bar[s],
+                        st + a_bytes + static_cast<size_t>(tl * p.c_blocks_per_group + j) * blk_bytes,
+                        c0, org[0] + p.tap_off[t][0], org[1] + p.tap_off[t][1],
+                        org[2] + p.tap_off[t][2], org[3] + p.tap_off[t][3]);
+          }
+        }
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t sbo = 8u * sw;
+      const int blocks_per_mma = 256 / p.blk < nblk ? 256 / p.blk : nblk;
+      int s = 0;
+      uint32_t ph = 0;
+      bool first = true;
+      for (int kt = kt0; kt < kt1; ++kt) {
+        mbar_wait(&full_bar[s], ph, 0x600u + s);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+        const uint32_t b_addr = a_addr + a_bytes;
+        const int ksteps = p.kp >> 4;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint32_t koff = static_cast<uint32_t>(k) * 16u * sw;
+          const uint64_t ad = umma_smem_desc(a_addr + koff, blk_bytes, sbo, sw);
+          for (int b0 = 0; b0 < nblk; b0 += blocks_per_mma) {
+            const int nb = (nblk - b0) < blocks_per_mma ? (nblk - b0) : blocks_per_mma;
+            const uint32_t idesc = umma_idesc_bf16(128, nb * p.blk, 1, 1);
+            const uint64_t bd = umma_smem_desc(b_addr + static_cast<uint32_t>(b0) * blk_bytes + koff,
+                                               blk_bytes, sbo, sw);
+            umma_bf16(tmem_base + static_cast<uint32_t>(b0 * p.blk), ad, bd, idesc,
+                      (first && k == 0) ? 0u : 1u);
+          }
+        }
+        first = false;
+        umma_commit(&empty_bar[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int m_local = quarter * 32 + lane;
+    const int m = mc * 128 + m_local;
+    const bool have_work = kt1 > kt0;
+    if (have_work) {
+      mbar_wait(done_bar, 0u, 0x700u);
+      tc_fence_after();
+    }
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    for (int c = 0; c < (n_cols >> 4); ++c) {
+      uint32_t v[16];
+      if (have_work) {
+        tmem_ld16(t_row + static_cast<uint32_t>(c * 16), v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+      const int col = c * 16;
+      const int b = col / p.blk;                 // block within the group
+      const int tl = b / p.c_blocks_per_group;   // local tap
+      const int cj = b - tl * p.c_blocks_per_group;
+      const int cc = (cg * p.c_blocks_per_group + cj) * p.blk + (col - b * p.blk);
+      const int t = t_first + tl;
+      if (m < p.m_total && cc < p.c_total && t < p.taps_total) {
+        float4* dst = reinterpret_cast<float4*>(
+            p.partial +
+            ((static_cast<size_t>(slice) * p.m_total + m) * p.taps_total + t) * p.c_total + cc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+// final[m*fs_m + t*fs_t + c*fs_c] = sum_slices P[slice][m][t][c], c < c_keep.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad,
+                                    int n_slices, int m_total, int taps, int c_total, int c_keep,
+                                    long long fs_m, long long fs_t, long long fs_c, int accumulate) {
+  const long long n = static_cast<long long>(m_total) * taps * c_total;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % c_total);
+  const int t = static_cast<int>((i / c_total) % taps);
+  const int m = static_cast<int>(i / (static_cast<long long>(c_total) * taps));
+  if (c >= c_keep) return;
+  float s = 0.f;
+  for (int k = 0; k < n_slices; ++k) s += partial[static_cast<long long>(k) * n + i];
+  float* dst = grad + m * fs_m + t * fs_t + c * fs_c;
+  *dst = accumulate ? (*dst + s) : s;
+}
+
+inline size_t wgrad_smem_bytes(int blk, int kp, int nblk, int stages) {
+  const size_t sw = static_cast<size_t>(blk) * 2;
+  const size_t blk_bytes = static_cast<size_t>(kp) * sw;
+  const size_t stage = (128 / blk + nblk) * blk_bytes;
+  return 1024 + stages * stage + (2 * WG_MAX_STAGES + 1) * 8 + 16 + 64;
+}
+
+}  // namespace rovr

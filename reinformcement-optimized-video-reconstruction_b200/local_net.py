@@ -1,0 +1,287 @@
+"""Drop-in for the reference `local_net` module: `LocalNetworkUNetNorm(freeze=False)`.
+
+Same class name, constructor argument, `forward(x, context)` signature, parameter order and
+72-key `state_dict` as rovr/local_net.py:7-72 (including the ten BatchNorm2d that the reference
+constructs but never calls — rovr/local_net.py:13-37 vs :52-68 — so checkpoints load unchanged),
+but the arithmetic runs in hand-written sm_100a kernels through librovr_b200.so:
+
+    pack(x, context) -> NHWC bf16, 16 ch          (replaces cat + rearrange, :48-49)
+    conv1..conv4 (+ReLU), 2x2 max-pool             tcgen05 implicit GEMM, pool kernel
+    upconv1..3 (+ReLU)                             GEMM + pixel-shuffle store into the concat slice
+    conv5..conv7 (+ReLU) on [up, skip] buffers     the torch.cat of :59,63,67 never materialises
+    conv8 1x1 + sigmoid (+ optional fused L2)      fused tail kernel
+
+and the backward pass (dgrad / wgrad on tensor cores, bias grads, pool scatter fused with the
+skip-gradient add and ReLU mask) is one autograd.Function. Inputs / outputs at the module
+boundary stay NCHW fp32 like the reference; internals are NHWC bf16 with fp32 accumulation and
+fp32 master weights. There is no fallback path: a CPU tensor or a non-sm_100 device raises.
+"""
+import torch
+import torch.nn as nn
+
+import ops
+
+# (name, kind, cin, cout) in the reference's registration order (rovr/local_net.py:12-39)
+_LAYERS = [
+    ("conv1", "conv", 9, 64), ("bn1", "bn", 64, 64),
+    ("conv2", "conv", 64, 128), ("bn2", "bn", 128, 128),
+    ("conv3", "conv", 128, 256), ("bn3", "bn", 256, 256),
+    ("conv4", "conv", 256, 512), ("bn4", "bn", 512, 512),
+    ("upconv1", "up", 512, 256), ("bn_up1", "bn", 256, 256),
+    ("conv5", "conv", 512, 256), ("bn5", "bn", 256, 256),
+    ("upconv2", "up", 256, 128), ("bn_up2", "bn", 128, 128),
+    ("conv6", "conv", 256, 128), ("bn6", "bn", 128, 128),
+    ("upconv3", "up", 128, 64), ("bn_up3", "bn", 64, 64),
+    ("conv7", "conv", 128, 64), ("bn7", "bn", 64, 64),
+]
+
+# parameters that take part in forward, in backward-completion order (decoder first): the order
+# in which their gradients become final, used for bucketed all-reduce overlap.
+_GRAD_ORDER = ["conv8", "conv7", "upconv3", "conv6", "upconv2", "conv5", "upconv1",
+               "conv4", "conv3", "conv2", "conv1"]
+_DECODER = _GRAD_ORDER[:7]
+_ENCODER = _GRAD_ORDER[7:]
+
+
+class _PackedWeights:
+    """bf16 GEMM-operand copies of the fp32 master weights, refreshed when a parameter changes."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def get(self, name, param, kind, for_dgrad):
+        key = (name, for_dgrad)
+        ver = (param.data_ptr(), param._version)
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        w = param.detach()
+        wk = ops.repack_convT2x2(w, for_dgrad) if kind == "up" else ops.repack_conv3x3(w, for_dgrad)
+        self._cache[key] = (ver, wk)
+        return wk
+
+
+def _flat_bucket(params, names, device):
+    """One flat fp32 buffer holding weight+bias grads of `names`; returns (flat, {pname: view})."""
+    total = sum(params[n + ".weight"].numel() + params[n + ".bias"].numel() for n in names)
+    flat = torch.empty(total, dtype=torch.float32, device=device)
+    views, off = {}, 0
+    for n in names:
+        for suffix in (".weight", ".bias"):
+            p = params[n + suffix]
+            views[n + suffix] = flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+    return flat, views
+
+
+class _LocalNetFunction(torch.autograd.Function):
+    """forward: (x, context, target_or_None, *live_params) -> (y_hat, loss_or_zero)."""
+
+    @staticmethod
+    def forward(ctx, net, x, context, target, *plist):
+        P = dict(zip(net._live_names, plist))
+        dev = x.device
+        B, _, H, W = x.shape
+        bf = torch.bfloat16
+        pk = net._packed
+
+        def wk(name, kind="conv"):
+            return pk.get(name, P[name + ".weight"], kind, False)
+
+        a = {}
+        a["in16"] = ops.pack_nchw([x, context.reshape(B, 6, H, W)], 16)
+        a["cat7"] = torch.empty((B, H, W, 128), dtype=bf, device=dev)
+        a["cat6"] = torch.empty((B, H // 2, W // 2, 256), dtype=bf, device=dev)
+        a["cat5"] = torch.empty((B, H // 4, W // 4, 512), dtype=bf, device=dev)
+        x1, x2, x3 = a["cat7"][..., 64:], a["cat6"][..., 128:], a["cat5"][..., 256:]
+        ops.conv3x3_fprop(a["in16"], wk("conv1"), P["conv1.bias"], x1)
+        a["p1"] = torch.empty((B, H // 2, W // 2, 64), dtype=bf, device=dev)
+        ops.maxpool_fwd(x1, a["p1"], 2)
+        ops.conv3x3_fprop(a["p1"], wk("conv2"), P["conv2.bias"], x2)
+        a["p2"] = torch.empty((B, H // 4, W // 4, 128), dtype=bf, device=dev)
+        ops.maxpool_fwd(x2, a["p2"], 2)
+        ops.conv3x3_fprop(a["p2"], wk("conv3"), P["conv3.bias"], x3)
+        a["p3"] = torch.empty((B, H // 8, W // 8, 256), dtype=bf, device=dev)
+        ops.maxpool_fwd(x3, a["p3"], 2)
+        a["x4"] = torch.empty((B, H // 8, W // 8, 512), dtype=bf, device=dev)
+        ops.conv3x3_fprop(a["p3"], wk("conv4"), P["conv4.bias"], a["x4"])
+
+        ops.convT2x2_fprop(a["x4"], wk("upconv1", "up"), P["upconv1.bias"], a["cat5"][..., :256])
+        a["y5"] = torch.empty((B, H // 4, W // 4, 256), dtype=bf, device=dev)
+        ops.conv3x3_fprop(a["cat5"], wk("conv5"), P["conv5.bias"], a["y5"])
+        ops.convT2x2_fprop(a["y5"], wk("upconv2", "up"), P["upconv2.bias"], a["cat6"][..., :128])
+        a["y6"] = torch.empty((B, H // 2, W // 2, 128), dtype=bf, device=dev)
+        ops.conv3x3_fprop(a["cat6"], wk("conv6"), P["conv6.bias"], a["y6"])
+        ops.convT2x2_fprop(a["y6"], wk("upconv3", "up"), P["upconv3.bias"], a["cat7"][..., :64])
+        a["y7"] = torch.empty((B, H, W, 64), dtype=bf, device=dev)
+        ops.conv3x3_fprop(a["cat7"], wk("conv7"), P["conv7.bias"], a["y7"])
+
+        out, loss = ops.tail_fwd(a["y7"], P["conv8.weight"], P["conv8.bias"], target)
+        a["out"] = out
+        ctx.net = net
+        ctx.acts = a
+        ctx.params = P
+        ctx.target = target
+        ctx.set_materialize_grads(False)
+        if loss is None:
+            loss = out.new_zeros(())
+            ctx.mark_non_differentiable(loss)
+        return out, loss
+
+    @staticmethod
+    def backward(ctx, g_out, g_loss):
+        net, a, P, target = ctx.net, ctx.acts, ctx.params, ctx.target
+        dev = a["out"].device
+        bf = torch.bfloat16
+        pk = net._packed
+        if g_out is None and (g_loss is None or target is None):
+            return (None,) * (4 + len(net._live_names))
+        if g_out is not None:
+            g_out = g_out.contiguous()
+        B, H, W, _ = a["y7"].shape
+
+        def wd(name, kind="conv"):
+            return pk.get(name, P[name + ".weight"], kind, True)
+
+        dec_flat, G = _flat_bucket(P, _DECODER, dev)
+        enc_flat, Ge = _flat_bucket(P, _ENCODER, dev)
+        G.update(Ge)
+
+        def el(t):
+            return torch.empty_like(t)
+
+        # ---- tail: conv8 + sigmoid (+L2) ----
+        g7 = el(a["y7"])
+        use_loss = target is not None and g_loss is not None
+        ops.tail_bwd(a["y7"], P["conv8.weight"], a["out"], g7, G["conv8.weight"], G["conv8.bias"],
+                     gout=g_out, target=target if use_loss else None,
+                     mse_scale=2.0 / a["out"].numel(),
+                     gloss=g_loss.contiguous() if use_loss else None)
+        # ---- conv7 ----
+        ops.conv3x3_wgrad(g7, a["cat7"], G["conv7.weight"])
+        ops.colsum(g7, G["conv7.bias"])
+        gcat7 = el(a["cat7"])
+        ops.conv3x3_dgrad(g7, wd("conv7"), gcat7, mask=a["cat7"])
+        # ---- upconv3 ----
+        gu3 = gcat7[..., :64]
+        ops.convT2x2_wgrad(gu3, a["y6"], G["upconv3.weight"])
+        ops.colsum(gu3, G["upconv3.bias"])
+        g6 = el(a["y6"])
+        ops.convT2x2_dgrad(gu3, wd("upconv3", "up"), g6, mask=a["y6"])
+        # ---- conv6 ----
+        ops.conv3x3_wgrad(g6, a["cat6"], G["conv6.weight"])
+        ops.colsum(g6, G["conv6.bias"])
+        gcat6 = el(a["cat6"])
+        ops.conv3x3_dgrad(g6, wd("conv6"), gcat6, mask=a["cat6"])
+        # ---- upconv2 ----
+        gu2 = gcat6[..., :128]
+        ops.convT2x2_wgrad(gu2, a["y5"], G["upconv2.weight"])
+        ops.colsum(gu2, G["upconv2.bias"])
+        g5 = el(a["y5"])
+        ops.convT2x2_dgrad(gu2, wd("upconv2", "up"), g5, mask=a["y5"])
+        # ---- conv5 ----
+        ops.conv3x3_wgrad(g5, a["cat5"], G["conv5.weight"])
+        ops.colsum(g5, G["conv5.bias"])
+        gcat5 = el(a["cat5"])
+        ops.conv3x3_dgrad(g5, wd("conv5"), gcat5, mask=a["cat5"])
+        # ---- upconv1 ----
+        gu1 = gcat5[..., :256]
+        ops.convT2x2_wgrad(gu1, a["x4"], G["upconv1.weight"])
+        ops.colsum(gu1, G["upconv1.bias"])
+        g4 = el(a["x4"])
+        ops.convT2x2_dgrad(gu1, wd("upconv1", "up"), g4, mask=a["x4"])
+        net._bucket_ready(0, dec_flat)
+        # ---- conv4 ----
+        ops.conv3x3_wgrad(g4, a["p3"], G["conv4.weight"])
+        ops.colsum(g4, G["conv4.bias"])
+        gp3 = el(a["p3"])
+        ops.conv3x3_dgrad(g4, wd("conv4"), gp3)
+        g3 = torch.empty((B, H // 4, W // 4, 256), dtype=bf, device=dev)
+        ops.maxpool_bwd(a["cat5"][..., 256:], gp3, g3, 2, gskip=gcat5[..., 256:], relu_mask=True)
+        # ---- conv3 ----
+        ops.conv3x3_wgrad(g3, a["p2"], G["conv3.weight"])
+        ops.colsum(g3, G["conv3.bias"])
+        gp2 = el(a["p2"])
+        ops.conv3x3_dgrad(g3, wd("conv3"), gp2)
+        g2 = torch.empty((B, H // 2, W // 2, 128), dtype=bf, device=dev)
+        ops.maxpool_bwd(a["cat6"][..., 128:], gp2, g2, 2, gskip=gcat6[..., 128:], relu_mask=True)
+        # ---- conv2 ----
+        ops.conv3x3_wgrad(g2, a["p1"], G["conv2.weight"])
+        ops.colsum(g2, G["conv2.bias"])
+        gp1 = el(a["p1"])
+        ops.conv3x3_dgrad(g2, wd("conv2"), gp1)
+        g1 = torch.empty((B, H, W, 64), dtype=bf, device=dev)
+        ops.maxpool_bwd(a["cat7"][..., 64:], gp1, g1, 2, gskip=gcat7[..., 64:], relu_mask=True)
+        # ---- conv1 (input needs no gradient: no dgrad, as in the reference's autograd graph) ----
+        ops.conv3x3_wgrad(g1, a["in16"], G["conv1.weight"])
+        ops.colsum(g1, G["conv1.bias"])
+        net._bucket_ready(1, enc_flat)
+        net._buckets_wait()
+
+        ctx.acts = None
+        grads = tuple(G[n] if P[n].requires_grad else None for n in net._live_names)
+        return (None, None, None, None) + grads
+
+
+class LocalNetworkUNetNorm(nn.Module):
+    """U-Net inpainting network; see the module docstring. Reference: rovr/local_net.py:7-72."""
+
+    def __init__(self, freeze=False):
+        super().__init__()
+        for name, kind, cin, cout in _LAYERS:
+            if kind == "conv":
+                layer = nn.Conv2d(cin, cout, kernel_size=3, padding=1)
+            elif kind == "up":
+                layer = nn.ConvTranspose2d(cin, cout, kernel_size=2, stride=2)
+            else:
+                layer = nn.BatchNorm2d(cout)  # registered for state_dict parity; never applied
+            setattr(self, name, layer)
+        self.conv8 = nn.Conv2d(64, 3, kernel_size=1)
+        self.maxpool = nn.MaxPool2d(kernel_size=2, stride=2)  # attribute kept for API parity
+        if freeze:
+            for param in self.parameters():
+                param.requires_grad = False
+        self._live_names = [n + s for n in
+                            ["conv1", "conv2", "conv3", "conv4", "upconv1", "conv5", "upconv2",
+                             "conv6", "upconv3", "conv7", "conv8"] for s in (".weight", ".bias")]
+        self._packed = _PackedWeights()
+        self._grad_bucket_hook = None  # set by data_parallel.GradientBuckets
+        self._grad_bucket_wait = None
+
+    # -- data-parallel hook points ---------------------------------------------------------------
+    def _bucket_ready(self, index, flat):
+        if self._grad_bucket_hook is not None:
+            self._grad_bucket_hook(index, flat)
+
+    def _buckets_wait(self):
+        if self._grad_bucket_wait is not None:
+            self._grad_bucket_wait()
+
+    # -- execution -------------------------------------------------------------------------------
+    def _live_params(self):
+        sd = dict(self.named_parameters())
+        return [sd[n] for n in self._live_names]
+
+    def _run(self, x, context, target):
+        if not x.is_cuda:
+            raise RuntimeError("LocalNetworkUNetNorm (B200) needs CUDA tensors: there is no CPU path")
+        B, C, H, W = x.shape
+        if C != 3 or context.shape != (B, 2, 3, H, W):
+            raise ValueError(f"expected x [b,3,h,w] and context [b,2,3,h,w], got {tuple(x.shape)} "
+                             f"{tuple(context.shape)}")
+        if H % 8 or W % 8:
+            raise ValueError("H and W must be multiples of 8 (three 2x2 poolings)")
+        x = x.float().contiguous()
+        context = context.float().contiguous()
+        if target is not None:
+            target = target.float().contiguous()
+        return _LocalNetFunction.apply(self, x, context, target, *self._live_params())
+
+    def forward(self, x, context):
+        out, _ = self._run(x, context, None)
+        return out
+
+    def forward_with_mse(self, x, context, target):
+        """(y_hat, mean((y_hat - target)^2)) with the loss and its gradient fused into the tail
+        kernel: the `mse_loss_fn(y_hat, target)` of rovr/train_local_net_unet.py:107."""
+        return self._run(x, context, target)

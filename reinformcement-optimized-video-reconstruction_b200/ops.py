@@ -1,0 +1,301 @@
+"""Tensor-level wrappers over the C ABI (include/rovr_b200.h).
+
+Every function takes torch CUDA tensors, checks layout, and launches on torch's current stream.
+Activations are NHWC bf16 views ([B, H, W, C] with unit channel stride, possibly a channel slice
+of a wider buffer); parameters / gradients are fp32 in the reference's PyTorch layouts.
+PyTorch is used for memory and streams only — no torch operator computes anything here.
+"""
+import ctypes
+
+import torch
+
+import _native as N
+
+_vp = ctypes.c_void_p
+
+
+def _ptr(t):
+    return _vp(t.data_ptr()) if t is not None else _vp(0)
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _act(t, name="activation"):
+    """Validate an NHWC bf16 view and return (B, H, W, C, ld)."""
+    if t.dtype != torch.bfloat16 or not t.is_cuda or t.dim() != 4:
+        raise ValueError(f"{name}: expected a 4-D CUDA bf16 NHWC tensor, got {t.dtype} {tuple(t.shape)}")
+    B, H, W, C = t.shape
+    ld = t.stride(2)
+    if t.stride(3) != 1 or t.stride(1) != W * ld or (B > 1 and t.stride(0) != H * W * ld):
+        raise ValueError(f"{name}: not a dense-pixel NHWC view, strides={t.stride()}")
+    return B, H, W, C, ld
+
+
+def _f32(t, name):
+    if t is None:
+        return
+    if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous CUDA fp32 tensor")
+
+
+# ---------------------------------------------------------------------------------------------
+# shared scratch workspace (one per device; ops on one stream run in order so it can be reused)
+# ---------------------------------------------------------------------------------------------
+_WS = {}
+
+
+def workspace(nbytes, device):
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+# ---------------------------------------------------------------------------------------------
+# packing
+# ---------------------------------------------------------------------------------------------
+def pack_nchw(srcs, cpad, out=None):
+    """cat(srcs, dim=1) -> NHWC bf16 with channels zero-padded to cpad. srcs: fp32 [B, c_i, H, W]."""
+    srcs = [s.contiguous() for s in srcs]
+    for s in srcs:
+        _f32(s, "pack source")
+    B, _, H, W = srcs[0].shape
+    if out is None:
+        out = torch.empty((B, H, W, cpad), dtype=torch.bfloat16, device=srcs[0].device)
+    args = []
+    for i in range(3):
+        if i < len(srcs):
+            args += [_ptr(srcs[i]), srcs[i].shape[1]]
+        else:
+            args += [_vp(0), 0]
+    N.call("rovr_pack_nchw_to_nhwc", *args, _ptr(out), B, H, W, cpad, _stream())
+    return out
+
+
+def unpack_nhwc(x, C=None):
+    B, H, W, Cx, ld = _act(x)
+    C = Cx if C is None else C
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    N.call("rovr_unpack_nhwc_to_nchw", _ptr(x), ld, _ptr(out), B, H, W, C, _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# weight repacking
+# ---------------------------------------------------------------------------------------------
+def pad16(c):
+    return (c + 15) // 16 * 16
+
+
+def repack_conv3x3(w, for_dgrad=False):
+    _f32(w, "conv weight")
+    Cout, Cin = w.shape[0], w.shape[1]
+    cin_pad = pad16(Cin)
+    if for_dgrad:
+        wk = torch.empty((cin_pad, 9 * Cout), dtype=torch.bfloat16, device=w.device)
+        N.call("rovr_repack_conv3x3_dgrad", _ptr(w), _ptr(wk), Cout, Cin, cin_pad, _stream())
+    else:
+        wk = torch.empty((Cout, 9 * cin_pad), dtype=torch.bfloat16, device=w.device)
+        N.call("rovr_repack_conv3x3_fprop", _ptr(w), _ptr(wk), Cout, Cin, cin_pad, _stream())
+    return wk
+
+
+def repack_convT2x2(w, for_dgrad=False):
+    _f32(w, "convT weight")
+    Cin, Cout = w.shape[0], w.shape[1]
+    if for_dgrad:
+        wk = torch.empty((Cin, 4 * Cout), dtype=torch.bfloat16, device=w.device)
+        N.call("rovr_repack_convT2x2_dgrad", _ptr(w), _ptr(wk), Cin, Cout, _stream())
+    else:
+        wk = torch.empty((4 * Cout, Cin), dtype=torch.bfloat16, device=w.device)
+        N.call("rovr_repack_convT2x2_fprop", _ptr(w), _ptr(wk), Cin, Cout, _stream())
+    return wk
+
+
+# ---------------------------------------------------------------------------------------------
+# Conv2d 3x3
+# ---------------------------------------------------------------------------------------------
+def conv3x3_fprop(x, wk, bias, y, relu=True):
+    B, H, W, Cin, x_ld = _act(x, "x")
+    By, Hy, Wy, Cout, y_ld = _act(y, "y")
+    assert (B, H, W) == (By, Hy, Wy) and wk.shape == (Cout, 9 * Cin), (x.shape, y.shape, wk.shape)
+    _f32(bias, "bias")
+    N.call("rovr_conv3x3_fprop", _ptr(x), x_ld, _ptr(wk), _ptr(bias), _ptr(y), y_ld, B, H, W, Cin,
+           Cout, int(relu), _stream())
+    return y
+
+
+def conv3x3_dgrad(dy, wk_d, dx, mask=None):
+    B, H, W, Cout, dy_ld = _act(dy, "dy")
+    Bx, Hx, Wx, Cin, dx_ld = _act(dx, "dx")
+    assert (B, H, W) == (Bx, Hx, Wx) and wk_d.shape == (Cin, 9 * Cout), (dy.shape, dx.shape, wk_d.shape)
+    mask_ld = 0
+    if mask is not None:
+        Bm, Hm, Wm, Cm, mask_ld = _act(mask, "mask")
+        assert (Bm, Hm, Wm, Cm) == (B, H, W, Cin)
+    N.call("rovr_conv3x3_dgrad", _ptr(dy), dy_ld, _ptr(wk_d), _ptr(dx), dx_ld, _ptr(mask), mask_ld,
+           B, H, W, Cin, Cout, _stream())
+    return dx
+
+
+def conv3x3_wgrad(dy, x, dw):
+    B, H, W, Cout, dy_ld = _act(dy, "dy")
+    Bx, Hx, Wx, Cin, x_ld = _act(x, "x")
+    assert (B, H, W) == (Bx, Hx, Wx)
+    _f32(dw, "dw")
+    cin_keep = dw.shape[1]
+    assert dw.shape == (Cout, cin_keep, 3, 3) and cin_keep <= Cin
+    need = N.lib.rovr_conv3x3_wgrad_workspace(B, H, W, Cin, Cout)
+    if need == 0:
+        raise N.RovrError("conv3x3_wgrad_workspace: " + N.last_error())
+    ws = workspace(need, dy.device)
+    N.call("rovr_conv3x3_wgrad", _ptr(dy), dy_ld, _ptr(x), x_ld, _ptr(dw), B, H, W, Cin, cin_keep,
+           Cout, _ptr(ws), ws.numel(), _stream())
+    return dw
+
+
+# ---------------------------------------------------------------------------------------------
+# ConvTranspose2d k2 s2
+# ---------------------------------------------------------------------------------------------
+def convT2x2_fprop(x, wk, bias, y, relu=True):
+    B, H, W, Cin, x_ld = _act(x, "x")
+    By, Hy, Wy, Cout, y_ld = _act(y, "y")
+    assert (By, Hy, Wy) == (B, 2 * H, 2 * W) and wk.shape == (4 * Cout, Cin), (x.shape, y.shape, wk.shape)
+    _f32(bias, "bias")
+    N.call("rovr_convT2x2_fprop", _ptr(x), x_ld, _ptr(wk), _ptr(bias), _ptr(y), y_ld, B, H, W, Cin,
+           Cout, int(relu), _stream())
+    return y
+
+
+def convT2x2_dgrad(dy, wk_d, dx, mask=None):
+    By, Hy, Wy, Cout, dy_ld = _act(dy, "dy")
+    B, H, W, Cin, dx_ld = _act(dx, "dx")
+    assert (By, Hy, Wy) == (B, 2 * H, 2 * W) and wk_d.shape == (Cin, 4 * Cout)
+    assert B == 1 or dy.stride(0) == Hy * Wy * dy_ld
+    mask_ld = 0
+    if mask is not None:
+        Bm, Hm, Wm, Cm, mask_ld = _act(mask, "mask")
+        assert (Bm, Hm, Wm, Cm) == (B, H, W, Cin)
+    N.call("rovr_convT2x2_dgrad", _ptr(dy), dy_ld, _ptr(wk_d), _ptr(dx), dx_ld, _ptr(mask), mask_ld,
+           B, H, W, Cin, Cout, _stream())
+    return dx
+
+
+def convT2x2_wgrad(dy, x, dw):
+    By, Hy, Wy, Cout, dy_ld = _act(dy, "dy")
+    B, H, W, Cin, x_ld = _act(x, "x")
+    assert (By, Hy, Wy) == (B, 2 * H, 2 * W)
+    _f32(dw, "dw")
+    assert dw.shape == (Cin, Cout, 2, 2)
+    need = N.lib.rovr_convT2x2_wgrad_workspace(B, H, W, Cin, Cout)
+    if need == 0:
+        raise N.RovrError("convT2x2_wgrad_workspace: " + N.last_error())
+    ws = workspace(need, dy.device)
+    N.call("rovr_convT2x2_wgrad", _ptr(dy), dy_ld, _ptr(x), x_ld, _ptr(dw), B, H, W, Cin, Cout,
+           _ptr(ws), ws.numel(), _stream())
+    return dw
+
+
+# ---------------------------------------------------------------------------------------------
+# GEMM
+# ---------------------------------------------------------------------------------------------
+def gemm_bf16(x, wk, bias=None, relu=False, out_dtype=torch.bfloat16, out=None):
+    """y[M, N] = x[M, K] @ wk[N, K]^T + bias. x: bf16 2-D (row stride = ld), wk: bf16 [N, K]."""
+    assert x.dim() == 2 and x.dtype == torch.bfloat16 and x.stride(1) == 1
+    M, K = x.shape
+    Nn = wk.shape[0]
+    assert wk.shape == (Nn, K) and wk.is_contiguous() and wk.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty((M, Nn), dtype=out_dtype, device=x.device)
+    assert out.stride(1) == 1
+    yb = _ptr(out) if out.dtype == torch.bfloat16 else _vp(0)
+    yf = _ptr(out) if out.dtype == torch.float32 else _vp(0)
+    N.call("rovr_gemm_bf16", _ptr(x), x.stride(0), _ptr(wk), _ptr(bias), yb, yf, out.stride(0), M,
+           Nn, K, int(relu), _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# pooling
+# ---------------------------------------------------------------------------------------------
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+def maxpool_fwd(x, y, kernel, stride=None):
+    kh, kw = _pair(kernel)
+    sh, sw = _pair(stride if stride is not None else kernel)
+    B, H, W, C, x_ld = _act(x, "x")
+    By, Ho, Wo, Cy, y_ld = _act(y, "y")
+    assert (By, Ho, Wo, Cy) == (B, (H - kh) // sh + 1, (W - kw) // sw + 1, C), (x.shape, y.shape)
+    N.call("rovr_maxpool_fwd", _ptr(x), x_ld, _ptr(y), y_ld, B, H, W, C, kh, kw, sh, sw, _stream())
+    return y
+
+
+def maxpool_bwd(x, gp, gx, kernel, stride=None, gskip=None, relu_mask=True):
+    kh, kw = _pair(kernel)
+    sh, sw = _pair(stride if stride is not None else kernel)
+    B, H, W, C, x_ld = _act(x, "x")
+    _, _, _, _, gp_ld = _act(gp, "gp")
+    _, _, _, _, gx_ld = _act(gx, "gx")
+    gs_ld = 0
+    if gskip is not None:
+        _, _, _, _, gs_ld = _act(gskip, "gskip")
+    N.call("rovr_maxpool_bwd", _ptr(x), x_ld, _ptr(gp), gp_ld, _ptr(gskip), gs_ld, _ptr(gx), gx_ld,
+           B, H, W, C, kh, kw, sh, sw, int(relu_mask), _stream())
+    return gx
+
+
+# ---------------------------------------------------------------------------------------------
+# LocalNet tail
+# ---------------------------------------------------------------------------------------------
+def tail_fwd(y7, w8, b8, target=None):
+    """conv8 (1x1, 64->3) + sigmoid. Returns (out NCHW fp32, loss scalar tensor or None)."""
+    B, H, W, C, ld = _act(y7, "y7")
+    assert C == 64 and ld == 64
+    w8 = w8.reshape(3, 64)
+    _f32(w8, "w8")
+    _f32(b8, "b8")
+    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=y7.device)
+    loss = None
+    ws = workspace(N.lib.rovr_tail_workspace(B, H, W), y7.device)
+    if target is not None:
+        _f32(target, "target")
+        assert target.shape == out.shape
+        loss = torch.empty((), dtype=torch.float32, device=y7.device)
+    N.call("rovr_tail_fwd", _ptr(y7), _ptr(w8), _ptr(b8), _ptr(out), _ptr(target), _ptr(loss),
+           _ptr(ws), ws.numel(), B, H, W, _stream())
+    return out, loss
+
+
+def tail_bwd(y7, w8, out, g7, dw8, db8, gout=None, target=None, mse_scale=0.0, gloss=None):
+    B, H, W, C, ld = _act(y7, "y7")
+    assert C == 64 and ld == 64
+    _, _, _, Cg, g_ld = _act(g7, "g7")
+    assert Cg == 64 and g_ld == 64
+    w8 = w8.reshape(3, 64)
+    _f32(w8, "w8")
+    _f32(out, "out")
+    _f32(gout, "gout")
+    _f32(target, "target")
+    _f32(gloss, "gloss")
+    ws = workspace(N.lib.rovr_tail_workspace(B, H, W), y7.device)
+    N.call("rovr_tail_bwd", _ptr(y7), _ptr(w8), _ptr(out), _ptr(gout), _ptr(target),
+           ctypes.c_float(mse_scale), _ptr(gloss), _ptr(g7), _ptr(dw8), _ptr(db8), _ptr(ws),
+           ws.numel(), B, H, W, _stream())
+
+
+# ---------------------------------------------------------------------------------------------
+# bias gradient
+# ---------------------------------------------------------------------------------------------
+def colsum(g, out):
+    B, H, W, C, ld = _act(g, "g")
+    _f32(out, "out")
+    assert out.numel() == C
+    ws = workspace(N.lib.rovr_colsum_workspace(C), g.device)
+    N.call("rovr_colsum", _ptr(g), ld, B * H * W, C, _ptr(out), _ptr(ws), ws.numel(), _stream())
+    return out
