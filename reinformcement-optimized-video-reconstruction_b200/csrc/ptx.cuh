@@ -19,8 +19,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 // A spin that never hangs the box: after ~2^31 SM cycles (about a second) the waiter records
-// which barrier it was stuck on and traps, so a protocol bug becomes a launch error instead of a
-// GPU that has to be reset.
+// which barrier it was stuck on and gives up (as does every later waiter), so a protocol bug
+// becomes a kernel that finishes with wrong results plus a non-zero rovr_hang_code(), instead of
+// a GPU that has to be reset.
 __device__ unsigned int g_rovr_hang_code = 0;
 
 // ---------------------------------------------------------------------------------------------
@@ -56,9 +57,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
   long long t0 = clock64();
   unsigned polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (((++polls) & 1023u) == 0u && (clock64() - t0) > (1ll << 31)) {
-      atomicExch(&g_rovr_hang_code, code | 0x80000000u);
-      __trap();
+    if (((++polls) & 255u) == 0u) {
+      // once any waiter has timed out, every later wait gives up at once so the grid drains
+      if (*reinterpret_cast<volatile unsigned int*>(&g_rovr_hang_code) != 0u) return;
+      if ((clock64() - t0) > (1ll << 31)) {
+        atomicCAS(&g_rovr_hang_code, 0u, code | 0x80000000u);
+        return;
+      }
     }
   }
 }

@@ -105,6 +105,10 @@ extern "C" int rovr_hang_code(unsigned int* code) {
   unsigned int v = 0;
   ROVR_CUDA(cudaMemcpyFromSymbol(&v, g_rovr_hang_code, sizeof(v)));
   *code = v;
+  if (v != 0) {  // reading clears it so that later launches run normally
+    const unsigned int zero = 0;
+    ROVR_CUDA(cudaMemcpyToSymbol(g_rovr_hang_code, &zero, sizeof(zero)));
+  }
   return 0;
 }
 

@@ -29,3 +29,18 @@ def _built_library():
     import build_native
     build_native.build()
     yield
+
+
+@pytest.fixture(autouse=True)
+def _no_kernel_hang(request):
+    """After every GPU test: no kernel may have hit an mbarrier timeout."""
+    yield
+    if request.node.get_closest_marker("gpu") is None:
+        return
+    import torch
+    if not torch.cuda.is_available():
+        return
+    import _native
+    torch.cuda.synchronize()
+    code = _native.hang_code()
+    assert code == 0, f"a kernel timed out on mbarrier code 0x{code:x}"

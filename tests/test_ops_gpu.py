@@ -1,0 +1,304 @@
+"""GPU parity tests, one per C-ABI operator: the CUDA kernels (called through ctypes) against a
+plain PyTorch fp32 evaluation of the same op on the same bf16-rounded inputs.
+
+Tolerances: operands are bf16 (exactly representable in fp32), accumulation is fp32 on both
+sides, so the only differences are summation order and the final bf16 rounding of the output:
+   bf16 outputs : |err| <= 1e-2 * max|ref|   (bf16 ulp is 2^-8 relative; north_star allows 2e-2)
+   fp32 outputs : |err| <= 2e-3 * max|ref|   (weight / bias gradients, fp32 partial sums)
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+def _dev():
+    import _native
+    _native.require_device()
+    return torch.device("cuda:0")
+
+
+def _rand_act(shape, gen, dev, scale=1.0, relu=False):
+    t = torch.randn(shape, generator=gen, device="cpu") * scale
+    if relu:
+        t = t.clamp_min(0)
+    return t.to(dev).to(BF)
+
+
+def _nchw(x_nhwc):
+    return x_nhwc.float().permute(0, 3, 1, 2).contiguous()
+
+
+def _nhwc(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous()
+
+
+def _report(name, got, ref, tol):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    scale = ref.abs().max().item() + 1e-12
+    bad = err > tol * scale
+    msg = (f"{name}: max_err={err.max().item():.4e} scale={scale:.4e} rel={err.max().item() / scale:.3e} "
+           f"bad={int(bad.sum())}/{bad.numel()} got_absmax={got.abs().max().item():.4e} "
+           f"nan={int(torch.isnan(got).sum())}")
+    if bad.any():
+        idx = bad.nonzero()[:5].tolist()
+        msg += f" first_bad={idx}"
+        for i in idx[:3]:
+            msg += f" got{tuple(i)}={got[tuple(i)].item():.4f} ref={ref[tuple(i)].item():.4f}"
+    print(msg)
+    assert not bad.any() and not torch.isnan(got).any(), msg
+
+
+CONV_SHAPES = [
+    # B, H, W, Cin, Cout
+    (2, 16, 16, 64, 64),
+    (1, 8, 128, 64, 32),
+    (2, 32, 32, 16, 64),     # bk = 16  (conv1 of LocalNet: 9 -> 16 padded)
+    (2, 16, 16, 32, 64),     # bk = 32  (policy net widths)
+    (1, 16, 16, 128, 128),   # 2 k-chunks per tap
+    (1, 8, 8, 256, 512),     # 2 N tiles
+    (3, 20, 20, 64, 64),     # ragged tiles
+    (5, 10, 10, 64, 128),    # patches spanning images
+    (7, 5, 5, 128, 256),     # tiny maps of policy_net_2
+    (2, 64, 64, 64, 16),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", CONV_SHAPES)
+def test_conv3x3_fprop(B, H, W, Cin, Cout):
+    import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 1000 + H + Cin + Cout)
+    x = _rand_act((B, H, W, Cin), g, dev)
+    w = (torch.randn((Cout, Cin, 3, 3), generator=g) * (1.0 / (3 * Cin ** 0.5))).to(dev)
+    b = torch.randn((Cout,), generator=g).to(dev) * 0.1
+    wk = ops.repack_conv3x3(w)
+    # write into a channel slice of a wider buffer to exercise ld / offset handling
+    ybuf = torch.full((B, H, W, Cout + 16), 7.0, dtype=BF, device=dev)
+    y = ybuf[..., 8:8 + Cout]
+    ops.conv3x3_fprop(x, wk, b, y, relu=True)
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(_nchw(x), w.to(BF).float(), b, padding=1))
+    _report(f"conv3x3_fprop{(B, H, W, Cin, Cout)}", _nchw(y), ref, 1e-2)
+    assert (ybuf[..., :8] == 7.0).all() and (ybuf[..., 8 + Cout:] == 7.0).all(), "wrote outside its slice"
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", CONV_SHAPES)
+def test_conv3x3_dgrad(B, H, W, Cin, Cout):
+    import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 1000 + H + Cin + Cout + 1)
+    dy = _rand_act((B, H, W, Cout), g, dev)
+    w = (torch.randn((Cout, Cin, 3, 3), generator=g) * (1.0 / (3 * Cout ** 0.5))).to(dev)
+    xmask = _rand_act((B, H, W, Cin), g, dev, relu=True)
+    wd = ops.repack_conv3x3(w, for_dgrad=True)
+    dx = torch.empty((B, H, W, Cin), dtype=BF, device=dev)
+    ops.conv3x3_dgrad(dy, wd, dx, mask=xmask)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(_nchw(dy), w.to(BF).float(), padding=1) * (_nchw(xmask) > 0)
+    _report(f"conv3x3_dgrad{(B, H, W, Cin, Cout)}", _nchw(dx), ref, 1e-2)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", CONV_SHAPES)
+def test_conv3x3_wgrad(B, H, W, Cin, Cout):
+    import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 1000 + H + Cin + Cout + 2)
+    dy = _rand_act((B, H, W, Cout), g, dev)
+    x = _rand_act((B, H, W, Cin), g, dev)
+    keep = Cin if Cin != 16 else 9
+    dw = torch.empty((Cout, keep, 3, 3), dtype=torch.float32, device=dev)
+    ops.conv3x3_wgrad(dy, x, dw)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(_nchw(x), (Cout, Cin, 3, 3), _nchw(dy), padding=1)[:, :keep]
+    _report(f"conv3x3_wgrad{(B, H, W, Cin, Cout)}", dw, ref, 2e-3)
+
+
+CONVT_SHAPES = [
+    # B, H, W (input), Cin, Cout
+    (2, 8, 8, 64, 32),
+    (1, 16, 16, 128, 64),
+    (2, 4, 4, 512, 256),     # N = 1024: 4 N tiles (upconv1 of LocalNet)
+    (3, 10, 10, 64, 32),     # policy_net_1 sizes
+    (2, 5, 5, 256, 128),
+    (1, 8, 64, 32, 16),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", CONVT_SHAPES)
+def test_convT2x2_fprop(B, H, W, Cin, Cout):
+    import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 1000 + H + Cin + Cout + 3)
+    x = _rand_act((B, H, W, Cin), g, dev)
+    w = (torch.randn((Cin, Cout, 2, 2), generator=g) * (1.0 / Cin ** 0.5)).to(dev)
+    b = torch.randn((Cout,), generator=g).to(dev) * 0.1
+    wk = ops.repack_convT2x2(w)
+    ybuf = torch.full((B, 2 * H, 2 * W, 2 * Cout), 7.0, dtype=BF, device=dev)
+    y = ybuf[..., :Cout]
+    ops.convT2x2_fprop(x, wk, b, y, relu=True)
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv_transpose2d(_nchw(x), w.to(BF).float(), b, stride=2))
+    _report(f"convT2x2_fprop{(B, H, W, Cin, Cout)}", _nchw(y), ref, 1e-2)
+    assert (ybuf[..., Cout:] == 7.0).all(), "wrote outside its slice"
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", CONVT_SHAPES)
+def test_convT2x2_dgrad(B, H, W, Cin, Cout):
+    import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 1000 + H + Cin + Cout + 4)
+    dybuf = _rand_act((B, 2 * H, 2 * W, 2 * Cout), g, dev)
+    dy = dybuf[..., :Cout]
+    w = (torch.randn((Cin, Cout, 2, 2), generator=g) * (1.0 / (2 * Cout ** 0.5))).to(dev)
+    xmask = _rand_act((B, H, W, Cin), g, dev, relu=True)
+    wd = ops.repack_convT2x2(w, for_dgrad=True)
+    dx = torch.empty((B, H, W, Cin), dtype=BF, device=dev)
+    ops.convT2x2_dgrad(dy, wd, dx, mask=xmask)
+    torch.cuda.synchronize()
+    ref = F.conv2d(_nchw(dy), w.to(BF).float(), stride=2) * (_nchw(xmask) > 0)
+    _report(f"convT2x2_dgrad{(B, H, W, Cin, Cout)}", _nchw(dx), ref, 1e-2)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", CONVT_SHAPES)
+def test_convT2x2_wgrad(B, H, W, Cin, Cout):
+    import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 1000 + H + Cin + Cout + 5)
+    dybuf = _rand_act((B, 2 * H, 2 * W, 2 * Cout), g, dev)
+    dy = dybuf[..., :Cout]
+    x = _rand_act((B, H, W, Cin), g, dev)
+    dw = torch.empty((Cin, Cout, 2, 2), dtype=torch.float32, device=dev)
+    ops.convT2x2_wgrad(dy, x, dw)
+    torch.cuda.synchronize()
+    # d/dW of conv_transpose2d(x, W, stride 2): dW[ci,co,ky,kx] = sum x[b,ci,y,x] dy[b,co,2y+ky,2x+kx]
+    xs = _nchw(x)
+    dys = _nchw(dy)
+    ref = torch.stack([torch.stack([torch.einsum("bihw,bohw->io", xs, dys[:, :, ky::2, kx::2])
+                                    for kx in range(2)], -1) for ky in range(2)], -2)
+    _report(f"convT2x2_wgrad{(B, H, W, Cin, Cout)}", dw, ref, 2e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 256, 128), (25, 768, 2048), (1000, 48, 32)])
+def test_gemm(M, N, K):
+    import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(M + N + K)
+    x = (torch.randn((M, K), generator=g) / K ** 0.5).to(dev).to(BF)
+    w = torch.randn((N, K), generator=g).to(dev).to(BF)
+    b = torch.randn((N,), generator=g).to(dev)
+    y = ops.gemm_bf16(x, w, b, relu=False, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t() + b
+    _report(f"gemm{(M, N, K)}", y, ref, 2e-3)
+    yb = ops.gemm_bf16(x, w, b, relu=True, out_dtype=BF)
+    torch.cuda.synchronize()
+    _report(f"gemm_bf16relu{(M, N, K)}", yb, F.relu(ref), 1e-2)
+
+
+@pytest.mark.parametrize("B,H,W,C,k,s", [(2, 16, 16, 64, 2, 2), (3, 160, 160, 64, 8, 8), (2, 20, 20, 128, 4, 4),
+                                          (2, 5, 5, 512, 2, (2, 1)), (2, 2, 4, 512, 2, 2), (2, 5, 5, 256, 1, 1)])
+def test_maxpool(B, H, W, C, k, s):
+    import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(B + H + C)
+    xbuf = _rand_act((B, H, W, C + 8), g, dev, relu=True)
+    x = xbuf[..., 8:]
+    sh, sw = (s, s) if isinstance(s, int) else s
+    Ho, Wo = (H - k) // sh + 1, (W - k) // sw + 1
+    y = torch.empty((B, Ho, Wo, C), dtype=BF, device=dev)
+    ops.maxpool_fwd(x, y, k, s)
+    xr = _nchw(x).requires_grad_(True)
+    yr = F.max_pool2d(xr, k, s)
+    torch.cuda.synchronize()
+    assert torch.equal(_nchw(y), yr.detach()), "maxpool forward must be exact"
+    gp = _rand_act((B, Ho, Wo, C), g, dev)
+    tiled = (k, k) == (sh, sw) and H % k == 0 and W % k == 0
+    gskip = _rand_act((B, H, W, C), g, dev) if tiled else None
+    gx = torch.empty((B, H, W, C), dtype=BF, device=dev)
+    ops.maxpool_bwd(x, gp, gx, k, s, gskip=gskip, relu_mask=True)
+    torch.cuda.synchronize()
+    yr.backward(_nchw(gp))
+    ref = xr.grad
+    if gskip is not None:
+        ref = ref + _nchw(gskip)
+    ref = ref * (xr.detach() > 0)
+    # bf16 ties inside a window can route the gradient to a different (equal-valued) element
+    # than ATen only if two equal maxima exist; the inputs are random normals so ties are only at 0
+    _report(f"maxpool_bwd{(B, H, W, C, k, s)}", _nchw(gx), ref, 1e-2)
+
+
+def test_pack_and_unpack():
+    import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    a = torch.rand((3, 3, 24, 40), generator=g).to(dev)
+    c = torch.rand((3, 2, 3, 24, 40), generator=g).to(dev)
+    p = ops.pack_nchw([a, c.reshape(3, 6, 24, 40)], 16)
+    torch.cuda.synchronize()
+    ref = torch.cat([a, c.reshape(3, 6, 24, 40)], 1).to(BF)
+    assert torch.equal(_nchw(p)[:, :9], ref.float())
+    assert (p[..., 9:] == 0).all()
+    back = ops.unpack_nhwc(p, 9)
+    torch.cuda.synchronize()
+    assert torch.equal(back, ref.float())
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (1, 64, 40), (3, 8, 8)])
+def test_tail(B, H, W):
+    import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(B + H)
+    y7 = _rand_act((B, H, W, 64), g, dev, relu=True)
+    w8 = (torch.randn((3, 64, 1, 1), generator=g) * 0.2).to(dev)
+    b8 = (torch.randn((3,), generator=g) * 0.1).to(dev)
+    tgt = torch.rand((B, 3, H, W), generator=g).to(dev)
+    out, loss = ops.tail_fwd(y7, w8, b8, tgt)
+    torch.cuda.synchronize()
+    y7r = _nchw(y7).requires_grad_(True)
+    w8r = w8.clone().requires_grad_(True)
+    b8r = b8.clone().requires_grad_(True)
+    ref = torch.sigmoid(F.conv2d(y7r, w8r, b8r))
+    lref = F.mse_loss(ref, tgt)
+    _report("tail_fwd", out, ref.detach(), 1e-5)
+    assert abs(loss.item() - lref.item()) < 1e-5 * max(1.0, abs(lref.item()))
+    # backward driven by the fused loss
+    g7 = torch.empty_like(y7)
+    dw8 = torch.empty((3, 64), device=dev)
+    db8 = torch.empty((3,), device=dev)
+    gl = torch.ones((), device=dev)
+    ops.tail_bwd(y7, w8, out, g7, dw8, db8, gout=None, target=tgt, mse_scale=2.0 / out.numel(), gloss=gl)
+    torch.cuda.synchronize()
+    lref.backward()
+    _report("tail_bwd.g7", _nchw(g7), y7r.grad * (y7r.detach() > 0), 1e-2)
+    _report("tail_bwd.dw8", dw8, w8r.grad.reshape(3, 64), 2e-3)
+    _report("tail_bwd.db8", db8, b8r.grad, 2e-3)
+    # backward driven by an explicit upstream gradient
+    gout = torch.randn((B, 3, H, W), generator=g).to(dev)
+    y7r.grad = None
+    w8r.grad = None
+    ref2 = torch.sigmoid(F.conv2d(y7r, w8r, b8r))
+    ref2.backward(gout)
+    ops.tail_bwd(y7, w8, out, g7, dw8, db8, gout=gout)
+    torch.cuda.synchronize()
+    _report("tail_bwd.g7(gout)", _nchw(g7), y7r.grad * (y7r.detach() > 0), 1e-2)
+    _report("tail_bwd.dw8(gout)", dw8, w8r.grad.reshape(3, 64), 2e-3)
+
+
+@pytest.mark.parametrize("npix_shape,C", [((2, 16, 16), 64), ((3, 7, 5), 256), ((1, 64, 64), 32), ((2, 4, 4), 512)])
+def test_colsum(npix_shape, C):
+    import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(C)
+    B, H, W = npix_shape
+    buf = _rand_act((B, H, W, C + 8), g, dev)
+    x = buf[..., :C]
+    out = torch.empty((C,), device=dev)
+    ops.colsum(x, out)
+    torch.cuda.synchronize()
+    _report("colsum", out, x.float().sum(dim=(0, 1, 2)), 1e-4)
