@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — masked frames/s through the ROVR hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference arithmetic on host cores
+
+A "step" is one pass of the hot path over one batch of synthetic masked frames: LocalNet U-Net
+forward + L2 loss + backward (+ bucketed gradient all-reduce when N > 1), the training step of
+rovr/train_local_net_unet.py:102-107,115 restricted to the path BASELINE.json names (no LPIPS, no
+optimizer). Workload = BASELINE.json configs[1]: B = 24 frames per GPU, 256x256, synthetic masked
+clips (rovr/train_local_net_unet.py:93; rovr/video_ds.py:62-87).
+
+One JSON line is printed by rank 0. Keys beyond the base contract:
+  roofline     : aggregate of every launch of the dominant kernel (igemm_kernel: conv fprop, conv
+                 dgrad, transposed-conv fprop/dgrad) inside the timed region; achieved = algorithmic
+                 FLOPs of those launches / their summed CUDA-event durations; peak = the measured
+                 sustained bf16 figure of MEASURED_PEAKS.json (kernel timed inside a long step).
+  kernel_classes: the same for the other kernel classes (explains where the step goes).
+  cpu_baseline : the oracle port timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "reinformcement-optimized-video-reconstruction_b200")
+ORACLE = os.path.join(ROOT, "oracle")
+sys.path.insert(0, PKG)
+
+import torch  # noqa: E402
+
+B_PER_GPU, H, W = 24, 256, 256
+METRIC = "masked frames/sec (LocalNet fwd+L2+bwd)"
+UNIT = "frames/s"
+
+# LocalNet layer table: (kind, cin, cout, output resolution divisor) — rovr/local_net.py:12-39
+_LAYERS = [("conv", 9, 64, 1), ("conv", 64, 128, 2), ("conv", 128, 256, 4), ("conv", 256, 512, 8),
+           ("up", 512, 256, 8), ("conv", 512, 256, 4), ("up", 256, 128, 4), ("conv", 256, 128, 2),
+           ("up", 128, 64, 2), ("conv", 128, 64, 1)]
+
+
+def algorithmic_macs_per_frame():
+    """GEMM MACs per 256x256 frame by kernel class (59.907 GMAC fwd+bwd total,
+    including the 1x1 conv8 that runs in the fused tail kernel)."""
+    fprop = dgrad = wgrad = 0
+    for i, (kind, cin, cout, div) in enumerate(_LAYERS):
+        if kind == "conv":
+            macs = (H // div) * (W // div) * 9 * cin * cout
+        else:  # transposed conv: input resolution H/div, 4 outputs per input pixel
+            macs = (H // div) * (W // div) * 4 * cin * cout
+        fprop += macs
+        wgrad += macs
+        if i > 0:  # conv1 has no data gradient (input needs none)
+            dgrad += macs
+    tail = H * W * 64 * 3
+    return {"igemm": fprop + dgrad, "wgrad": wgrad, "tail": 3 * tail}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"tensor_tflops": p.get("bf16_tflops_sustained", p.get("bf16_tflops")),
+                "tensor_tflops_burst": p.get("bf16_tflops"), "hbm_gbs": p.get("hbm_gbs"),
+                "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"tensor_tflops": 1400.0, "tensor_tflops_burst": 1590.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        clocks, reasons, mx = [], set(), None
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    clocks.append(float(f[1]))
+                    mx = float(f[2])
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                      "sw_power_cap"), f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if clocks:
+            clocks.sort()
+            out.update(sm_mhz=clocks[len(clocks) // 2], sm_max_mhz=mx, reasons=sorted(reasons),
+                       samples=len(clocks))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step_rate(steps, warmup, sample_b=None, budget_s=None):
+    """Times LocalNet fwd + MSE + bwd of the oracle port (fp32, all host threads) on a bounded
+    sample of the workload: `sample_b` frames of 256x256 per step."""
+    sys.path.insert(0, ORACLE)
+    import rovr_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = O.localnet_state_dict(0)
+    if sample_b is None:
+        # size the sample so one step is about a second on this box
+        x, c, t = O.synthetic_localnet_batch(1, H, W, seed=1234)
+        O.localnet_step(sd, x, c, t)
+        t0 = time.perf_counter()
+        O.localnet_step(sd, x, c, t)
+        per_frame = time.perf_counter() - t0
+        sample_b = max(1, min(B_PER_GPU, int(1.0 / max(per_frame, 1e-3))))
+    x, c, t = O.synthetic_localnet_batch(sample_b, H, W, seed=1234)
+    for _ in range(warmup):
+        O.localnet_step(sd, x, c, t)
+    done = 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.localnet_step(sd, x, c, t)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": sample_b * done / dt, "unit": UNIT, "cores": torch.get_num_threads(),
+            "kind": "port",
+            "sample": f"{done} timed step(s) after {warmup} warm-up of the oracle port (PyTorch fp32 CPU, "
+                      f"LocalNet fwd+MSE+bwd) on {sample_b} frame(s) of {H}x{W} per step"}, dt / max(done, 1)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    base, ms = cpu_step_rate(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "LocalNet U-Net fwd+L2+bwd, 256x256 masked frames (CPU sample of configs[1])",
+                       "note": "reference is pure PyTorch; its modules cannot travel to the GPU box, so the "
+                               "oracle port (pinned to the reference by tests/golden) is what is timed"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# the CUDA arm
+# ------------------------------------------------------------------------------------------------
+def synthetic_batch_gpu(dev, seed):
+    from synthetic import masked_frame_batch
+    return masked_frame_batch(B_PER_GPU, H, W, seed=seed)
+
+
+def run_cuda(args, rank, local_rank, world):
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import _native
+    _native.require_device()
+    import ops
+    from local_net import LocalNetworkUNetNorm
+    from data_parallel import GradientBuckets, broadcast_parameters
+
+    torch.manual_seed(0)
+    net = LocalNetworkUNetNorm().to(dev)
+    if world > 1:
+        broadcast_parameters(net)
+        GradientBuckets(net)
+    xh, ch, th = synthetic_batch_gpu(dev, 1234 + rank)
+    xh, ch, th = xh.pin_memory(), ch.pin_memory(), th.pin_memory()
+    x, c, t = xh.to(dev), ch.to(dev), th.to(dev)
+
+    def step_resident():
+        net.zero_grad(set_to_none=True)
+        _, loss = net.forward_with_mse(x, c, t)
+        loss.backward()
+        return loss
+
+    def step_e2e():
+        xd = xh.to(dev, non_blocking=True)
+        cd = ch.to(dev, non_blocking=True)
+        td = th.to(dev, non_blocking=True)
+        net.zero_grad(set_to_none=True)
+        y = net(xd, cd)                                  # the reference-facing call
+        loss = torch.nn.functional.mse_loss(y, td)       # rovr/train_local_net_unet.py:107
+        loss.backward()
+        return float(loss)                               # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=None):
+        barrier()
+        ops.set_profile(profile)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ops.set_profile(None)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tms = torch.tensor([ms], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    prof = []
+    n0 = _native.lib.rovr_launch_count()
+    ms_total = timed(step_resident, args.steps, profile=prof)
+    launches = _native.lib.rovr_launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else {}
+    frames = B_PER_GPU * world * args.steps
+    value = frames / (ms_total * 1e-3)
+
+    if args.profile_run:
+        ms_e2e, e2e_value = float("nan"), None
+    else:
+        for _ in range(2):
+            step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+        e2e_value = frames / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel-class roofline from the events recorded inside the timed region ----
+    peaks = measured_peaks()
+    classes = {"igemm": ["rovr_conv3x3_fprop", "rovr_conv3x3_dgrad", "rovr_convT2x2_fprop", "rovr_convT2x2_dgrad"],
+               "wgrad": ["rovr_conv3x3_wgrad", "rovr_convT2x2_wgrad"],
+               "tail": ["rovr_tail_fwd", "rovr_tail_bwd"],
+               "pool": ["rovr_maxpool_fwd", "rovr_maxpool_bwd"],
+               "bias_grad": ["rovr_colsum"],
+               "pack": ["rovr_pack_nchw_to_nhwc", "rovr_repack_conv3x3_fprop", "rovr_repack_conv3x3_dgrad",
+                        "rovr_repack_convT2x2_fprop", "rovr_repack_convT2x2_dgrad"]}
+    dur = {k: 0.0 for k in classes}
+    cnt = {k: 0 for k in classes}
+    per_name = {}
+    for name, a, b in prof:
+        ms = a.elapsed_time(b)
+        per_name[name] = per_name.get(name, 0.0) + ms
+        for k, names in classes.items():
+            if name in names:
+                dur[k] += ms
+                cnt[k] += 1
+    macs = algorithmic_macs_per_frame()
+    frames_rank0 = B_PER_GPU * args.steps
+    kc = {}
+    for k in classes:
+        entry = {"calls_per_step": cnt[k] / args.steps, "ms_per_step": dur[k] / args.steps}
+        if k in macs and dur[k] > 0:
+            entry["tflops"] = 2.0 * macs[k] * frames_rank0 / (dur[k] * 1e-3) / 1e12
+        kc[k] = entry
+    ig_calls = max(cnt["igemm"], 1)
+    ig_flops_per_launch = 2.0 * macs["igemm"] * frames_rank0 / ig_calls
+    ig_avg_s = dur["igemm"] * 1e-3 / ig_calls
+    achieved = ig_flops_per_launch / ig_avg_s / 1e12 if ig_avg_s > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("igemm_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "igemm_kernel (tcgen05 implicit GEMM: conv/convT fprop + dgrad)",
+                "bound": "tensor", "achieved": achieved, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["tensor_tflops"], "traffic": traffic,
+                "launches_per_step": cnt["igemm"] / args.steps,
+                "avg_launch_ms": ig_avg_s * 1e3, "flops_per_launch": ig_flops_per_launch,
+                "peak_source": peaks["source"]}
+    total_flops_per_frame = 2.0 * (macs["igemm"] + macs["wgrad"] + macs["tail"])
+    cpu_base = None if args.profile_run else cpu_step_rate(steps=2, warmup=1, budget_s=25.0)[0]
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "LocalNet U-Net fwd+L2+bwd (configs[1]): B=24 frames/GPU, 256x256, "
+                                   "synthetic masked clips, random-init weights",
+                       "global_batch": B_PER_GPU * world, "parallelism": f"dp{world}",
+                       "l2": "each step streams ~2.5 GB of activations/gradients (>> 126 MB L2); no explicit flush",
+                       "precision": "bf16 operands + bf16 activation storage, fp32 accumulate, fp32 master weights/grads"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": (xh.numel() + ch.numel() + th.numel()) * 4, "d2h_bytes_per_step": 4,
+                    "api": "y = LocalNetworkUNetNorm()(frame, context); F.mse_loss(y, target).backward(); float(loss)"},
+            "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+            "clocks": clocks, "roofline": roofline, "kernel_classes": kc,
+            "model_tflops": total_flops_per_frame * value / world / 1e12,
+            "model_frac_of_peak": total_flops_per_frame * value / world / 1e12 / peaks["tensor_tflops"],
+            "cpu_baseline": cpu_base}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--profile-run", action="store_true",
+                    help="for runs under ncu: skip the e2e and cpu_baseline legs (their numbers are null)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run on this node
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__),
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        sys.exit(subprocess.call(cmd))
+    run_cuda(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

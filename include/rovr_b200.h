@@ -31,6 +31,8 @@ const char* rovr_last_error(void);
 int rovr_device_check(void);
 /* last mbarrier-timeout code recorded by a kernel (0 = none); debugging aid. */
 int rovr_hang_code(unsigned int* code);
+/* number of kernels this library has launched in this process (bench.py reports it). */
+unsigned long long rovr_launch_count(void);
 
 /* ---- layout packing ------------------------------------------------------------------------
  * cat of up to three NCHW fp32 tensors along C, converted to NHWC bf16 padded to cpad channels.

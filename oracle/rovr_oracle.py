@@ -417,3 +417,59 @@ def action_lstm_step(sd, action, new_tensor, hx, cx):
     hx = torch.sigmoid(o) * torch.tanh(cx)
     out = F.linear(hx, sd["fc.weight"], sd["fc.bias"]).view(-1, 3, 80, 80)
     return out, hx, cx
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 storage emulation (to separate "inherent bf16 noise" from implementation error in tests)
+# ------------------------------------------------------------------------------------------------
+class _RoundTrip(torch.autograd.Function):
+    """Identity whose forward value and backward gradient are rounded to bf16 and back — the
+    storage precision of activations and activation-gradients on the B200 path."""
+
+    @staticmethod
+    def forward(ctx, t, round_grad):
+        ctx.round_grad = round_grad
+        return t.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g.to(torch.bfloat16).to(torch.float32) if ctx.round_grad else g), None
+
+
+def localnet_step_bf16_storage(sd, x, context, target):
+    """localnet_step with fp32 arithmetic but bf16 *storage* at the points where the B200 path
+    stores bf16: packed input, conv/upconv weights (conv8 stays fp32), every post-ReLU
+    activation, and every activation gradient. Differences between this and localnet_step are
+    what any bf16 tensor-core implementation must show; differences between this and the CUDA
+    path are implementation error (plus the occasional 1-ulp rounding flip)."""
+    leaf = {k: (v.clone().requires_grad_(True) if k in LOCALNET_LIVE else v) for k, v in sd.items()}
+
+    def w(name):
+        p = leaf[name + ".weight"]
+        return p + (p.to(torch.bfloat16).to(torch.float32) - p).detach()  # straight-through rounding
+
+    rt = _RoundTrip.apply
+    b = x.shape[0]
+    h = torch.cat([x[:, None], context], dim=1).reshape(b, 9, x.shape[2], x.shape[3])
+    h = rt(h, False)
+
+    def conv(name, t):
+        return rt(F.relu(F.conv2d(t, w(name), leaf[name + ".bias"], padding=1)), True)
+
+    def up(name, t):
+        return rt(F.relu(F.conv_transpose2d(t, w(name), leaf[name + ".bias"], stride=2)), True)
+
+    def pool(t):
+        return rt(F.max_pool2d(t, 2), True)
+
+    e1 = conv("conv1", h)
+    e2 = conv("conv2", pool(e1))
+    e3 = conv("conv3", pool(e2))
+    e4 = conv("conv4", pool(e3))
+    d = conv("conv5", rt(torch.cat([up("upconv1", e4), e3], 1), True))
+    d = conv("conv6", rt(torch.cat([up("upconv2", d), e2], 1), True))
+    d = conv("conv7", rt(torch.cat([up("upconv3", d), e1], 1), True))
+    y = torch.sigmoid(F.conv2d(d, leaf["conv8.weight"], leaf["conv8.bias"]))
+    loss = F.mse_loss(y, target)
+    loss.backward()
+    return y.detach(), loss.detach(), {k: leaf[k].grad for k in LOCALNET_LIVE}

@@ -29,6 +29,7 @@ SIGNATURES = {
     "rovr_last_error": (ctypes.c_char_p, []),
     "rovr_device_check": (_i, []),
     "rovr_hang_code": (_i, [ctypes.POINTER(ctypes.c_uint)]),
+    "rovr_launch_count": (ctypes.c_ulonglong, []),
     "rovr_pack_nchw_to_nhwc": (_i, [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p]),
     "rovr_unpack_nhwc_to_nchw": (_i, [_p, _i, _p, _i, _i, _i, _i, _p]),
     "rovr_repack_conv3x3_fprop": (_i, [_p, _p, _i, _i, _i, _p]),

@@ -7,6 +7,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -41,11 +42,14 @@ static int fail(int code, const char* fmt, ...) {
   do {                          \
     if (!(cond)) return fail(-1, __VA_ARGS__); \
   } while (0)
+static std::atomic<unsigned long long> g_launches{0};
 static int launch_check(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(-3, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
+extern "C" unsigned long long rovr_launch_count(void) { return g_launches.load(); }
 
 extern "C" int rovr_abi_version(void) { return 1; }
 extern "C" const char* rovr_last_error(void) { return g_err; }

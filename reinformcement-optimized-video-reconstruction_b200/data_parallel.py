@@ -1,0 +1,77 @@
+"""Data parallelism for the ROVR hot path: one process per GPU, parameters replicated, the video
+batch sharded by frame (LocalNet) or by whole clip (policy nets), gradients averaged with one
+all-reduce per bucket, overlapped with the rest of backward.
+
+The reference has no distributed code at all (`parallel_and_device()` is just
+`.to(device)`, rovr/train_local_net_unet.py:73-75), so this is new work specified by §8e:
+
+  * LocalNet's backward produces its gradients decoder-first. `local_net._LocalNetFunction`
+    writes them into two flat fp32 buckets (decoder: conv8..upconv1 = 2 237 507 elements, ready
+    first; encoder: conv4..conv1 = 1 554 432) and calls `_bucket_ready(i, flat)` the moment a
+    bucket is complete. `GradientBuckets` then launches the all-reduce of that bucket on a side
+    stream (NCCL over NVLink/NVSwitch) while the encoder half of backward is still running, and
+    makes the main stream wait for both before autograd accumulates into `.grad`.
+  * No other collective exists on the path (no all-gather / all-to-all): frames are independent.
+  * Policy nets use train-mode BatchNorm; they are sharded by whole clip so each replica sees
+    exactly the per-clip batch of the reference (§8e caveat) and only gradients are reduced.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total, rank, world):
+    """Contiguous [lo, hi) slice of `total` items owned by `rank` (remainder to the low ranks)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class GradientBuckets:
+    """Bucketed, overlapped gradient averaging for a module that exposes the
+    `_grad_bucket_hook` / `_grad_bucket_wait` hook points (LocalNetworkUNetNorm)."""
+
+    def __init__(self, module, process_group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.group = process_group
+        self.world = dist.get_world_size(process_group)
+        self.backend = dist.get_backend(process_group)
+        self.on_gpu = self.backend == "nccl"
+        self.stream = torch.cuda.Stream() if self.on_gpu else None
+        self.pending = []
+        self.launched = 0
+        module._grad_bucket_hook = self.ready
+        module._grad_bucket_wait = self.wait
+
+    def ready(self, index, flat):
+        if self.world == 1:
+            return
+        self.launched += 1
+        if self.on_gpu:
+            main = torch.cuda.current_stream()
+            self.stream.wait_stream(main)          # the bucket's producers have been enqueued
+            flat.record_stream(self.stream)
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+            self.pending.append(flat)
+        else:
+            # gloo (CPU tests of the host logic): SUM then scale
+            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self.pending.append((work, flat))
+
+    def wait(self):
+        if self.world == 1:
+            return
+        if self.on_gpu:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        else:
+            for work, flat in self.pending:
+                work.wait()
+                flat.div_(self.world)
+        self.pending = []
+
+
+def broadcast_parameters(module, src=0, process_group=None):
+    """Make every replica start from rank `src`'s parameters and buffers."""
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=process_group)

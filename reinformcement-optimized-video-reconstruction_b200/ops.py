@@ -22,6 +22,28 @@ def _stream():
     return _vp(torch.cuda.current_stream().cuda_stream)
 
 
+# Optional per-call timing for bench.py's roofline: when a list is installed with
+# `set_profile(list)`, every C-ABI call is bracketed by CUDA events on the launching stream and
+# (name, start_event, end_event) is appended. None (the default) adds no overhead.
+_PROFILE = None
+
+
+def set_profile(sink):
+    global _PROFILE
+    _PROFILE = sink
+
+
+def _launch(name, *args):
+    if _PROFILE is None:
+        return N.call(name, *args)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    N.call(name, *args)
+    e1.record()
+    _PROFILE.append((name, e0, e1))
+
+
 def _act(t, name="activation"):
     """Validate an NHWC bf16 view and return (B, H, W, C, ld)."""
     if t.dtype != torch.bfloat16 or not t.is_cuda or t.dim() != 4:
@@ -72,7 +94,7 @@ def pack_nchw(srcs, cpad, out=None):
             args += [_ptr(srcs[i]), srcs[i].shape[1]]
         else:
             args += [_vp(0), 0]
-    N.call("rovr_pack_nchw_to_nhwc", *args, _ptr(out), B, H, W, cpad, _stream())
+    _launch("rovr_pack_nchw_to_nhwc", *args, _ptr(out), B, H, W, cpad, _stream())
     return out
 
 
@@ -80,7 +102,7 @@ def unpack_nhwc(x, C=None):
     B, H, W, Cx, ld = _act(x)
     C = Cx if C is None else C
     out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
-    N.call("rovr_unpack_nhwc_to_nchw", _ptr(x), ld, _ptr(out), B, H, W, C, _stream())
+    _launch("rovr_unpack_nhwc_to_nchw", _ptr(x), ld, _ptr(out), B, H, W, C, _stream())
     return out
 
 
@@ -97,10 +119,10 @@ def repack_conv3x3(w, for_dgrad=False):
     cin_pad = pad16(Cin)
     if for_dgrad:
         wk = torch.empty((cin_pad, 9 * Cout), dtype=torch.bfloat16, device=w.device)
-        N.call("rovr_repack_conv3x3_dgrad", _ptr(w), _ptr(wk), Cout, Cin, cin_pad, _stream())
+        _launch("rovr_repack_conv3x3_dgrad", _ptr(w), _ptr(wk), Cout, Cin, cin_pad, _stream())
     else:
         wk = torch.empty((Cout, 9 * cin_pad), dtype=torch.bfloat16, device=w.device)
-        N.call("rovr_repack_conv3x3_fprop", _ptr(w), _ptr(wk), Cout, Cin, cin_pad, _stream())
+        _launch("rovr_repack_conv3x3_fprop", _ptr(w), _ptr(wk), Cout, Cin, cin_pad, _stream())
     return wk
 
 
@@ -109,10 +131,10 @@ def repack_convT2x2(w, for_dgrad=False):
     Cin, Cout = w.shape[0], w.shape[1]
     if for_dgrad:
         wk = torch.empty((Cin, 4 * Cout), dtype=torch.bfloat16, device=w.device)
-        N.call("rovr_repack_convT2x2_dgrad", _ptr(w), _ptr(wk), Cin, Cout, _stream())
+        _launch("rovr_repack_convT2x2_dgrad", _ptr(w), _ptr(wk), Cin, Cout, _stream())
     else:
         wk = torch.empty((4 * Cout, Cin), dtype=torch.bfloat16, device=w.device)
-        N.call("rovr_repack_convT2x2_fprop", _ptr(w), _ptr(wk), Cin, Cout, _stream())
+        _launch("rovr_repack_convT2x2_fprop", _ptr(w), _ptr(wk), Cin, Cout, _stream())
     return wk
 
 
@@ -124,7 +146,7 @@ def conv3x3_fprop(x, wk, bias, y, relu=True):
     By, Hy, Wy, Cout, y_ld = _act(y, "y")
     assert (B, H, W) == (By, Hy, Wy) and wk.shape == (Cout, 9 * Cin), (x.shape, y.shape, wk.shape)
     _f32(bias, "bias")
-    N.call("rovr_conv3x3_fprop", _ptr(x), x_ld, _ptr(wk), _ptr(bias), _ptr(y), y_ld, B, H, W, Cin,
+    _launch("rovr_conv3x3_fprop", _ptr(x), x_ld, _ptr(wk), _ptr(bias), _ptr(y), y_ld, B, H, W, Cin,
            Cout, int(relu), _stream())
     return y
 
@@ -137,7 +159,7 @@ def conv3x3_dgrad(dy, wk_d, dx, mask=None):
     if mask is not None:
         Bm, Hm, Wm, Cm, mask_ld = _act(mask, "mask")
         assert (Bm, Hm, Wm, Cm) == (B, H, W, Cin)
-    N.call("rovr_conv3x3_dgrad", _ptr(dy), dy_ld, _ptr(wk_d), _ptr(dx), dx_ld, _ptr(mask), mask_ld,
+    _launch("rovr_conv3x3_dgrad", _ptr(dy), dy_ld, _ptr(wk_d), _ptr(dx), dx_ld, _ptr(mask), mask_ld,
            B, H, W, Cin, Cout, _stream())
     return dx
 
@@ -153,7 +175,7 @@ def conv3x3_wgrad(dy, x, dw):
     if need == 0:
         raise N.RovrError("conv3x3_wgrad_workspace: " + N.last_error())
     ws = workspace(need, dy.device)
-    N.call("rovr_conv3x3_wgrad", _ptr(dy), dy_ld, _ptr(x), x_ld, _ptr(dw), B, H, W, Cin, cin_keep,
+    _launch("rovr_conv3x3_wgrad", _ptr(dy), dy_ld, _ptr(x), x_ld, _ptr(dw), B, H, W, Cin, cin_keep,
            Cout, _ptr(ws), ws.numel(), _stream())
     return dw
 
@@ -166,7 +188,7 @@ def convT2x2_fprop(x, wk, bias, y, relu=True):
     By, Hy, Wy, Cout, y_ld = _act(y, "y")
     assert (By, Hy, Wy) == (B, 2 * H, 2 * W) and wk.shape == (4 * Cout, Cin), (x.shape, y.shape, wk.shape)
     _f32(bias, "bias")
-    N.call("rovr_convT2x2_fprop", _ptr(x), x_ld, _ptr(wk), _ptr(bias), _ptr(y), y_ld, B, H, W, Cin,
+    _launch("rovr_convT2x2_fprop", _ptr(x), x_ld, _ptr(wk), _ptr(bias), _ptr(y), y_ld, B, H, W, Cin,
            Cout, int(relu), _stream())
     return y
 
@@ -180,7 +202,7 @@ def convT2x2_dgrad(dy, wk_d, dx, mask=None):
     if mask is not None:
         Bm, Hm, Wm, Cm, mask_ld = _act(mask, "mask")
         assert (Bm, Hm, Wm, Cm) == (B, H, W, Cin)
-    N.call("rovr_convT2x2_dgrad", _ptr(dy), dy_ld, _ptr(wk_d), _ptr(dx), dx_ld, _ptr(mask), mask_ld,
+    _launch("rovr_convT2x2_dgrad", _ptr(dy), dy_ld, _ptr(wk_d), _ptr(dx), dx_ld, _ptr(mask), mask_ld,
            B, H, W, Cin, Cout, _stream())
     return dx
 
@@ -195,7 +217,7 @@ def convT2x2_wgrad(dy, x, dw):
     if need == 0:
         raise N.RovrError("convT2x2_wgrad_workspace: " + N.last_error())
     ws = workspace(need, dy.device)
-    N.call("rovr_convT2x2_wgrad", _ptr(dy), dy_ld, _ptr(x), x_ld, _ptr(dw), B, H, W, Cin, Cout,
+    _launch("rovr_convT2x2_wgrad", _ptr(dy), dy_ld, _ptr(x), x_ld, _ptr(dw), B, H, W, Cin, Cout,
            _ptr(ws), ws.numel(), _stream())
     return dw
 
@@ -214,7 +236,7 @@ def gemm_bf16(x, wk, bias=None, relu=False, out_dtype=torch.bfloat16, out=None):
     assert out.stride(1) == 1
     yb = _ptr(out) if out.dtype == torch.bfloat16 else _vp(0)
     yf = _ptr(out) if out.dtype == torch.float32 else _vp(0)
-    N.call("rovr_gemm_bf16", _ptr(x), x.stride(0), _ptr(wk), _ptr(bias), yb, yf, out.stride(0), M,
+    _launch("rovr_gemm_bf16", _ptr(x), x.stride(0), _ptr(wk), _ptr(bias), yb, yf, out.stride(0), M,
            Nn, K, int(relu), _stream())
     return out
 
@@ -232,7 +254,7 @@ def maxpool_fwd(x, y, kernel, stride=None):
     B, H, W, C, x_ld = _act(x, "x")
     By, Ho, Wo, Cy, y_ld = _act(y, "y")
     assert (By, Ho, Wo, Cy) == (B, (H - kh) // sh + 1, (W - kw) // sw + 1, C), (x.shape, y.shape)
-    N.call("rovr_maxpool_fwd", _ptr(x), x_ld, _ptr(y), y_ld, B, H, W, C, kh, kw, sh, sw, _stream())
+    _launch("rovr_maxpool_fwd", _ptr(x), x_ld, _ptr(y), y_ld, B, H, W, C, kh, kw, sh, sw, _stream())
     return y
 
 
@@ -245,7 +267,7 @@ def maxpool_bwd(x, gp, gx, kernel, stride=None, gskip=None, relu_mask=True):
     gs_ld = 0
     if gskip is not None:
         _, _, _, _, gs_ld = _act(gskip, "gskip")
-    N.call("rovr_maxpool_bwd", _ptr(x), x_ld, _ptr(gp), gp_ld, _ptr(gskip), gs_ld, _ptr(gx), gx_ld,
+    _launch("rovr_maxpool_bwd", _ptr(x), x_ld, _ptr(gp), gp_ld, _ptr(gskip), gs_ld, _ptr(gx), gx_ld,
            B, H, W, C, kh, kw, sh, sw, int(relu_mask), _stream())
     return gx
 
@@ -267,7 +289,7 @@ def tail_fwd(y7, w8, b8, target=None):
         _f32(target, "target")
         assert target.shape == out.shape
         loss = torch.empty((), dtype=torch.float32, device=y7.device)
-    N.call("rovr_tail_fwd", _ptr(y7), _ptr(w8), _ptr(b8), _ptr(out), _ptr(target), _ptr(loss),
+    _launch("rovr_tail_fwd", _ptr(y7), _ptr(w8), _ptr(b8), _ptr(out), _ptr(target), _ptr(loss),
            _ptr(ws), ws.numel(), B, H, W, _stream())
     return out, loss
 
@@ -284,7 +306,7 @@ def tail_bwd(y7, w8, out, g7, dw8, db8, gout=None, target=None, mse_scale=0.0, g
     _f32(target, "target")
     _f32(gloss, "gloss")
     ws = workspace(N.lib.rovr_tail_workspace(B, H, W), y7.device)
-    N.call("rovr_tail_bwd", _ptr(y7), _ptr(w8), _ptr(out), _ptr(gout), _ptr(target),
+    _launch("rovr_tail_bwd", _ptr(y7), _ptr(w8), _ptr(out), _ptr(gout), _ptr(target),
            ctypes.c_float(mse_scale), _ptr(gloss), _ptr(g7), _ptr(dw8), _ptr(db8), _ptr(ws),
            ws.numel(), B, H, W, _stream())
 
@@ -297,5 +319,5 @@ def colsum(g, out):
     _f32(out, "out")
     assert out.numel() == C
     ws = workspace(N.lib.rovr_colsum_workspace(C), g.device)
-    N.call("rovr_colsum", _ptr(g), ld, B * H * W, C, _ptr(out), _ptr(ws), ws.numel(), _stream())
+    _launch("rovr_colsum", _ptr(g), ld, B * H * W, C, _ptr(out), _ptr(ws), ws.numel(), _stream())
     return out

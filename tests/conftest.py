@@ -16,6 +16,10 @@ for p in (PKG, ORACLE, ROOT):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    # the PyTorch checker must be true fp32: no TF32 in its convolutions / matmuls
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 
 
 @pytest.fixture(scope="session")

@@ -265,8 +265,8 @@ def test_tail(B, H, W):
     b8r = b8.clone().requires_grad_(True)
     ref = torch.sigmoid(F.conv2d(y7r, w8r, b8r))
     lref = F.mse_loss(ref, tgt)
-    _report("tail_fwd", out, ref.detach(), 1e-5)
-    assert abs(loss.item() - lref.item()) < 1e-5 * max(1.0, abs(lref.item()))
+    _report("tail_fwd", out, ref.detach(), 1e-4)
+    assert abs(loss.item() - lref.item()) < 1e-4 * max(1.0, abs(lref.item()))
     # backward driven by the fused loss
     g7 = torch.empty_like(y7)
     dw8 = torch.empty((3, 64), device=dev)
