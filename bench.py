@@ -292,6 +292,13 @@ def run_cuda(args, rank, local_rank, world):
             if name in names:
                 dur[k] += ms
                 cnt[k] += 1
+    # average duration of every call position inside a step (the launch order is fixed)
+    per_step = len(prof) // max(args.steps, 1)
+    call_table = []
+    if per_step * args.steps == len(prof):
+        for i in range(per_step):
+            ms = sum(prof[s * per_step + i][1].elapsed_time(prof[s * per_step + i][2]) for s in range(args.steps))
+            call_table.append([prof[i][0].replace("rovr_", ""), round(ms / args.steps * 1e3, 1)])
     macs = algorithmic_macs_per_frame()
     frames_rank0 = B_PER_GPU * args.steps
     kc = {}
@@ -335,7 +342,7 @@ def run_cuda(args, rank, local_rank, world):
             "clocks": clocks, "roofline": roofline, "kernel_classes": kc,
             "model_tflops": total_flops_per_frame * value / world / 1e12,
             "model_frac_of_peak": total_flops_per_frame * value / world / 1e12 / peaks["tensor_tflops"],
-            "cpu_baseline": cpu_base}
+            "cpu_baseline": cpu_base, "calls_us": call_table}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

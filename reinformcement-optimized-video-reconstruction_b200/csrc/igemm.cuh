@@ -14,15 +14,23 @@
 //   * its data gradient                 4 taps gathered through a 5-D strided view of dy
 //   * 1x1 convolutions / plain GEMMs    1 tap
 //
-// Data movement: activations are fetched by TMA (cp.async.bulk.tensor.5d) as a [rows<=128][bk]
-// box of a (C, d1, d2, d3, d4) tensor map; out-of-bounds coordinates (the 3x3 halo, ragged edge
-// tiles, padded batch) are zero-filled by the TMA unit, which is exactly the conv zero padding.
-// Both operands land in shared memory in the 128/64/32-byte swizzled K-major layout that
-// tcgen05.mma reads directly. Accumulators live in TMEM (2 stages x n_tile fp32 columns) so the
-// epilogue of tile i overlaps the main loop of tile i+1.
+// Data movement
+//   loads   : TMA (cp.async.bulk.tensor.5d) fetches a [rows<=128][bk] box of a (C, d1..d4) tensor
+//             map per tap; out-of-bounds coordinates (the 3x3 halo, ragged edge tiles, padded
+//             batch) are zero-filled by the TMA unit — exactly the conv zero padding. Operands
+//             land in the 128/64/32-byte swizzled K-major layout tcgen05.mma reads directly. A
+//             pipeline stage holds `tps` (tap, k-chunk) sub-tiles so that thin layers (Cin = 16)
+//             still move tens of KB per barrier round trip.
+//   compute : accumulators live in TMEM (2 stages x n_tile fp32 columns): the epilogue of tile i
+//             overlaps the main loop of tile i+1.
+//   stores  : the epilogue converts 64-channel column blocks to bf16 into a swizzled smem staging
+//             tile and a TMA store (cp.async.bulk.tensor...global.shared::cta) writes it out, so
+//             global writes are full 128-byte lines and ragged tiles are clipped by the TMA unit.
+//             The ReLU mask of dgrad (the forward activation at the same coordinates) is
+//             prefetched by TMA into smem the same way.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU/mask -> bf16 -> global).
+// warps 2..5 = epilogue.
 #pragma once
 #include "ptx.cuh"
 
@@ -31,37 +39,69 @@ namespace rovr {
 constexpr int IG_MAX_STAGES = 8;
 constexpr int IG_MAX_TAPS = 9;
 constexpr int IG_THREADS = 192;
+constexpr int IG_EPI_THREADS = 128;
 
 enum : int { IG_EPI_PLAIN = 0, IG_EPI_PIXSHUF = 1 };
 
 struct IgemmParams {
-  int dimM[4];            // logical output extent along each tiled dim (for edge masking)
+  int dimM[4];            // logical output extent along each tiled dim (direct fp32 epilogue only)
   int boxM[4];            // tile extent along each dim; rows per tile = prod(boxM) <= 128
   int ntile[4];           // tiles per dim
-  long long ostride[4];   // output element stride per dim
-  long long mstride[4];   // mask element stride per dim
+  long long ostride[4];   // output element stride per dim (direct fp32 epilogue only)
   int ntaps;
   int tap_off[IG_MAX_TAPS][4];
   int cin;                // K extent per tap (multiple of bk)
-  int bk;                 // K elements per pipeline stage: 16 / 32 / 64  (swizzle 32/64/128 B)
+  int bk;                 // K elements per sub-tile: 16 / 32 / 64  (swizzle 32/64/128 B)
+  int tps;                // (tap, k-chunk) sub-tiles per pipeline stage
   int n_tile;             // N per tile, multiple of 16, <= 256
   int n_tiles_n;
-  int n_total;            // valid N (multiple of 16)
+  int n_total;            // valid N (multiple of cw)
   int stages;
   int tmem_cols;          // power of two >= 2*n_tile, >= 32
   int epi_mode;
+  int cw;                 // epilogue column-block width: 16 / 32 / 64 channels
   int relu;
+  int has_mask;
   int bias_mod;           // bias index = n % bias_mod
   int shuf_cout;          // pixel-shuffle: channels per quadrant
-  long long shuf_sy, shuf_sx;
   const float* bias;      // may be null
-  __nv_bfloat16* out;
-  const __nv_bfloat16* mask;  // may be null: out *= (mask > 0)
-  float* out_f32;         // optional fp32 output instead of bf16 (plain mode only)
+  float* out_f32;         // non-null: direct fp32 epilogue (plain mode) instead of the TMA store
 };
+
+// ---- TMA store / bulk-group helpers ------------------------------------------------------------
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int c1,
+                                             int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(IG_EPI_THREADS) : "memory");
+}
+// byte offset of 16-byte chunk `j` of row `m` in a TMA-swizzled tile whose rows are `rowb` bytes
+__device__ __forceinline__ uint32_t swz_off(int m, int j, int rowb) {
+  const uint32_t a = static_cast<uint32_t>(m) * rowb + static_cast<uint32_t>(j) * 16u;
+  const uint32_t msk = (rowb == 128) ? 7u : ((rowb == 64) ? 3u : 1u);
+  return a ^ (((a >> 7) & msk) << 4);
+}
 
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmMask,
              const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is what SWIZZLE_128B tiles need.
@@ -71,27 +111,37 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int lane = threadIdx.x & 31;
 
   const int sw = p.bk * 2;  // bytes per operand row == swizzle span
-  int rows = p.boxM[0] * p.boxM[1] * p.boxM[2] * p.boxM[3];
+  const int rows = p.boxM[0] * p.boxM[1] * p.boxM[2] * p.boxM[3];
   const uint32_t a_bytes = 128u * sw;  // always reserve the full 128-row tile
   const uint32_t b_bytes = static_cast<uint32_t>(p.n_tile) * sw;
-  const uint32_t stage_bytes = a_bytes + b_bytes;  // multiples of 1024 when sw=128
-  const uint32_t tx_bytes = static_cast<uint32_t>(rows) * sw + b_bytes;
+  const uint32_t sub_bytes = a_bytes + b_bytes;
+  const uint32_t stage_bytes = sub_bytes * p.tps;
+  const uint32_t sub_tx = static_cast<uint32_t>(rows) * sw + b_bytes;
+  const int epi_rowb = p.cw * 2;
+  const uint32_t stg_bytes = 128u * epi_rowb;
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  uint8_t* stg_base = smem + static_cast<size_t>(p.stages) * stage_bytes;       // 2 staging tiles
+  stg_base += (1024u - (smem_u32(stg_base) & 1023u)) & 1023u;                    // swizzle alignment
+  uint8_t* msk_base = stg_base + 2 * stg_bytes;                                  // 2 mask tiles
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(msk_base + (p.has_mask ? 2 * stg_bytes : 0));
   uint64_t* empty_bar = full_bar + IG_MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + IG_MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* mfull_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mfull_bar + 2);
   float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int m_tiles = p.ntile[0] * p.ntile[1] * p.ntile[2] * p.ntile[3];
   const int total_tiles = m_tiles * p.n_tiles_n;
   const int kchunks = p.cin / p.bk;
   const int k_iters = p.ntaps * kchunks;
+  const int s_iters = (k_iters + p.tps - 1) / p.tps;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    if (p.has_mask) tma_prefetch_desc(&tmMask);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -99,6 +149,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 4);
+      mbar_init(&mfull_bar[a], 1);
     }
     mbar_fence_init();
   }
@@ -124,18 +175,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           org[j] = (mt % p.ntile[j]) * p.boxM[j];
           mt /= p.ntile[j];
         }
-        for (int t = 0; t < p.ntaps; ++t) {
-          for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(&empty_bar[s], ph ^ 1u, 0x100u + s);
-            uint8_t* a_dst = smem + static_cast<size_t>(s) * stage_bytes;
-            uint8_t* b_dst = a_dst + a_bytes;
-            mbar_expect_tx(&full_bar[s], tx_bytes);
+        for (int si = 0; si < s_iters; ++si) {
+          const int it0 = si * p.tps;
+          const int nsub = (k_iters - it0) < p.tps ? (k_iters - it0) : p.tps;
+          mbar_wait(&empty_bar[s], ph ^ 1u, 0x100u + s);
+          uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
+          mbar_expect_tx(&full_bar[s], sub_tx * nsub);
+          for (int u = 0; u < nsub; ++u) {
+            const int it = it0 + u;
+            const int t = it / kchunks;
+            const int kc = it - t * kchunks;
+            uint8_t* a_dst = st + static_cast<size_t>(u) * sub_bytes;
             tma_load_5d(&tmA, &full_bar[s], a_dst, kc * p.bk, org[0] + p.tap_off[t][0],
                         org[1] + p.tap_off[t][1], org[2] + p.tap_off[t][2],
                         org[3] + p.tap_off[t][3]);
-            tma_load_2d(&tmB, &full_bar[s], b_dst, t * p.cin + kc * p.bk, nt * p.n_tile);
-            if (++s == p.stages) { s = 0; ph ^= 1u; }
+            tma_load_2d(&tmB, &full_bar[s], a_dst + a_bytes, t * p.cin + kc * p.bk, nt * p.n_tile);
           }
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -144,6 +200,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, p.n_tile, 0, 0);
       const uint32_t sbo = 8u * sw;
+      const int ksteps = p.bk >> 4;
       int s = 0;
       uint32_t ph = 0;
       int acc = 0;
@@ -152,16 +209,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(&tempty_bar[acc], aph ^ 1u, 0x200u + acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
-        for (int it = 0; it < k_iters; ++it) {
+        uint32_t accum = 0;
+        for (int si = 0; si < s_iters; ++si) {
+          const int it0 = si * p.tps;
+          const int nsub = (k_iters - it0) < p.tps ? (k_iters - it0) : p.tps;
           mbar_wait(&full_bar[s], ph, 0x300u + s);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-          const uint32_t b_addr = a_addr + a_bytes;
-          const int ksteps = p.bk >> 4;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = umma_smem_desc(a_addr + k * 32u, 0u, sbo, sw);
-            const uint64_t bd = umma_smem_desc(b_addr + k * 32u, 0u, sbo, sw);
-            umma_bf16(d_tmem, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          const uint32_t st = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+          for (int u = 0; u < nsub; ++u) {
+            const uint32_t a_addr = st + static_cast<uint32_t>(u) * sub_bytes;
+            const uint32_t b_addr = a_addr + a_bytes;
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ad = umma_smem_desc(a_addr + k * 32u, 0u, sbo, sw);
+              const uint64_t bd = umma_smem_desc(b_addr + k * 32u, 0u, sbo, sw);
+              umma_bf16(d_tmem, ad, bd, idesc, accum);
+              accum = 1u;
+            }
           }
           umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
           if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -174,86 +237,157 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ================================ epilogue ====================================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
     const int m = quarter * 32 + lane;
+    const bool elected = (threadIdx.x == 64);
+    const int nblk = p.n_tile / p.cw;
+    const int chunks = p.cw >> 4;
     int acc = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles_n;
-      int mt = tile / p.n_tiles_n;
-      bool valid = m < rows;
-      long long obase = 0, mbase = 0;
-      {
-        int mm = m;
+
+    if (p.out_f32 != nullptr) {
+      // ---- direct fp32 epilogue (small GEMMs whose consumer wants fp32) ----
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles_n;
+        int mt = tile / p.n_tiles_n;
+        bool valid = m < rows;
+        long long obase = 0;
+        {
+          int mm = m;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int org = (mt % p.ntile[j]) * p.boxM[j];
-          mt /= p.ntile[j];
-          const int pj = org + (mm % p.boxM[j]);
-          mm /= p.boxM[j];
-          valid = valid && (pj < p.dimM[j]);
-          obase += static_cast<long long>(pj) * p.ostride[j];
-          mbase += static_cast<long long>(pj) * p.mstride[j];
+          for (int j = 0; j < 4; ++j) {
+            const int org = (mt % p.ntile[j]) * p.boxM[j];
+            mt /= p.ntile[j];
+            const int pj = org + (mm % p.boxM[j]);
+            mm /= p.boxM[j];
+            valid = valid && (pj < p.dimM[j]);
+            obase += static_cast<long long>(pj) * p.ostride[j];
+          }
         }
-      }
-      mbar_wait(&tfull_bar[acc], aph, 0x400u + acc);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                             static_cast<uint32_t>(acc * p.n_tile);
-      const int nchunks = p.n_tile >> 4;
-      for (int c = 0; c < nchunks; ++c) {
-        const int n0 = nt * p.n_tile + c * 16;
-        if (n0 >= p.n_total) break;  // uniform across the CTA
-        uint32_t v[16];
-        tmem_ld16(t_row + static_cast<uint32_t>(c * 16), v);
-        tmem_ld_wait();
-        if (valid) {
-          float f[16];
+        mbar_wait(&tfull_bar[acc], aph, 0x400u + acc);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>(acc * p.n_tile);
+        for (int c = 0; c < (p.n_tile >> 4); ++c) {
+          const int n0 = nt * p.n_tile + c * 16;
+          uint32_t v[16];
+          tmem_ld16(t_row + static_cast<uint32_t>(c * 16), v);
+          tmem_ld_wait();
+          if (valid) {
+            float4* op = reinterpret_cast<float4*>(p.out_f32 + obase + n0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            f[j] = __uint_as_float(v[j]) + sbias[n0 + j];
-            if (p.relu) f[j] = fmaxf(f[j], 0.f);
-          }
-          long long off;
-          if (p.epi_mode == IG_EPI_PIXSHUF) {
-            const int q = n0 / p.shuf_cout;
-            off = obase + (q >> 1) * p.shuf_sy + (q & 1) * p.shuf_sx + (n0 - q * p.shuf_cout);
-          } else {
-            off = obase + n0;
-          }
-          if (p.mask) {
-            const uint4* mp = reinterpret_cast<const uint4*>(p.mask + mbase + n0);
-            const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
-            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            for (int j = 0; j < 4; ++j) {
+              float f[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (!(bf16_lo(mw[j]) > 0.f)) f[2 * j] = 0.f;
-              if (!(bf16_hi(mw[j]) > 0.f)) f[2 * j + 1] = 0.f;
+              for (int e = 0; e < 4; ++e) {
+                f[e] = __uint_as_float(v[4 * j + e]) + sbias[n0 + 4 * j + e];
+                if (p.relu) f[e] = fmaxf(f[e], 0.f);
+              }
+              op[j] = make_float4(f[0], f[1], f[2], f[3]);
             }
           }
-          if (p.out_f32) {
-            float4* op = reinterpret_cast<float4*>(p.out_f32 + off);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) { acc = 0; aph ^= 1u; }
+      }
+    } else {
+      // ---- bf16 epilogue: TMEM -> regs -> swizzled smem staging -> TMA store ----
+      // gb counts column blocks handled by this CTA; staging / mask buffers are gb & 1.
+      const int my_tiles = (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                           static_cast<int>(gridDim.x);
+      const long long total_blocks = static_cast<long long>(my_tiles) * nblk;
+      const uint32_t mask_tx = static_cast<uint32_t>(rows) * epi_rowb;
+
+      // coordinates of column block `g` (in this CTA's sequence)
+      auto block_coords = [&](long long g, int* c) {
+        const int tile = static_cast<int>(blockIdx.x) + static_cast<int>(g / nblk) * static_cast<int>(gridDim.x);
+        const int cb = static_cast<int>(g % nblk);
+        const int nt = tile % p.n_tiles_n;
+        int mt = tile / p.n_tiles_n;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-            uint4 o0, o1;
-            o0.x = pack_bf16x2(f[0], f[1]);
-            o0.y = pack_bf16x2(f[2], f[3]);
-            o0.z = pack_bf16x2(f[4], f[5]);
-            o0.w = pack_bf16x2(f[6], f[7]);
-            o1.x = pack_bf16x2(f[8], f[9]);
-            o1.y = pack_bf16x2(f[10], f[11]);
-            o1.z = pack_bf16x2(f[12], f[13]);
-            o1.w = pack_bf16x2(f[14], f[15]);
-            uint4* op = reinterpret_cast<uint4*>(p.out + off);
-            op[0] = o0;
-            op[1] = o1;
+        for (int j = 0; j < 4; ++j) {
+          c[1 + j] = (mt % p.ntile[j]) * p.boxM[j];
+          mt /= p.ntile[j];
+        }
+        const int n0 = nt * p.n_tile + cb * p.cw;
+        if (p.epi_mode == IG_EPI_PIXSHUF) {
+          const int q = n0 / p.shuf_cout;
+          c[0] = n0 - q * p.shuf_cout;
+          c[1] += q & 1;
+          c[3] += q >> 1;
+        } else {
+          c[0] = n0;
+        }
+      };
+      auto issue_mask = [&](long long g) {
+        int c[5];
+        block_coords(g, c);
+        const int sb = static_cast<int>(g & 1);
+        mbar_expect_tx(&mfull_bar[sb], mask_tx);
+        tma_load_5d(&tmMask, &mfull_bar[sb], msk_base + sb * stg_bytes, c[0], c[1], c[2], c[3], c[4]);
+      };
+      if (p.has_mask && elected) {
+        if (total_blocks > 0) issue_mask(0);
+        if (total_blocks > 1) issue_mask(1);
+      }
+      long long gb = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles_n;
+        mbar_wait(&tfull_bar[acc], aph, 0x400u + acc);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>(acc * p.n_tile);
+        for (int cb = 0; cb < nblk; ++cb, ++gb) {
+          const int sb = static_cast<int>(gb & 1);
+          uint8_t* stg = stg_base + sb * stg_bytes;
+          const uint8_t* msk = msk_base + sb * stg_bytes;
+          if (p.has_mask) mbar_wait(&mfull_bar[sb], static_cast<uint32_t>((gb >> 1) & 1), 0x800u + sb);
+          if (elected) bulk_wait_read<1>();  // the store that last read staging[sb] has drained
+          epi_bar_sync();
+          const int nloc = cb * p.cw;            // column offset inside the tile
+          const int nglb = nt * p.n_tile + nloc;  // global column (bias index)
+          for (int ch = 0; ch < chunks; ++ch) {
+            uint32_t v[16];
+            tmem_ld16(t_row + static_cast<uint32_t>(nloc + ch * 16), v);
+            tmem_ld_wait();
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              f[j] = __uint_as_float(v[j]) + sbias[nglb + ch * 16 + j];
+              if (p.relu) f[j] = fmaxf(f[j], 0.f);
+            }
+            const uint32_t o0 = swz_off(m, ch * 2, epi_rowb), o1 = swz_off(m, ch * 2 + 1, epi_rowb);
+            if (p.has_mask) {
+              const uint4 m0 = *reinterpret_cast<const uint4*>(msk + o0);
+              const uint4 m1 = *reinterpret_cast<const uint4*>(msk + o1);
+              const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (!(bf16_lo(mw[j]) > 0.f)) f[2 * j] = 0.f;
+                if (!(bf16_hi(mw[j]) > 0.f)) f[2 * j + 1] = 0.f;
+              }
+            }
+            *reinterpret_cast<uint4*>(stg + o0) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                             pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            *reinterpret_cast<uint4*>(stg + o1) = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                                                             pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+          }
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
+          epi_bar_sync();
+          if (elected) {
+            int c[5];
+            block_coords(gb, c);
+            tma_store_5d(&tmOut, stg, c[0], c[1], c[2], c[3], c[4]);
+            bulk_commit();
+            if (p.has_mask && gb + 2 < total_blocks) issue_mask(gb + 2);  // mask[sb] is free again
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) { acc = 0; aph ^= 1u; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) { acc = 0; aph ^= 1u; }
+      if (elected) bulk_wait_all<0>();
     }
   }
 
@@ -265,11 +399,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
-// Shared memory the kernel needs for a given configuration (host side).
-inline size_t igemm_smem_bytes(int bk, int n_tile, int stages, int n_total) {
-  const size_t sw = static_cast<size_t>(bk) * 2;
-  const size_t stage = 128 * sw + static_cast<size_t>(n_tile) * sw;
-  return 1024 + stages * stage + (2 * IG_MAX_STAGES + 4) * 8 + 16 + static_cast<size_t>(n_total) * 4 + 64;
+// Fixed (non-pipeline) shared memory of a configuration (host side).
+inline size_t igemm_fixed_smem(int cw, int has_mask, int n_total) {
+  const size_t stg = 128 * static_cast<size_t>(cw) * 2;
+  return 2048 + 2 * stg + (has_mask ? 2 * stg : 0) + (2 * IG_MAX_STAGES + 6) * 8 + 16 +
+         static_cast<size_t>(n_total) * 4 + 64;
+}
+inline size_t igemm_stage_bytes(int bk, int n_tile, int tps) {
+  return (128 + static_cast<size_t>(n_tile)) * bk * 2 * tps;
 }
 
 }  // namespace rovr

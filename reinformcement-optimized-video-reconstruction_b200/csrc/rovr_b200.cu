@@ -208,23 +208,6 @@ static void pick_patch(int W, int H, int B, int max_rows, int* tw_o, int* th_o, 
   *nb_o = bnb;
 }
 
-static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmParams& p,
-                        cudaStream_t st, const char* what) {
-  const size_t stage = (128 + static_cast<size_t>(p.n_tile)) * p.bk * 2;
-  int stages = static_cast<int>((200 * 1024) / stage);
-  stages = std::max(2, std::min(stages, IG_MAX_STAGES));
-  p.stages = stages;
-  p.tmem_cols = pow2_at_least(2 * p.n_tile);
-  ROVR_REQUIRE(p.tmem_cols <= 512, "n_tile %d too large for TMEM double buffering", p.n_tile);
-  ROVR_REQUIRE(p.n_total <= 4096, "n_total too large for the bias stage");
-  const size_t smem = igemm_smem_bytes(p.bk, p.n_tile, stages, p.n_total);
-  ROVR_REQUIRE(smem <= 227 * 1024, "igemm smem %zu exceeds 227 KB", smem);
-  const long long m_tiles = 1ll * p.ntile[0] * p.ntile[1] * p.ntile[2] * p.ntile[3];
-  const long long tiles = m_tiles * p.n_tiles_n;
-  const int grid = static_cast<int>(std::min<long long>(tiles, g_dev.sms));
-  igemm_kernel<<<grid, IG_THREADS, smem, st>>>(tmA, tmB, p);
-  return launch_check(what);
-}
 
 // ------------------------------------------------------------------------------------------------
 // packing / repacking
@@ -290,375 +273,8 @@ extern "C" int rovr_repack_convT2x2_dgrad(const float* w, void* wk, int Cin, int
   return repack(w, wk, Cin, 4, Cout, 1ll * Cout * 4, 1, 4, Cin, Cout, stream);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Conv2d 3x3 pad 1: forward and data gradient share one code path (the tap table differs)
-// ------------------------------------------------------------------------------------------------
-static int conv3x3_common(const void* x, int x_ld, const void* wk, const float* bias, void* y,
-                          int y_ld, const void* mask, int mask_ld, int B, int H, int W, int Cin,
-                          int Cout, int relu, bool flip, void* stream, const char* what) {
-  if (int rc = ensure_device()) return rc;
-  ROVR_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0, "%s: Cin=%d Cout=%d must be multiples of 16", what,
-               Cin, Cout);
-  ROVR_REQUIRE(x_ld % 8 == 0 && y_ld % 8 == 0, "%s: ld must be a multiple of 8", what);
-  int tw, th, nb;
-  pick_patch(W, H, B, 128, &tw, &th, &nb);
-  IgemmParams p;
-  memset(&p, 0, sizeof(p));
-  p.bk = pick_bk(Cin);
-  const int sw = p.bk * 2;
-  p.dimM[0] = W; p.dimM[1] = H; p.dimM[2] = B; p.dimM[3] = 1;
-  p.boxM[0] = tw; p.boxM[1] = th; p.boxM[2] = nb; p.boxM[3] = 1;
-  p.ntile[0] = ceil_div(W, tw); p.ntile[1] = ceil_div(H, th); p.ntile[2] = ceil_div(B, nb); p.ntile[3] = 1;
-  p.ostride[0] = y_ld; p.ostride[1] = 1ll * W * y_ld; p.ostride[2] = 1ll * H * W * y_ld; p.ostride[3] = 0;
-  p.mstride[0] = mask_ld; p.mstride[1] = 1ll * W * mask_ld; p.mstride[2] = 1ll * H * W * mask_ld; p.mstride[3] = 0;
-  p.ntaps = 9;
-  for (int r = 0; r < 3; ++r)
-    for (int s = 0; s < 3; ++s) {
-      const int t = r * 3 + s;
-      // forward: out(y,x) reads in(y+r-1, x+s-1); dgrad: dx(y,x) reads dy(y+1-r, x+1-s)
-      p.tap_off[t][0] = flip ? (1 - s) : (s - 1);
-      p.tap_off[t][1] = flip ? (1 - r) : (r - 1);
-      p.tap_off[t][2] = 0;
-      p.tap_off[t][3] = 0;
-    }
-  p.cin = Cin;
-  p.n_tile = Cout <= 256 ? Cout : 256;
-  ROVR_REQUIRE(Cout % p.n_tile == 0, "%s: Cout=%d not divisible by n_tile", what, Cout);
-  p.n_tiles_n = Cout / p.n_tile;
-  p.n_total = Cout;
-  p.epi_mode = IG_EPI_PLAIN;
-  p.relu = relu;
-  p.bias = bias;
-  p.bias_mod = Cout;
-  p.out = static_cast<__nv_bfloat16*>(y);
-  p.mask = static_cast<const __nv_bfloat16*>(mask);
-  CUtensorMap tmA, tmB;
-  const long long dims[5] = {Cin, W, H, B, 1};
-  const long long strides[4] = {x_ld, 1ll * W * x_ld, 1ll * H * W * x_ld, 1ll * B * H * W * x_ld};
-  const int box[5] = {p.bk, tw, th, nb, 1};
-  if (int rc = make_map5(&tmA, x, dims, strides, box, sw)) return rc;
-  if (int rc = make_map2(&tmB, wk, Cout, 9ll * Cin, 9ll * Cin, p.n_tile, p.bk, sw)) return rc;
-  return launch_igemm(tmA, tmB, p, static_cast<cudaStream_t>(stream), what);
-}
-
-extern "C" int rovr_conv3x3_fprop(const void* x, int x_ld, const void* wk, const float* bias,
-                                  void* y, int y_ld, int B, int H, int W, int Cin, int Cout,
-                                  int relu, void* stream) {
-  return conv3x3_common(x, x_ld, wk, bias, y, y_ld, nullptr, 0, B, H, W, Cin, Cout, relu, false,
-                        stream, "conv3x3_fprop");
-}
-extern "C" int rovr_conv3x3_dgrad(const void* dy, int dy_ld, const void* wk_d, void* dx, int dx_ld,
-                                  const void* mask, int mask_ld, int B, int H, int W, int Cin,
-                                  int Cout, void* stream) {
-  // a 3x3 conv over dy with Cout input channels producing Cin channels
-  return conv3x3_common(dy, dy_ld, wk_d, nullptr, dx, dx_ld, mask, mask_ld, B, H, W, Cout, Cin, 0,
-                        true, stream, "conv3x3_dgrad");
-}
-
-// ------------------------------------------------------------------------------------------------
-// ConvTranspose2d k2 s2
-// ------------------------------------------------------------------------------------------------
-extern "C" int rovr_convT2x2_fprop(const void* x, int x_ld, const void* wk, const float* bias,
-                                   void* y, int y_ld, int B, int H, int W, int Cin, int Cout,
-                                   int relu, void* stream) {
-  if (int rc = ensure_device()) return rc;
-  ROVR_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0, "convT2x2_fprop: Cin=%d Cout=%d must be multiples of 16", Cin, Cout);
-  ROVR_REQUIRE(x_ld % 8 == 0 && y_ld % 8 == 0, "convT2x2_fprop: ld must be a multiple of 8");
-  // rows = input pixels; B and H merge into one dim because no halo is needed
-  int tw, th, nb;
-  pick_patch(W, B * H, 1, 128, &tw, &th, &nb);
-  IgemmParams p;
-  memset(&p, 0, sizeof(p));
-  p.bk = pick_bk(Cin);
-  const int sw = p.bk * 2;
-  const int BH = B * H;
-  p.dimM[0] = W; p.dimM[1] = BH; p.dimM[2] = 1; p.dimM[3] = 1;
-  p.boxM[0] = tw; p.boxM[1] = th; p.boxM[2] = 1; p.boxM[3] = 1;
-  p.ntile[0] = ceil_div(W, tw); p.ntile[1] = ceil_div(BH, th); p.ntile[2] = 1; p.ntile[3] = 1;
-  // output pixel (b, 2y+qy, 2x+qx): merged row index bh = b*H + y -> output row 2*bh (+qy)
-  p.ostride[0] = 2ll * y_ld;
-  p.ostride[1] = 2ll * (2ll * W) * y_ld;
-  p.ntaps = 1;
-  p.cin = Cin;
-  const int Ntot = 4 * Cout;
-  p.n_tile = Ntot <= 256 ? Ntot : 256;
-  ROVR_REQUIRE(Ntot % p.n_tile == 0, "convT2x2_fprop: 4*Cout=%d not divisible by n_tile", Ntot);
-  p.n_tiles_n = Ntot / p.n_tile;
-  p.n_total = Ntot;
-  p.epi_mode = IG_EPI_PIXSHUF;
-  p.relu = relu;
-  p.bias = bias;
-  p.bias_mod = Cout;
-  p.shuf_cout = Cout;
-  p.shuf_sy = 2ll * W * y_ld;
-  p.shuf_sx = y_ld;
-  p.out = static_cast<__nv_bfloat16*>(y);
-  CUtensorMap tmA, tmB;
-  const long long dims[5] = {Cin, W, BH, 1, 1};
-  const long long strides[4] = {x_ld, 1ll * W * x_ld, 1ll * BH * W * x_ld, 1ll * BH * W * x_ld};
-  const int box[5] = {p.bk, tw, th, 1, 1};
-  if (int rc = make_map5(&tmA, x, dims, strides, box, sw)) return rc;
-  if (int rc = make_map2(&tmB, wk, Ntot, Cin, Cin, p.n_tile, p.bk, sw)) return rc;
-  return launch_igemm(tmA, tmB, p, static_cast<cudaStream_t>(stream), "convT2x2_fprop");
-}
-
-// 5-D view of a [B][2H][2W][ld] tensor as (C, qx, W, qy, B*H)
-static void subpixel_view(int W, int BH, int C, int ld, long long dims[5], long long strides[4]) {
-  dims[0] = C; dims[1] = 2; dims[2] = W; dims[3] = 2; dims[4] = BH;
-  strides[0] = ld;              // qx
-  strides[1] = 2ll * ld;        // W
-  strides[2] = 2ll * W * ld;    // qy
-  strides[3] = 4ll * W * ld;    // merged (b, y)
-}
-
-extern "C" int rovr_convT2x2_dgrad(const void* dy, int dy_ld, const void* wk_d, void* dx, int dx_ld,
-                                   const void* mask, int mask_ld, int B, int H, int W, int Cin,
-                                   int Cout, void* stream) {
-  if (int rc = ensure_device()) return rc;
-  ROVR_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0, "convT2x2_dgrad: Cin=%d Cout=%d must be multiples of 16", Cin, Cout);
-  ROVR_REQUIRE(dy_ld % 8 == 0 && dx_ld % 8 == 0, "convT2x2_dgrad: ld must be a multiple of 8");
-  const int BH = B * H;
-  int tw, th, nb;
-  pick_patch(W, BH, 1, 128, &tw, &th, &nb);
-  IgemmParams p;
-  memset(&p, 0, sizeof(p));
-  p.bk = pick_bk(Cout);
-  const int sw = p.bk * 2;
-  // M-space dims follow the tensor-map coordinate order (qx, W, qy, BH)
-  p.dimM[0] = 1; p.dimM[1] = W; p.dimM[2] = 1; p.dimM[3] = BH;
-  p.boxM[0] = 1; p.boxM[1] = tw; p.boxM[2] = 1; p.boxM[3] = th;
-  p.ntile[0] = 1; p.ntile[1] = ceil_div(W, tw); p.ntile[2] = 1; p.ntile[3] = ceil_div(BH, th);
-  p.ostride[1] = dx_ld; p.ostride[3] = 1ll * W * dx_ld;
-  p.mstride[1] = mask_ld; p.mstride[3] = 1ll * W * mask_ld;
-  p.ntaps = 4;
-  for (int q = 0; q < 4; ++q) {
-    p.tap_off[q][0] = q & 1;   // qx
-    p.tap_off[q][1] = 0;
-    p.tap_off[q][2] = q >> 1;  // qy
-    p.tap_off[q][3] = 0;
-  }
-  p.cin = Cout;
-  p.n_tile = Cin <= 256 ? Cin : 256;
-  ROVR_REQUIRE(Cin % p.n_tile == 0, "convT2x2_dgrad: Cin=%d not divisible by n_tile", Cin);
-  p.n_tiles_n = Cin / p.n_tile;
-  p.n_total = Cin;
-  p.epi_mode = IG_EPI_PLAIN;
-  p.bias_mod = 1;
-  p.out = static_cast<__nv_bfloat16*>(dx);
-  p.mask = static_cast<const __nv_bfloat16*>(mask);
-  CUtensorMap tmA, tmB;
-  long long dims[5], strides[4];
-  subpixel_view(W, BH, Cout, dy_ld, dims, strides);
-  const int box[5] = {p.bk, 1, tw, 1, th};
-  if (int rc = make_map5(&tmA, dy, dims, strides, box, sw)) return rc;
-  if (int rc = make_map2(&tmB, wk_d, Cin, 4ll * Cout, 4ll * Cout, p.n_tile, p.bk, sw)) return rc;
-  return launch_igemm(tmA, tmB, p, static_cast<cudaStream_t>(stream), "convT2x2_dgrad");
-}
-
-// ------------------------------------------------------------------------------------------------
-// plain GEMM
-// ------------------------------------------------------------------------------------------------
-extern "C" int rovr_gemm_bf16(const void* x, int x_ld, const void* wk, const float* bias,
-                              void* y_bf16, float* y_f32, int y_ld, int M, int N, int K, int relu,
-                              void* stream) {
-  if (int rc = ensure_device()) return rc;
-  ROVR_REQUIRE(K % 16 == 0 && N % 16 == 0, "gemm: K=%d N=%d must be multiples of 16", K, N);
-  ROVR_REQUIRE(x_ld % 8 == 0, "gemm: x_ld must be a multiple of 8");
-  ROVR_REQUIRE((y_bf16 != nullptr) != (y_f32 != nullptr), "gemm: exactly one output must be given");
-  IgemmParams p;
-  memset(&p, 0, sizeof(p));
-  p.bk = pick_bk(K);
-  const int sw = p.bk * 2;
-  p.dimM[0] = M; p.dimM[1] = 1; p.dimM[2] = 1; p.dimM[3] = 1;
-  p.boxM[0] = 128; p.boxM[1] = 1; p.boxM[2] = 1; p.boxM[3] = 1;
-  p.ntile[0] = ceil_div(M, 128); p.ntile[1] = 1; p.ntile[2] = 1; p.ntile[3] = 1;
-  p.ostride[0] = y_ld;
-  p.ntaps = 1;
-  p.cin = K;
-  int n_tile = 256;
-  while (N % n_tile != 0) n_tile -= 16;
-  p.n_tile = n_tile;
-  p.n_tiles_n = N / n_tile;
-  p.n_total = N;
-  p.epi_mode = IG_EPI_PLAIN;
-  p.relu = relu;
-  p.bias = bias;
-  p.bias_mod = N;
-  p.out = static_cast<__nv_bfloat16*>(y_bf16);
-  p.out_f32 = y_f32;
-  CUtensorMap tmA, tmB;
-  const long long dims[5] = {K, M, 1, 1, 1};
-  const long long strides[4] = {x_ld, 1ll * M * x_ld, 1ll * M * x_ld, 1ll * M * x_ld};
-  const int box[5] = {p.bk, 128, 1, 1, 1};
-  if (int rc = make_map5(&tmA, x, dims, strides, box, sw)) return rc;
-  if (int rc = make_map2(&tmB, wk, N, K, K, p.n_tile, p.bk, sw)) return rc;
-  return launch_igemm(tmA, tmB, p, static_cast<cudaStream_t>(stream), "gemm_bf16");
-}
-
-// ------------------------------------------------------------------------------------------------
-// weight gradients
-// ------------------------------------------------------------------------------------------------
-struct WgradPlan {
-  WgradParams p;
-  int blk;
-  size_t ws_bytes;
-  int grid;
-  size_t smem;
-};
-
-// m_total: channels of the un-shifted operand A; c_total: channels of the tapped operand B.
-static int plan_wgrad(WgradPlan* pl, int m_total, int c_total, int taps, const int box[4],
-                      const int ntile[4], int sms) {
-  WgradParams& p = pl->p;
-  memset(&p, 0, sizeof(p));
-  int blk = 64;
-  while (blk > 16 && (m_total % blk != 0 || c_total % blk != 0)) blk >>= 1;
-  ROVR_REQUIRE(m_total % blk == 0 && c_total % blk == 0, "wgrad: channel counts %d/%d not multiples of 16", m_total, c_total);
-  pl->blk = blk;
-  p.blk = blk;
-  int rows = 1;
-  for (int j = 0; j < 4; ++j) {
-    p.boxM[j] = box[j];
-    p.ntile[j] = ntile[j];
-    rows *= box[j];
-  }
-  p.kp = (rows + 15) / 16 * 16;
-  p.m_total = m_total;
-  p.m_chunks = ceil_div(m_total, 128);
-  p.a_blocks = std::min(128, m_total) / blk;
-  p.taps_total = taps;
-  p.c_total = c_total;
-  // taps per CTA: all of them if the accumulators fit in 512 TMEM columns, else one kernel row /
-  // half of the sub-pixels
-  int tpg = taps;
-  if (taps * std::min(c_total, blk) > 512 || taps * c_total > 512) tpg = (taps == 9) ? 3 : 2;
-  int cb = c_total / blk;
-  while (tpg * cb * blk > 512) cb = (cb + 1) / 2;
-  ROVR_REQUIRE((c_total / blk) % cb == 0, "wgrad: channel blocks %d not divisible by group %d", c_total / blk, cb);
-  p.taps_per_group = tpg;
-  p.tap_groups = ceil_div(taps, tpg);
-  p.c_blocks_per_group = cb;
-  p.c_groups = (c_total / blk) / cb;
-  p.k_tiles = ntile[0] * ntile[1] * ntile[2] * ntile[3];
-  const int groups = p.m_chunks * p.tap_groups * p.c_groups;
-  p.n_slices = std::max(1, std::min(p.k_tiles, sms / std::max(1, groups)));
-  const int nblk = tpg * cb;
-  p.tmem_cols = pow2_at_least(nblk * blk);
-  const size_t stage = (128 / blk + nblk) * static_cast<size_t>(p.kp) * blk * 2;
-  int stages = static_cast<int>((200 * 1024) / stage);
-  stages = std::max(2, std::min(stages, WG_MAX_STAGES));
-  p.stages = stages;
-  pl->smem = wgrad_smem_bytes(blk, p.kp, nblk, stages);
-  ROVR_REQUIRE(pl->smem <= 227 * 1024, "wgrad smem %zu exceeds 227 KB", pl->smem);
-  pl->grid = groups * p.n_slices;
-  pl->ws_bytes = static_cast<size_t>(p.n_slices) * m_total * taps * c_total * sizeof(float);
-  return 0;
-}
-
-static void conv3_patch_for_wgrad(int B, int H, int W, int box[4], int ntile[4]) {
-  int tw, th, nb;
-  pick_patch(W, H, B, 64, &tw, &th, &nb);
-  box[0] = tw; box[1] = th; box[2] = nb; box[3] = 1;
-  ntile[0] = ceil_div(W, tw); ntile[1] = ceil_div(H, th); ntile[2] = ceil_div(B, nb); ntile[3] = 1;
-}
-
-extern "C" size_t rovr_conv3x3_wgrad_workspace(int B, int H, int W, int Cin, int Cout) {
-  if (ensure_device()) return 0;
-  int box[4], ntile[4];
-  conv3_patch_for_wgrad(B, H, W, box, ntile);
-  WgradPlan pl;
-  if (plan_wgrad(&pl, Cout, Cin, 9, box, ntile, g_dev.sms)) return 0;
-  return pl.ws_bytes;
-}
-
-extern "C" int rovr_conv3x3_wgrad(const void* dy, int dy_ld, const void* x, int x_ld, float* dw,
-                                  int B, int H, int W, int Cin, int cin_keep, int Cout, void* ws,
-                                  size_t ws_bytes, void* stream) {
-  if (int rc = ensure_device()) return rc;
-  ROVR_REQUIRE(dy_ld % 8 == 0 && x_ld % 8 == 0, "conv3x3_wgrad: ld must be a multiple of 8");
-  int box[4], ntile[4];
-  conv3_patch_for_wgrad(B, H, W, box, ntile);
-  WgradPlan pl;
-  if (int rc = plan_wgrad(&pl, Cout, Cin, 9, box, ntile, g_dev.sms)) return rc;
-  ROVR_REQUIRE(ws_bytes >= pl.ws_bytes, "conv3x3_wgrad: workspace %zu < %zu", ws_bytes, pl.ws_bytes);
-  WgradParams& p = pl.p;
-  for (int r = 0; r < 3; ++r)
-    for (int s = 0; s < 3; ++s) {
-      p.tap_off[r * 3 + s][0] = s - 1;
-      p.tap_off[r * 3 + s][1] = r - 1;
-    }
-  p.partial = static_cast<float*>(ws);
-  const int sw = pl.blk * 2;
-  CUtensorMap tmA, tmB;
-  const long long dimsA[5] = {Cout, W, H, B, 1};
-  const long long stA[4] = {dy_ld, 1ll * W * dy_ld, 1ll * H * W * dy_ld, 1ll * B * H * W * dy_ld};
-  const long long dimsB[5] = {Cin, W, H, B, 1};
-  const long long stB[4] = {x_ld, 1ll * W * x_ld, 1ll * H * W * x_ld, 1ll * B * H * W * x_ld};
-  const int bx[5] = {pl.blk, box[0], box[1], box[2], 1};
-  if (int rc = make_map5(&tmA, dy, dimsA, stA, bx, sw)) return rc;
-  if (int rc = make_map5(&tmB, x, dimsB, stB, bx, sw)) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  wgrad_kernel<<<pl.grid, WG_THREADS, pl.smem, st>>>(tmA, tmB, p);
-  if (int rc = launch_check("conv3x3_wgrad")) return rc;
-  // partial [slice][co][t][ci] -> dw[co][ci_keep][t]
-  const long long n = 1ll * Cout * 9 * Cin;
-  wgrad_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
-      p.partial, dw, p.n_slices, Cout, 9, Cin, cin_keep, 9ll * cin_keep, 1, 9, 0);
-  return launch_check("wgrad_reduce");
-}
-
-static void convT_patch_for_wgrad(int BH, int W, int box[4], int ntile[4]) {
-  int tw, th, nb;
-  pick_patch(W, BH, 1, 64, &tw, &th, &nb);
-  box[0] = 1; box[1] = tw; box[2] = 1; box[3] = th;
-  ntile[0] = 1; ntile[1] = ceil_div(W, tw); ntile[2] = 1; ntile[3] = ceil_div(BH, th);
-}
-
-extern "C" size_t rovr_convT2x2_wgrad_workspace(int B, int H, int W, int Cin, int Cout) {
-  if (ensure_device()) return 0;
-  int box[4], ntile[4];
-  convT_patch_for_wgrad(B * H, W, box, ntile);
-  WgradPlan pl;
-  if (plan_wgrad(&pl, Cin, Cout, 4, box, ntile, g_dev.sms)) return 0;
-  return pl.ws_bytes;
-}
-
-extern "C" int rovr_convT2x2_wgrad(const void* dy, int dy_ld, const void* x, int x_ld, float* dw,
-                                   int B, int H, int W, int Cin, int Cout, void* ws, size_t ws_bytes,
-                                   void* stream) {
-  if (int rc = ensure_device()) return rc;
-  ROVR_REQUIRE(dy_ld % 8 == 0 && x_ld % 8 == 0, "convT2x2_wgrad: ld must be a multiple of 8");
-  const int BH = B * H;
-  int box[4], ntile[4];
-  convT_patch_for_wgrad(BH, W, box, ntile);
-  WgradPlan pl;
-  if (int rc = plan_wgrad(&pl, Cin, Cout, 4, box, ntile, g_dev.sms)) return rc;
-  ROVR_REQUIRE(ws_bytes >= pl.ws_bytes, "convT2x2_wgrad: workspace %zu < %zu", ws_bytes, pl.ws_bytes);
-  WgradParams& p = pl.p;
-  for (int q = 0; q < 4; ++q) {
-    p.tap_off[q][0] = q & 1;
-    p.tap_off[q][2] = q >> 1;
-  }
-  p.partial = static_cast<float*>(ws);
-  const int sw = pl.blk * 2;
-  CUtensorMap tmA, tmB;
-  // A = x viewed as (Cin, 1, W, 1, BH); B = dy viewed as (Cout, qx, W, qy, BH)
-  const long long dimsA[5] = {Cin, 1, W, 1, BH};
-  const long long stA[4] = {x_ld, x_ld, 1ll * W * x_ld, 1ll * W * x_ld};
-  long long dimsB[5], stB[4];
-  subpixel_view(W, BH, Cout, dy_ld, dimsB, stB);
-  const int bx[5] = {pl.blk, 1, box[1], 1, box[3]};
-  if (int rc = make_map5(&tmA, x, dimsA, stA, bx, sw)) return rc;
-  if (int rc = make_map5(&tmB, dy, dimsB, stB, bx, sw)) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  wgrad_kernel<<<pl.grid, WG_THREADS, pl.smem, st>>>(tmA, tmB, p);
-  if (int rc = launch_check("convT2x2_wgrad")) return rc;
-  // partial [slice][ci][q][co] -> dw[ci][co][q]
-  const long long n = 1ll * Cin * 4 * Cout;
-  wgrad_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
-      p.partial, dw, p.n_slices, Cin, 4, Cout, Cout, 4ll * Cout, 1, 4, 0);
-  return launch_check("wgrad_reduce");
-}
+#include "api_igemm.inc"
+#include "api_wgrad.inc"
 
 // ------------------------------------------------------------------------------------------------
 // pooling
@@ -752,10 +368,10 @@ extern "C" int rovr_tail_bwd(const void* y7, const float* w8, const float* out, 
                                                   static_cast<__nv_bfloat16*>(g7), partial, B, H * W);
   if (int rc = launch_check("tail_bwd")) return rc;
   // columns [0, 192) -> dw8, [192, 195) -> db8
-  reduce_rows_kernel<<<1, 256, 0, st>>>(partial, grid, ncols, 3 * TAIL_C, dw8, 0);
+  reduce_rows_kernel<<<(3 * TAIL_C + 31) / 32, 256, 0, st>>>(partial, grid, ncols, 3 * TAIL_C, dw8, 0);
   if (int rc = launch_check("reduce_rows(dw8)")) return rc;
   // dw8 buffer is [3][64] contiguous; db8 is separate: run a second tiny reduce on the tail columns
-  reduce_rows_kernel<<<1, 32, 0, st>>>(partial + 3 * TAIL_C, grid, ncols, 3, db8, 0);
+  reduce_rows_kernel<<<1, 256, 0, st>>>(partial + 3 * TAIL_C, grid, ncols, 3, db8, 0);
   return launch_check("reduce_rows(db8)");
 }
 
@@ -777,6 +393,6 @@ extern "C" int rovr_colsum(const void* g, int ld, long long npix, int C, float* 
   colsum_partial_kernel<<<grid, threads, threads * 2 * sizeof(float), st>>>(
       static_cast<const __nv_bfloat16*>(g), ld, npix, C, static_cast<float*>(ws));
   if (int rc = launch_check("colsum_partial")) return rc;
-  reduce_rows_kernel<<<(C + 255) / 256, 256, 0, st>>>(static_cast<float*>(ws), grid, C, C, out, 0);
+  reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(static_cast<float*>(ws), grid, C, C, out, 0);
   return launch_check("reduce_rows(colsum)");
 }

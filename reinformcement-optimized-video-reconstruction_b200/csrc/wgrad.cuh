@@ -2,12 +2,15 @@
 //
 //     P[slice][m][t][c] = sum_{pixels p in slice}  A[p][m] * B_t[p][c]
 //
-// A is the un-shifted NHWC bf16 tensor (dy for Conv2d 3x3, x for ConvTranspose2d), B_t the other
-// tensor read at tap offset t (x shifted by the 3x3 tap / dy at the 2x2 sub-pixel). The reduction
-// index is the pixel, which in NHWC is the *strided* dimension, so both operands are fed to the
-// tensor core as MN-major tiles: a TMA box of [kp pixels][blk channels] lands in shared memory as
-// kp rows of `sw` bytes and is described to tcgen05.mma with the MN-major flag — no transposed
-// copy of any activation is ever written to HBM.
+// A is an un-shifted NHWC bf16 tensor, B_t the other tensor read at tap offset t. For Conv2d 3x3
+// either (A = dy, B_t = x shifted by the tap) or, when Cout is narrower than the 128-row MMA,
+// (A = x, B_t = dy shifted by minus the tap) so that all 128 rows do useful work; for
+// ConvTranspose2d A = x and B_t = dy at the 2x2 sub-pixel t. The reduction index is the pixel,
+// which in NHWC is the *strided* dimension, so both operands are fed to the tensor core as
+// MN-major tiles: a TMA box of [kp pixels][blk channels] lands in shared memory as kp rows of
+// `2*blk` bytes and is described to tcgen05.mma with the MN-major flag — no transposed copy of any
+// activation is ever written to HBM. A and B choose their channel-block width (16/32/64)
+// independently, so a 16-channel operand does not force 16-channel boxes on the other side.
 //
 // Work split: a CTA owns one accumulator group (128 rows of m, a tap group, a channel chunk of
 // c — at most 512 TMEM columns) and a contiguous slice of pixel tiles (split-K). Partial sums go
@@ -25,18 +28,19 @@ constexpr int WG_MAX_STAGES = 6;
 constexpr int WG_THREADS = 192;
 
 struct WgradParams {
-  int boxM[4];   // pixel tile extents (rows per K-step kp = prod, multiple of 16, <= 128)
+  int boxM[4];   // pixel tile extents (rows per K-step = prod <= kp)
   int ntile[4];  // pixel tiles per dim
-  int kp;        // rows reserved per block (>= prod(boxM), multiple of 16)
-  int blk;       // channels per block = sw/2 (16/32/64)
-  int a_blocks;  // A blocks loaded per group (M = 128 rows reserved)
+  int kp;        // rows reserved per block (>= prod(boxM), multiple of 16, <= 128)
+  int blk_a;     // channels per A block (16/32/64)
+  int blk_b;     // channels per B block (16/32/64)
+  int a_blocks;  // A blocks actually loaded per group (M = 128 rows are always addressable)
   int m_chunks;  // number of 128-row chunks of m
   int m_total;   // valid m
   int taps_total;          // T
   int taps_per_group;      // taps handled by one CTA
   int tap_groups;
   int tap_off[9][4];
-  int c_total;             // valid c (multiple of blk)
+  int c_total;             // valid c (multiple of blk_b)
   int c_blocks_per_group;  // B channel blocks per tap in one CTA
   int c_groups;
   int n_slices;
@@ -54,14 +58,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int sw = p.blk * 2;
-  const uint32_t blk_bytes = static_cast<uint32_t>(p.kp) * sw;
-  const int m_blocks = 128 / p.blk;  // blocks reserved for A so that M = 128 is addressable
+  const int sw_a = p.blk_a * 2, sw_b = p.blk_b * 2;
+  const uint32_t ablk_bytes = static_cast<uint32_t>(p.kp) * sw_a;
+  const uint32_t bblk_bytes = static_cast<uint32_t>(p.kp) * sw_b;
   const int nblk = p.taps_per_group * p.c_blocks_per_group;
-  const uint32_t a_bytes = static_cast<uint32_t>(m_blocks) * blk_bytes;
-  const uint32_t stage_bytes = a_bytes + static_cast<uint32_t>(nblk) * blk_bytes;
+  const uint32_t a_bytes = static_cast<uint32_t>(128 / p.blk_a) * ablk_bytes;  // = 256 * kp
+  const uint32_t stage_bytes = a_bytes + static_cast<uint32_t>(nblk) * bblk_bytes;
   const int rows = p.boxM[0] * p.boxM[1] * p.boxM[2] * p.boxM[3];
-  const uint32_t tx_bytes = static_cast<uint32_t>(p.a_blocks + nblk) * rows * sw;
+  const uint32_t tx_bytes = static_cast<uint32_t>(p.a_blocks * sw_a + nblk * sw_b) * rows;
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
   uint64_t* empty_bar = full_bar + WG_MAX_STAGES;
@@ -80,7 +84,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int kt0 = static_cast<int>((static_cast<long long>(p.k_tiles) * slice) / p.n_slices);
   const int kt1 = static_cast<int>((static_cast<long long>(p.k_tiles) * (slice + 1)) / p.n_slices);
   const int t_first = tg * p.taps_per_group;
-  const int n_cols = nblk * p.blk;
+  const int n_cols = nblk * p.blk_b;
 
   // Rows of a block that TMA never writes (kp > rows) and A blocks that are never loaded must
   // read as zero / be harmless: zero the whole staging area once.
@@ -122,14 +126,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
         mbar_expect_tx(&full_bar[s], tx_bytes);
         for (int i = 0; i < p.a_blocks; ++i)
-          tma_load_5d(&tmA, &full_bar[s], st + static_cast<size_t>(i) * blk_bytes,
-                      mc * 128 + i * p.blk, org[0], org[1], org[2], org[3]);
+          tma_load_5d(&tmA, &full_bar[s], st + static_cast<size_t>(i) * ablk_bytes,
+                      mc * 128 + i * p.blk_a, org[0], org[1], org[2], org[3]);
         for (int tl = 0; tl < p.taps_per_group; ++tl) {
           const int t = t_first + tl;
           for (int j = 0; j < p.c_blocks_per_group; ++j) {
-            const int c0 = (cg * p.c_blocks_per_group + j) * p.blk;
+            const int c0 = (cg * p.c_blocks_per_group + j) * p.blk_b;
             tma_load_5d(&tmB, &full_bar[s],
-                        st + a_bytes + static_cast<size_t>(tl * p.c_blocks_per_group + j) * blk_bytes,
+                        st + a_bytes + static_cast<size_t>(tl * p.c_blocks_per_group + j) * bblk_bytes,
                         c0, org[0] + p.tap_off[t][0], org[1] + p.tap_off[t][1],
                         org[2] + p.tap_off[t][2], org[3] + p.tap_off[t][3]);
           }
@@ -139,8 +143,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t sbo = 8u * sw;
-      const int blocks_per_mma = 256 / p.blk < nblk ? 256 / p.blk : nblk;
+      const uint32_t sbo_a = 8u * sw_a, sbo_b = 8u * sw_b;
+      const int blocks_per_mma = 256 / p.blk_b < nblk ? 256 / p.blk_b : nblk;
       int s = 0;
       uint32_t ph = 0;
       bool first = true;
@@ -151,14 +155,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const uint32_t b_addr = a_addr + a_bytes;
         const int ksteps = p.kp >> 4;
         for (int k = 0; k < ksteps; ++k) {
-          const uint32_t koff = static_cast<uint32_t>(k) * 16u * sw;
-          const uint64_t ad = umma_smem_desc(a_addr + koff, blk_bytes, sbo, sw);
+          const uint64_t ad = umma_smem_desc(a_addr + static_cast<uint32_t>(k) * 16u * sw_a, ablk_bytes, sbo_a, sw_a);
           for (int b0 = 0; b0 < nblk; b0 += blocks_per_mma) {
             const int nb = (nblk - b0) < blocks_per_mma ? (nblk - b0) : blocks_per_mma;
-            const uint32_t idesc = umma_idesc_bf16(128, nb * p.blk, 1, 1);
-            const uint64_t bd = umma_smem_desc(b_addr + static_cast<uint32_t>(b0) * blk_bytes + koff,
-                                               blk_bytes, sbo, sw);
-            umma_bf16(tmem_base + static_cast<uint32_t>(b0 * p.blk), ad, bd, idesc,
+            const uint32_t idesc = umma_idesc_bf16(128, nb * p.blk_b, 1, 1);
+            const uint64_t bd = umma_smem_desc(
+                b_addr + static_cast<uint32_t>(b0) * bblk_bytes + static_cast<uint32_t>(k) * 16u * sw_b,
+                bblk_bytes, sbo_b, sw_b);
+            umma_bf16(tmem_base + static_cast<uint32_t>(b0 * p.blk_b), ad, bd, idesc,
                       (first && k == 0) ? 0u : 1u);
           }
         }
@@ -188,10 +192,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int j = 0; j < 16; ++j) v[j] = 0u;
       }
       const int col = c * 16;
-      const int b = col / p.blk;                 // block within the group
+      const int b = col / p.blk_b;               // block within the group
       const int tl = b / p.c_blocks_per_group;   // local tap
       const int cj = b - tl * p.c_blocks_per_group;
-      const int cc = (cg * p.c_blocks_per_group + cj) * p.blk + (col - b * p.blk);
+      const int cc = (cg * p.c_blocks_per_group + cj) * p.blk_b + (col - b * p.blk_b);
       const int t = t_first + tl;
       if (m < p.m_total && cc < p.c_total && t < p.taps_total) {
         float4* dst = reinterpret_cast<float4*>(
@@ -212,28 +216,29 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
-// final[m*fs_m + t*fs_t + c*fs_c] = sum_slices P[slice][m][t][c], c < c_keep.
+// final[m*fs_m + t*fs_t + c*fs_c] = sum_slices P[slice][m][t][c], for m < m_keep, c < c_keep.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad,
-                                    int n_slices, int m_total, int taps, int c_total, int c_keep,
-                                    long long fs_m, long long fs_t, long long fs_c, int accumulate) {
+                                    int n_slices, int m_total, int taps, int c_total, int m_keep,
+                                    int c_keep, long long fs_m, long long fs_t, long long fs_c,
+                                    int accumulate) {
   const long long n = static_cast<long long>(m_total) * taps * c_total;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int c = static_cast<int>(i % c_total);
   const int t = static_cast<int>((i / c_total) % taps);
   const int m = static_cast<int>(i / (static_cast<long long>(c_total) * taps));
-  if (c >= c_keep) return;
+  if (c >= c_keep || m >= m_keep) return;
   float s = 0.f;
   for (int k = 0; k < n_slices; ++k) s += partial[static_cast<long long>(k) * n + i];
   float* dst = grad + m * fs_m + t * fs_t + c * fs_c;
   *dst = accumulate ? (*dst + s) : s;
 }
 
-inline size_t wgrad_smem_bytes(int blk, int kp, int nblk, int stages) {
-  const size_t sw = static_cast<size_t>(blk) * 2;
-  const size_t blk_bytes = static_cast<size_t>(kp) * sw;
-  const size_t stage = (128 / blk + nblk) * blk_bytes;
-  return 1024 + stages * stage + (2 * WG_MAX_STAGES + 1) * 8 + 16 + 64;
+inline size_t wgrad_stage_bytes(int kp, int blk_b, int nblk) {
+  return 256 * static_cast<size_t>(kp) + static_cast<size_t>(nblk) * kp * blk_b * 2;
+}
+inline size_t wgrad_smem_bytes(int kp, int blk_b, int nblk, int stages) {
+  return 1024 + stages * wgrad_stage_bytes(kp, blk_b, nblk) + (2 * WG_MAX_STAGES + 1) * 8 + 16 + 64;
 }
 
 }  // namespace rovr
