@@ -163,7 +163,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    {
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -180,58 +180,69 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int nsub = (k_iters - it0) < p.tps ? (k_iters - it0) : p.tps;
           mbar_wait(&empty_bar[s], ph ^ 1u, 0x100u + s);
           uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
-          mbar_expect_tx(&full_bar[s], sub_tx * nsub);
+          if (elect_one_sync()) mbar_expect_tx(&full_bar[s], sub_tx * nsub);
           for (int u = 0; u < nsub; ++u) {
             const int it = it0 + u;
             const int t = it / kchunks;
             const int kc = it - t * kchunks;
             uint8_t* a_dst = st + static_cast<size_t>(u) * sub_bytes;
-            tma_load_5d(&tmA, &full_bar[s], a_dst, kc * p.bk, org[0] + p.tap_off[t][0],
-                        org[1] + p.tap_off[t][1], org[2] + p.tap_off[t][2],
-                        org[3] + p.tap_off[t][3]);
-            tma_load_2d(&tmB, &full_bar[s], a_dst + a_bytes, t * p.cin + kc * p.bk, nt * p.n_tile);
+            if (elect_one_sync()) {
+              tma_load_5d(&tmA, &full_bar[s], a_dst, kc * p.bk, org[0] + p.tap_off[t][0],
+                          org[1] + p.tap_off[t][1], org[2] + p.tap_off[t][2],
+                          org[3] + p.tap_off[t][3]);
+              tma_load_2d(&tmB, &full_bar[s], a_dst + a_bytes, t * p.cin + kc * p.bk, nt * p.n_tile);
+            }
           }
+          __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.n_tile, 0, 0);
-      const uint32_t sbo = 8u * sw;
-      const int ksteps = p.bk >> 4;
-      int s = 0;
-      uint32_t ph = 0;
-      int acc = 0;
-      uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], aph ^ 1u, 0x200u + acc);
+    // The whole warp walks the pipeline with warp-uniform control flow (so that addresses and
+    // descriptors live in uniform registers); lane 0 alone issues tcgen05.mma / tcgen05.commit.
+    const uint32_t idesc = umma_idesc_bf16(128, p.n_tile, 0, 0);
+    const uint64_t dhi = umma_smem_desc(0u, 0u, 8u * sw, sw);  // descriptor minus the address
+    const int ksteps = p.bk >> 4;
+    const uint32_t sub16 = sub_bytes >> 4, a16 = a_bytes >> 4;
+    int s = 0;
+    uint32_t ph = 0;
+    int acc = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], aph ^ 1u, 0x200u + acc);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
+      uint32_t accum = 0;
+      for (int si = 0; si < s_iters; ++si) {
+        const int it0 = si * p.tps;
+        const int nsub = (k_iters - it0) < p.tps ? (k_iters - it0) : p.tps;
+        mbar_wait(&full_bar[s], ph, 0x300u + s);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
-        uint32_t accum = 0;
-        for (int si = 0; si < s_iters; ++si) {
-          const int it0 = si * p.tps;
-          const int nsub = (k_iters - it0) < p.tps ? (k_iters - it0) : p.tps;
-          mbar_wait(&full_bar[s], ph, 0x300u + s);
-          tc_fence_after();
-          const uint32_t st = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+        const uint32_t st16 = smem_u32(smem + static_cast<size_t>(s) * stage_bytes) >> 4;
+        if (elect_one_sync()) {
           for (int u = 0; u < nsub; ++u) {
-            const uint32_t a_addr = st + static_cast<uint32_t>(u) * sub_bytes;
-            const uint32_t b_addr = a_addr + a_bytes;
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t ad = umma_smem_desc(a_addr + k * 32u, 0u, sbo, sw);
-              const uint64_t bd = umma_smem_desc(b_addr + k * 32u, 0u, sbo, sw);
-              umma_bf16(d_tmem, ad, bd, idesc, accum);
-              accum = 1u;
+            const uint32_t ad = st16 + static_cast<uint32_t>(u) * sub16;
+            const uint32_t bd = ad + a16;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k < ksteps) {
+                umma_bf16(d_tmem, dhi | static_cast<uint64_t>(ad + 2u * k),
+                          dhi | static_cast<uint64_t>(bd + 2u * k), idesc, accum);
+                accum = 1u;
+              }
             }
           }
           umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
-          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; aph ^= 1u; }
+        __syncwarp();
+        accum = 1u;
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
+      if (elect_one_sync()) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
+      if (++acc == 2) { acc = 0; aph ^= 1u; }
     }
   } else {
     // ================================ epilogue ====================================

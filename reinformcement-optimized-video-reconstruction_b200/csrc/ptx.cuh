@@ -17,6 +17,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+// One lane of a converged warp (always the same one for a full mask). Guarding single-thread
+// instructions (tcgen05.mma, TMA issue) with elect.sync rather than `lane == 0` lets ptxas keep
+// their operands in uniform registers instead of emitting a per-thread waterfall loop.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // A spin that never hangs the box: after ~2^31 SM cycles (about a second) the waiter records
 // which barrier it was stuck on and gives up (as does every later waiter), so a protocol bug

@@ -111,19 +111,19 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kt = kt0; kt < kt1; ++kt) {
-        int org[4];
-        int r = kt;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kt = kt0; kt < kt1; ++kt) {
+      int org[4];
+      int r = kt;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          org[j] = (r % p.ntile[j]) * p.boxM[j];
-          r /= p.ntile[j];
-        }
-        mbar_wait(&empty_bar[s], ph ^ 1u, 0x500u + s);
-        uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
+      for (int j = 0; j < 4; ++j) {
+        org[j] = (r % p.ntile[j]) * p.boxM[j];
+        r /= p.ntile[j];
+      }
+      mbar_wait(&empty_bar[s], ph ^ 1u, 0x500u + s);
+      uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
+      if (elect_one_sync()) {
         mbar_expect_tx(&full_bar[s], tx_bytes);
         for (int i = 0; i < p.a_blocks; ++i)
           tma_load_5d(&tmA, &full_bar[s], st + static_cast<size_t>(i) * ablk_bytes,
@@ -138,40 +138,54 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         org[2] + p.tap_off[t][2], org[3] + p.tap_off[t][3]);
           }
         }
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t sbo_a = 8u * sw_a, sbo_b = 8u * sw_b;
-      const int blocks_per_mma = 256 / p.blk_b < nblk ? 256 / p.blk_b : nblk;
-      int s = 0;
-      uint32_t ph = 0;
-      bool first = true;
-      for (int kt = kt0; kt < kt1; ++kt) {
-        mbar_wait(&full_bar[s], ph, 0x600u + s);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-        const uint32_t b_addr = a_addr + a_bytes;
-        const int ksteps = p.kp >> 4;
+    // Warp-uniform walk (uniform registers for addresses/descriptors); lane 0 issues.
+    // The N columns of a group are covered by at most 3 MMAs per 16-pixel K step.
+    const uint64_t dhi_a = umma_smem_desc(0u, ablk_bytes, 8u * sw_a, sw_a);
+    const uint64_t dhi_b = umma_smem_desc(0u, bblk_bytes, 8u * sw_b, sw_b);
+    const int blocks_per_mma = 256 / p.blk_b < nblk ? 256 / p.blk_b : nblk;
+    const int n_mma = (nblk + blocks_per_mma - 1) / blocks_per_mma;  // <= 3 (<= 512 columns)
+    const int nb_last = nblk - (n_mma - 1) * blocks_per_mma;
+    const uint32_t idesc_full = umma_idesc_bf16(128, blocks_per_mma * p.blk_b, 1, 1);
+    const uint32_t idesc_last = umma_idesc_bf16(128, nb_last * p.blk_b, 1, 1);
+    const uint32_t kstep_a16 = static_cast<uint32_t>(16 * sw_a) >> 4;  // 16 pixel rows, in 16 B units
+    const uint32_t kstep_b16 = static_cast<uint32_t>(16 * sw_b) >> 4;
+    const uint32_t mma_b16 = (static_cast<uint32_t>(blocks_per_mma) * bblk_bytes) >> 4;
+    const uint32_t mma_cols = static_cast<uint32_t>(blocks_per_mma * p.blk_b);
+    const int ksteps = p.kp >> 4;
+    int s = 0;
+    uint32_t ph = 0;
+    uint32_t accum = 0;
+    for (int kt = kt0; kt < kt1; ++kt) {
+      mbar_wait(&full_bar[s], ph, 0x600u + s);
+      tc_fence_after();
+      const uint32_t a16 = smem_u32(smem + static_cast<size_t>(s) * stage_bytes) >> 4;
+      const uint32_t b16 = a16 + (a_bytes >> 4);
+      if (elect_one_sync()) {
         for (int k = 0; k < ksteps; ++k) {
-          const uint64_t ad = umma_smem_desc(a_addr + static_cast<uint32_t>(k) * 16u * sw_a, ablk_bytes, sbo_a, sw_a);
-          for (int b0 = 0; b0 < nblk; b0 += blocks_per_mma) {
-            const int nb = (nblk - b0) < blocks_per_mma ? (nblk - b0) : blocks_per_mma;
-            const uint32_t idesc = umma_idesc_bf16(128, nb * p.blk_b, 1, 1);
-            const uint64_t bd = umma_smem_desc(
-                b_addr + static_cast<uint32_t>(b0) * bblk_bytes + static_cast<uint32_t>(k) * 16u * sw_b,
-                bblk_bytes, sbo_b, sw_b);
-            umma_bf16(tmem_base + static_cast<uint32_t>(b0 * p.blk_b), ad, bd, idesc,
-                      (first && k == 0) ? 0u : 1u);
+          const uint64_t ad = dhi_a | static_cast<uint64_t>(a16 + k * kstep_a16);
+          const uint32_t bk16 = b16 + k * kstep_b16;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            if (j < n_mma) {
+              umma_bf16(tmem_base + j * mma_cols, ad, dhi_b | static_cast<uint64_t>(bk16 + j * mma_b16),
+                        (j == n_mma - 1) ? idesc_last : idesc_full, accum);
+            }
           }
+          accum = 1u;
         }
-        first = false;
         umma_commit(&empty_bar[s]);
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
-      umma_commit(done_bar);
+      __syncwarp();
+      accum = 1u;
+      if (++s == p.stages) { s = 0; ph ^= 1u; }
     }
+    if (elect_one_sync()) umma_commit(done_bar);
+    __syncwarp();
   } else {
     const int quarter = warp & 3;
     const int m_local = quarter * 32 + lane;
