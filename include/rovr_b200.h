@@ -98,16 +98,18 @@ int rovr_maxpool_bwd(const void* x, int x_ld, const void* gp, int gp_ld, const v
 
 /* ---- LocalNet tail: conv8 1x1 (64->3) + sigmoid (+ fused L2 loss) ------------------------------
  * rovr/local_net.py:39,71; nn.MSELoss of rovr/train_local_net_unet.py:90,107.
- * out: NCHW fp32 [B][3][H][W]. If target != NULL, *loss = mean((out-target)^2) (ws >= 4*ceil(B*H*W/256)). */
+ * out: NCHW fp32 [B][3][H][W]. If target != NULL, *loss = mean((out-target)^2) (ws >= rovr_tail_workspace). */
 size_t rovr_tail_workspace(int B, int H, int W);
 int rovr_tail_fwd(const void* y7, const float* w8, const float* b8, float* out, const float* target,
                   float* loss, void* ws, size_t ws_bytes, int B, int H, int W, void* stream);
-/* g7 (NHWC bf16, ld 64), dw8[3][64], db8[3]. dL/dout = gout (NCHW fp32, may be NULL) +
- * mse_scale * (*gloss) * (out - target) when target != NULL (mse_scale = 2 / numel; gloss is the
- * device scalar dL/dloss, NULL = 1). */
+/* g7 (NHWC bf16, ld 64), dw8[3][64], db8[3], db7[64] (= column sums of g7, conv7's bias
+ * gradient; may be NULL). dL/dout = gout (NCHW fp32, may be NULL) + mse_scale * (*gloss) *
+ * (out - target) when target != NULL (mse_scale = 2 / numel; gloss is the device scalar
+ * dL/dloss, NULL = 1). */
 int rovr_tail_bwd(const void* y7, const float* w8, const float* out, const float* gout,
                   const float* target, float mse_scale, const float* gloss, void* g7, float* dw8,
-                  float* db8, void* ws, size_t ws_bytes, int B, int H, int W, void* stream);
+                  float* db8, float* db7, void* ws, size_t ws_bytes, int B, int H, int W,
+                  void* stream);
 
 /* ---- bias gradient: out[c] = sum over pixels of g[pixel][c]; C even, C <= 512 ------------------ */
 size_t rovr_colsum_workspace(int C);

@@ -49,7 +49,7 @@ SIGNATURES = {
     "rovr_maxpool_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "rovr_tail_workspace": (_sz, [_i, _i, _i]),
     "rovr_tail_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _p]),
-    "rovr_tail_bwd": (_i, [_p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _p]),
+    "rovr_tail_bwd": (_i, [_p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _p]),
     "rovr_colsum_workspace": (_sz, [_i]),
     "rovr_colsum": (_i, [_p, _i, _ll, _i, _p, _p, _sz, _p]),
 }

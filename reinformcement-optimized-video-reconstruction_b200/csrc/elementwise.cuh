@@ -190,65 +190,6 @@ __global__ void maxpool_bwd_generic_kernel(const __nv_bfloat16* __restrict__ x, 
   gx[pix * gx_ld + c] = __float2bfloat16_rn(g);
 }
 
-// ---------------------------------------------------------------------------------------------
-// LocalNet tail: conv8 (1x1, 64 -> 3) + sigmoid, output NCHW fp32; optional fused L2 loss.
-// Reference: rovr/local_net.py:39,71 and nn.MSELoss of rovr/train_local_net_unet.py:90,107.
-// One thread per pixel: 128 B of y7 in, 3 coalesced plane stores out.
-// ---------------------------------------------------------------------------------------------
-constexpr int TAIL_C = 64;
-__global__ void tail_fwd_kernel(const __nv_bfloat16* __restrict__ y7, const float* __restrict__ w8,
-                                const float* __restrict__ b8, float* __restrict__ out,
-                                const float* __restrict__ target, float* __restrict__ loss_partial,
-                                int B, int HW) {
-  __shared__ float sw[3 * TAIL_C + 3];
-  __shared__ float sred[32];
-  for (int i = threadIdx.x; i < 3 * TAIL_C + 3; i += blockDim.x)
-    sw[i] = i < 3 * TAIL_C ? w8[i] : b8[i - 3 * TAIL_C];
-  __syncthreads();
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  float se = 0.f;
-  if (i < static_cast<long long>(B) * HW) {
-    const int b = static_cast<int>(i / HW);
-    const int px = static_cast<int>(i - static_cast<long long>(b) * HW);
-    float a0 = sw[3 * TAIL_C], a1 = sw[3 * TAIL_C + 1], a2 = sw[3 * TAIL_C + 2];
-    const uint4* xp = reinterpret_cast<const uint4*>(y7 + i * TAIL_C);
-#pragma unroll
-    for (int v = 0; v < TAIL_C / 8; ++v) {
-      const uint4 q = __ldg(xp + v);
-      const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float lo = bf16_lo(wds[j]), hi = bf16_hi(wds[j]);
-        const int c = v * 8 + 2 * j;
-        a0 = fmaf(lo, sw[c], a0);            a0 = fmaf(hi, sw[c + 1], a0);
-        a1 = fmaf(lo, sw[TAIL_C + c], a1);   a1 = fmaf(hi, sw[TAIL_C + c + 1], a1);
-        a2 = fmaf(lo, sw[2 * TAIL_C + c], a2); a2 = fmaf(hi, sw[2 * TAIL_C + c + 1], a2);
-      }
-    }
-    const float y0 = 1.f / (1.f + expf(-a0)), y1 = 1.f / (1.f + expf(-a1)), y2 = 1.f / (1.f + expf(-a2));
-    const long long o = static_cast<long long>(b) * 3 * HW + px;
-    out[o] = y0;
-    out[o + HW] = y1;
-    out[o + 2ll * HW] = y2;
-    if (target) {
-      const float d0 = y0 - target[o], d1 = y1 - target[o + HW], d2 = y2 - target[o + 2ll * HW];
-      se = d0 * d0 + d1 * d1 + d2 * d2;
-    }
-  }
-  if (loss_partial) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = se;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      float v = threadIdx.x < (blockDim.x >> 5) ? sred[threadIdx.x] : 0.f;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (threadIdx.x == 0) loss_partial[blockIdx.x] = v;
-    }
-  }
-}
-
 // sum a vector of per-block partials in a fixed order -> out[0] = scale * sum
 __global__ void sum_partials_kernel(const float* __restrict__ partial, int n, float scale,
                                     float* __restrict__ out) {
@@ -265,93 +206,6 @@ __global__ void sum_partials_kernel(const float* __restrict__ partial, int n, fl
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (threadIdx.x == 0) out[0] = v * scale;
   }
-}
-
-// Tail backward. gz_k = g_k * y_k (1 - y_k) with g_k = gout_k (if given) + mse_scale * gloss *
-// (y_k - t_k) (if a fused L2 target is given; mse_scale = 2 / numel, gloss = dL/dloss on device); g7[c] = (sum_k w8[k][c] gz_k) * (y7[c] > 0);
-// dW8[k][c] = sum_p gz_k y7[c]; db8[k] = sum_p gz_k. Per-block partials [grid][3*64+3].
-constexpr int TAILB_THREADS = 256;
-constexpr int TAILB_PIX_PER_THREAD = 8;
-__global__ void __launch_bounds__(TAILB_THREADS)
-tail_bwd_kernel(const __nv_bfloat16* __restrict__ y7, const float* __restrict__ w8,
-                const float* __restrict__ yout, const float* __restrict__ gout,
-                const float* __restrict__ target, float mse_scale,
-                const float* __restrict__ gloss, __nv_bfloat16* __restrict__ g7,
-                float* __restrict__ partial, int B, int HW) {
-  __shared__ float sw[3 * TAIL_C];
-  __shared__ float sacc[3 * TAIL_C + 3];
-  for (int i = threadIdx.x; i < 3 * TAIL_C; i += blockDim.x) sw[i] = w8[i];
-  for (int i = threadIdx.x; i < 3 * TAIL_C + 3; i += blockDim.x) sacc[i] = 0.f;
-  const float lscale = mse_scale * (gloss ? __ldg(gloss) : 1.f);
-  __syncthreads();
-  // Each warp handles 32 consecutive pixels per iteration; lane l accumulates dW for channels
-  // (2l, 2l+1) of all three outputs over the warp's pixels via shuffles of gz.
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long npix = static_cast<long long>(B) * HW;
-  const long long base = (static_cast<long long>(blockIdx.x) * (TAILB_THREADS / 32) + warp) * 32ll * TAILB_PIX_PER_THREAD;
-  float dw[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-  float db[3] = {0.f, 0.f, 0.f};
-  float wl[3][2];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { wl[k][0] = sw[k * TAIL_C + 2 * lane]; wl[k][1] = sw[k * TAIL_C + 2 * lane + 1]; }
-  for (int it = 0; it < TAILB_PIX_PER_THREAD; ++it) {
-    const long long i = base + static_cast<long long>(it) * 32 + lane;
-    float gz[3] = {0.f, 0.f, 0.f};
-    const bool ok = i < npix;
-    if (ok) {
-      const int b = static_cast<int>(i / HW);
-      const int px = static_cast<int>(i - static_cast<long long>(b) * HW);
-      const long long o = static_cast<long long>(b) * 3 * HW + px;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const float y = yout[o + static_cast<long long>(k) * HW];
-        float g = 0.f;
-        if (gout) g = gout[o + static_cast<long long>(k) * HW];
-        if (target) g += lscale * (y - target[o + static_cast<long long>(k) * HW]);
-        gz[k] = g * y * (1.f - y);
-        db[k] += gz[k];
-      }
-    }
-    // dW: for each of the 32 pixels of this warp iteration, lane l reads channels (2l,2l+1).
-    const long long wbase = base + static_cast<long long>(it) * 32;
-    for (int s = 0; s < 32; ++s) {
-      const float z0 = __shfl_sync(0xffffffffu, gz[0], s);
-      const float z1 = __shfl_sync(0xffffffffu, gz[1], s);
-      const float z2 = __shfl_sync(0xffffffffu, gz[2], s);
-      const long long pi = wbase + s;
-      if (pi < npix) {
-        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(y7 + pi * TAIL_C) + lane);
-        const float lo = bf16_lo(u), hi = bf16_hi(u);
-        dw[0][0] = fmaf(z0, lo, dw[0][0]); dw[0][1] = fmaf(z0, hi, dw[0][1]);
-        dw[1][0] = fmaf(z1, lo, dw[1][0]); dw[1][1] = fmaf(z1, hi, dw[1][1]);
-        dw[2][0] = fmaf(z2, lo, dw[2][0]); dw[2][1] = fmaf(z2, hi, dw[2][1]);
-        // g7 for channels (2l, 2l+1) of this pixel: coalesced 128 B row store across the warp
-        float glo = z0 * wl[0][0] + z1 * wl[1][0] + z2 * wl[2][0];
-        float ghi = z0 * wl[0][1] + z1 * wl[1][1] + z2 * wl[2][1];
-        if (!(lo > 0.f)) glo = 0.f;
-        if (!(hi > 0.f)) ghi = 0.f;
-        reinterpret_cast<uint32_t*>(g7 + pi * TAIL_C)[lane] = pack_bf16x2(glo, ghi);
-      }
-    }
-  }
-  // block reduction in a fixed order: warps take turns adding into shared memory
-#pragma unroll
-  for (int k = 0; k < 3; ++k)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) db[k] += __shfl_xor_sync(0xffffffffu, db[k], o);
-  for (int w = 0; w < TAILB_THREADS / 32; ++w) {
-    if (warp == w) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        sacc[k * TAIL_C + 2 * lane] += dw[k][0];
-        sacc[k * TAIL_C + 2 * lane + 1] += dw[k][1];
-        if (lane == 0) sacc[3 * TAIL_C + k] += db[k];
-      }
-    }
-    __syncthreads();
-  }
-  for (int i = threadIdx.x; i < 3 * TAIL_C + 3; i += blockDim.x)
-    partial[static_cast<long long>(blockIdx.x) * (3 * TAIL_C + 3) + i] = sacc[i];
 }
 
 // out[j] = sum_{r < nrows} partial[r][j]   (fixed order), optional accumulate into out

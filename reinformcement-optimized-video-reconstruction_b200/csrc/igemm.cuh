@@ -221,23 +221,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(&full_bar[s], ph, 0x300u + s);
         tc_fence_after();
         const uint32_t st16 = smem_u32(smem + static_cast<size_t>(s) * stage_bytes) >> 4;
-        if (elect_one_sync()) {
-          for (int u = 0; u < nsub; ++u) {
-            const uint32_t ad = st16 + static_cast<uint32_t>(u) * sub16;
-            const uint32_t bd = ad + a16;
+        // descriptors are computed in warp-uniform code (uniform registers); each MMA is
+        // individually guarded by elect.sync, the form ptxas lowers without register moves
+        for (int u = 0; u < nsub; ++u) {
+          const uint32_t ad = st16 + static_cast<uint32_t>(u) * sub16;
+          const uint32_t bd = ad + a16;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (k < ksteps) {
-                umma_bf16(d_tmem, dhi | static_cast<uint64_t>(ad + 2u * k),
-                          dhi | static_cast<uint64_t>(bd + 2u * k), idesc, accum);
-                accum = 1u;
-              }
+          for (int k = 0; k < 4; ++k) {
+            if (k < ksteps) {
+              const uint64_t da = dhi | static_cast<uint64_t>(ad + 2u * k);
+              const uint64_t db = dhi | static_cast<uint64_t>(bd + 2u * k);
+              if (elect_one_sync()) umma_bf16(d_tmem, da, db, idesc, accum);
+              accum = 1u;
             }
           }
-          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
         }
+        if (elect_one_sync()) umma_commit(&empty_bar[s]);  // frees the slot once these MMAs retire
         __syncwarp();
-        accum = 1u;
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
       if (elect_one_sync()) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue

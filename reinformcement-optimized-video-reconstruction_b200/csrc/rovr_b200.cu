@@ -16,6 +16,7 @@
 #include "elementwise.cuh"
 #include "igemm.cuh"
 #include "norm.cuh"
+#include "tail.cuh"
 #include "wgrad.cuh"
 
 using namespace rovr;
@@ -319,61 +320,8 @@ extern "C" int rovr_maxpool_bwd(const void* x, int x_ld, const void* gp, int gp_
 // ------------------------------------------------------------------------------------------------
 // LocalNet tail
 // ------------------------------------------------------------------------------------------------
-static int tail_bwd_grid(long long npix) {
-  const long long per_block = 1ll * TAILB_THREADS * TAILB_PIX_PER_THREAD;
-  return static_cast<int>((npix + per_block - 1) / per_block);
-}
-extern "C" size_t rovr_tail_workspace(int B, int H, int W) {
-  const long long npix = 1ll * B * H * W;
-  const size_t fwd = static_cast<size_t>((npix + 255) / 256) * sizeof(float);
-  const size_t bwd = static_cast<size_t>(tail_bwd_grid(npix)) * (3 * TAIL_C + 3) * sizeof(float);
-  return std::max(fwd, bwd) + 256;
-}
-extern "C" int rovr_tail_fwd(const void* y7, const float* w8, const float* b8, float* out,
-                             const float* target, float* loss, void* ws, size_t ws_bytes, int B,
-                             int H, int W, void* stream) {
-  if (int rc = ensure_device()) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const long long npix = 1ll * B * H * W;
-  const int grid = static_cast<int>((npix + 255) / 256);
-  float* partial = nullptr;
-  if (target) {
-    ROVR_REQUIRE(loss != nullptr && ws != nullptr && ws_bytes >= grid * sizeof(float),
-                 "tail_fwd: loss requested but loss/ws missing or too small");
-    partial = static_cast<float*>(ws);
-  }
-  tail_fwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(y7), w8, b8, out, target,
-                                        partial, B, H * W);
-  if (int rc = launch_check("tail_fwd")) return rc;
-  if (target) {
-    sum_partials_kernel<<<1, 1024, 0, st>>>(partial, grid, 1.f / (3.f * static_cast<float>(npix)), loss);
-    return launch_check("sum_partials");
-  }
-  return 0;
-}
-extern "C" int rovr_tail_bwd(const void* y7, const float* w8, const float* out, const float* gout,
-                             const float* target, float mse_scale, const float* gloss, void* g7,
-                             float* dw8, float* db8, void* ws, size_t ws_bytes, int B, int H, int W,
-                             void* stream) {
-  if (int rc = ensure_device()) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const long long npix = 1ll * B * H * W;
-  const int grid = tail_bwd_grid(npix);
-  const int ncols = 3 * TAIL_C + 3;
-  ROVR_REQUIRE(ws_bytes >= static_cast<size_t>(grid) * ncols * sizeof(float), "tail_bwd: workspace too small");
-  ROVR_REQUIRE(gout != nullptr || target != nullptr, "tail_bwd: give gout and/or target");
-  float* partial = static_cast<float*>(ws);
-  tail_bwd_kernel<<<grid, TAILB_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(y7), w8, out, gout,
-                                                  target, mse_scale, gloss,
-                                                  static_cast<__nv_bfloat16*>(g7), partial, B, H * W);
-  if (int rc = launch_check("tail_bwd")) return rc;
-  // columns [0, 192) -> dw8, [192, 195) -> db8
-  reduce_rows_kernel<<<(3 * TAIL_C + 31) / 32, 256, 0, st>>>(partial, grid, ncols, 3 * TAIL_C, dw8, 0);
-  if (int rc = launch_check("reduce_rows(dw8)")) return rc;
-  // dw8 buffer is [3][64] contiguous; db8 is separate: run a second tiny reduce on the tail columns
-  reduce_rows_kernel<<<1, 256, 0, st>>>(partial + 3 * TAIL_C, grid, ncols, 3, db8, 0);
-  return launch_check("reduce_rows(db8)");
-}
+#include "api_tail.inc"
+
 
 // ------------------------------------------------------------------------------------------------
 // bias gradient

@@ -165,23 +165,21 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tc_fence_after();
       const uint32_t a16 = smem_u32(smem + static_cast<size_t>(s) * stage_bytes) >> 4;
       const uint32_t b16 = a16 + (a_bytes >> 4);
-      if (elect_one_sync()) {
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t ad = dhi_a | static_cast<uint64_t>(a16 + k * kstep_a16);
-          const uint32_t bk16 = b16 + k * kstep_b16;
+      for (int k = 0; k < ksteps; ++k) {
+        const uint64_t ad = dhi_a | static_cast<uint64_t>(a16 + k * kstep_a16);
+        const uint32_t bk16 = b16 + k * kstep_b16;
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            if (j < n_mma) {
-              umma_bf16(tmem_base + j * mma_cols, ad, dhi_b | static_cast<uint64_t>(bk16 + j * mma_b16),
-                        (j == n_mma - 1) ? idesc_last : idesc_full, accum);
-            }
+        for (int j = 0; j < 2; ++j) {
+          if (j < n_mma) {
+            const uint64_t bd = dhi_b | static_cast<uint64_t>(bk16 + j * mma_b16);
+            const uint32_t id = (j == n_mma - 1) ? idesc_last : idesc_full;
+            if (elect_one_sync()) umma_bf16(tmem_base + j * mma_cols, ad, bd, id, accum);
           }
-          accum = 1u;
         }
-        umma_commit(&empty_bar[s]);
+        accum = 1u;
       }
+      if (elect_one_sync()) umma_commit(&empty_bar[s]);
       __syncwarp();
-      accum = 1u;
       if (++s == p.stages) { s = 0; ph ^= 1u; }
     }
     if (elect_one_sync()) umma_commit(done_bar);

@@ -156,10 +156,9 @@ class _LocalNetFunction(torch.autograd.Function):
         ops.tail_bwd(a["y7"], P["conv8.weight"], a["out"], g7, G["conv8.weight"], G["conv8.bias"],
                      gout=g_out, target=target if use_loss else None,
                      mse_scale=2.0 / a["out"].numel(),
-                     gloss=g_loss.contiguous() if use_loss else None)
-        # ---- conv7 ----
+                     gloss=g_loss.contiguous() if use_loss else None, db7=G["conv7.bias"])
+        # ---- conv7 (its bias gradient came out of the tail kernel) ----
         ops.conv3x3_wgrad(g7, a["cat7"], G["conv7.weight"])
-        ops.colsum(g7, G["conv7.bias"])
         gcat7 = el(a["cat7"])
         ops.conv3x3_dgrad(g7, wd("conv7"), gcat7, mask=a["cat7"])
         # ---- upconv3 ----

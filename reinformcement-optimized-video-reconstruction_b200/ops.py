@@ -294,7 +294,7 @@ def tail_fwd(y7, w8, b8, target=None):
     return out, loss
 
 
-def tail_bwd(y7, w8, out, g7, dw8, db8, gout=None, target=None, mse_scale=0.0, gloss=None):
+def tail_bwd(y7, w8, out, g7, dw8, db8, gout=None, target=None, mse_scale=0.0, gloss=None, db7=None):
     B, H, W, C, ld = _act(y7, "y7")
     assert C == 64 and ld == 64
     _, _, _, Cg, g_ld = _act(g7, "g7")
@@ -307,7 +307,7 @@ def tail_bwd(y7, w8, out, g7, dw8, db8, gout=None, target=None, mse_scale=0.0, g
     _f32(gloss, "gloss")
     ws = workspace(N.lib.rovr_tail_workspace(B, H, W), y7.device)
     _launch("rovr_tail_bwd", _ptr(y7), _ptr(w8), _ptr(out), _ptr(gout), _ptr(target),
-           ctypes.c_float(mse_scale), _ptr(gloss), _ptr(g7), _ptr(dw8), _ptr(db8), _ptr(ws),
+           ctypes.c_float(mse_scale), _ptr(gloss), _ptr(g7), _ptr(dw8), _ptr(db8), _ptr(db7), _ptr(ws),
            ws.numel(), B, H, W, _stream())
 
 
