@@ -49,10 +49,13 @@ constexpr int IG_EPI_THREADS = 128;
 // This cuts the L2 -> SM traffic of the activation operand 6.4x, which is what bounds an
 // implicit-GEMM conv on B200 (the fabric delivers ~42 B/clk/SM; a 128x128 tile wants 128).
 constexpr int IG_HALO_TW = 8, IG_HALO_TH = 16;
-constexpr int IG_HALO_ROWS = (IG_HALO_TW + 2) * (IG_HALO_TH + 2);     // 180
-constexpr int IG_HALO_BYTES = IG_HALO_ROWS * 128;                      // 23040
-constexpr int IG_HALO_SLOT = (IG_HALO_BYTES + 1023) / 1024 * 1024;     // 23552
+constexpr int IG_HALO_ROWS = (IG_HALO_TW + 2) * (IG_HALO_TH + 2);     // 180 rows of `sw` bytes
 constexpr int IG_MAX_ASLOTS = 4;
+__host__ __device__ inline uint32_t ig_halo_bytes(int sw) { return IG_HALO_ROWS * sw; }
+__host__ __device__ inline uint32_t ig_halo_slot(int sw) { return (ig_halo_bytes(sw) + 1023u) / 1024u * 1024u; }
+// Resident-weight mode (halo convs whose whole packed weight matrix fits in shared memory, e.g.
+// conv7 of LocalNet: 64 x 1152 bf16 = 144 KB): every (tap, k-chunk) weight tile is loaded once
+// per CTA and the pipeline only streams input patches.
 
 enum : int { IG_EPI_PLAIN = 0, IG_EPI_PIXSHUF = 1 };
 
@@ -77,6 +80,7 @@ struct IgemmParams {
   int has_mask;
   int halo;               // 1: Conv2d 3x3 with the input patch loaded once per k-chunk (see below)
   int a_slots;            // halo mode: depth of the A (halo tile) ring
+  int resident_b;         // halo mode: all weight tiles stay in shared memory for the whole kernel
   int bias_mod;           // bias index = n % bias_mod
   int shuf_cout;          // pixel-shuffle: channels per quadrant
   const float* bias;      // may be null
@@ -136,9 +140,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int epi_rowb = p.cw * 2;
   const uint32_t stg_bytes = 128u * epi_rowb;
 
-  uint8_t* aring = smem + static_cast<size_t>(p.stages) * stage_bytes;          // halo tiles
+  const uint32_t halo_bytes = ig_halo_bytes(sw), halo_slot = ig_halo_slot(sw);
+  // [pipeline stages | resident weights] [halo ring] [staging] [mask] [barriers] [bias]
+  const size_t front_bytes = p.resident_b ? static_cast<size_t>(p.ntaps) * (p.cin / p.bk) * b_bytes
+                                          : static_cast<size_t>(p.stages) * stage_bytes;
+  uint8_t* aring = smem + front_bytes;                                           // halo tiles
   aring += (1024u - (smem_u32(aring) & 1023u)) & 1023u;                          // swizzle alignment
-  uint8_t* stg_base = aring + (halo ? p.a_slots * IG_HALO_SLOT : 0);             // 2 staging tiles
+  uint8_t* stg_base = aring + (halo ? p.a_slots * halo_slot : 0);                // 2 staging tiles
   uint8_t* msk_base = stg_base + 2 * stg_bytes;                                  // 2 mask tiles
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(msk_base + (p.has_mask ? 2 * stg_bytes : 0));
   uint64_t* empty_bar = full_bar + IG_MAX_STAGES;
@@ -147,7 +155,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* mfull_bar = tempty_bar + 2;
   uint64_t* afull_bar = mfull_bar + 2;
   uint64_t* aempty_bar = afull_bar + IG_MAX_ASLOTS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + IG_MAX_ASLOTS);
+  uint64_t* wfull_bar = aempty_bar + IG_MAX_ASLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
   float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int m_tiles = p.ntile[0] * p.ntile[1] * p.ntile[2] * p.ntile[3];
@@ -174,6 +183,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(&afull_bar[a], 1);
       mbar_init(&aempty_bar[a], 1);
     }
+    mbar_init(wfull_bar, 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
@@ -187,6 +197,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0) {
     // ================================ TMA producer ================================
     {
+      if (p.resident_b) {  // all weight tiles, once: tile index = t * kchunks + kc
+        if (elect_one_sync()) {
+          mbar_expect_tx(wfull_bar, static_cast<uint32_t>(k_iters) * b_bytes);
+          for (int it = 0; it < k_iters; ++it)
+            tma_load_2d(&tmB, wfull_bar, smem + static_cast<size_t>(it) * b_bytes, it * p.bk, 0);
+        }
+        __syncwarp();
+      }
       int s = 0, sa = 0;
       uint32_t ph = 0, pha = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -199,17 +217,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mt /= p.ntile[j];
         }
         if (halo) {
-          // per 64-channel chunk: one halo tile of the input, then the nine weight tiles
+          // per k-chunk: one halo tile of the input, then (unless resident) the nine weight tiles
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(&aempty_bar[sa], pha ^ 1u, 0x900u + sa);
             if (elect_one_sync()) {
-              mbar_expect_tx(&afull_bar[sa], IG_HALO_BYTES);
-              tma_load_5d(&tmA, &afull_bar[sa], aring + sa * IG_HALO_SLOT, kc * 64, org[0] - 1,
+              mbar_expect_tx(&afull_bar[sa], halo_bytes);
+              tma_load_5d(&tmA, &afull_bar[sa], aring + sa * halo_slot, kc * p.bk, org[0] - 1,
                           org[1] - 1, org[2], org[3]);
             }
             __syncwarp();
             if (++sa == p.a_slots) { sa = 0; pha ^= 1u; }
-            for (int t0 = 0; t0 < 9; t0 += p.tps) {
+            for (int t0 = 0; t0 < (p.resident_b ? 0 : 9); t0 += p.tps) {
               const int nsub = (9 - t0) < p.tps ? (9 - t0) : p.tps;
               mbar_wait(&empty_bar[s], ph ^ 1u, 0x100u + s);
               uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
@@ -217,7 +235,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 mbar_expect_tx(&full_bar[s], b_bytes * nsub);
                 for (int u = 0; u < nsub; ++u)
                   tma_load_2d(&tmB, &full_bar[s], st + static_cast<size_t>(u) * b_bytes,
-                              (t0 + u) * p.cin + kc * 64, nt * p.n_tile);
+                              (t0 + u) * p.cin + kc * p.bk, nt * p.n_tile);
               }
               __syncwarp();
               if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -260,17 +278,47 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t ph = 0, pha = 0;
     int acc = 0;
     uint32_t aph = 0;
+    if (p.resident_b) {
+      mbar_wait(wfull_bar, 0u, 0xb00u);
+      tc_fence_after();
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[acc], aph ^ 1u, 0x200u + acc);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
       uint32_t accum = 0;
-      if (halo) {
-        const uint64_t dhi_a = umma_smem_desc(0u, 0u, (IG_HALO_TW + 2) * 128u, 128);
+      if (halo && p.resident_b) {
+        const uint64_t dhi_a = umma_smem_desc(0u, 0u, static_cast<uint32_t>((IG_HALO_TW + 2) * sw), sw);
+        const uint32_t w16 = smem_u32(smem) >> 4, b16 = b_bytes >> 4, row16 = static_cast<uint32_t>(sw) >> 4;
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(&afull_bar[sa], pha, 0xa00u + sa);
           tc_fence_after();
-          const uint32_t a_slot16 = smem_u32(aring + sa * IG_HALO_SLOT) >> 4;
+          const uint32_t a_slot16 = smem_u32(aring + sa * halo_slot) >> 4;
+          for (int t = 0; t < 9; ++t) {
+            const uint32_t ad = a_slot16 + static_cast<uint32_t>(
+                (p.tap_off[t][1] + 1) * (IG_HALO_TW + 2) + p.tap_off[t][0] + 1) * row16;
+            const uint32_t bd = w16 + static_cast<uint32_t>(t * kchunks + kc) * b16;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k < ksteps) {
+                const uint64_t da = dhi_a | static_cast<uint64_t>(ad + 2u * k);
+                const uint64_t db = dhi | static_cast<uint64_t>(bd + 2u * k);
+                if (elect_one_sync()) umma_bf16(d_tmem, da, db, idesc, accum);
+                accum = 1u;
+              }
+            }
+          }
+          if (elect_one_sync()) umma_commit(&aempty_bar[sa]);
+          __syncwarp();
+          if (++sa == p.a_slots) { sa = 0; pha ^= 1u; }
+        }
+      } else if (halo) {
+        const uint64_t dhi_a = umma_smem_desc(0u, 0u, static_cast<uint32_t>((IG_HALO_TW + 2) * sw), sw);
+        const uint32_t row16 = static_cast<uint32_t>(sw) >> 4;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&afull_bar[sa], pha, 0xa00u + sa);
+          tc_fence_after();
+          const uint32_t a_slot16 = smem_u32(aring + sa * halo_slot) >> 4;
           for (int t0 = 0; t0 < 9; t0 += p.tps) {
             const int nsub = (9 - t0) < p.tps ? (9 - t0) : p.tps;
             mbar_wait(&full_bar[s], ph, 0x300u + s);
@@ -280,14 +328,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               const int t = t0 + u;
               // first halo row of this tap's view: (dy + 1) * 10 + (dx + 1); 8 x 16-byte units per row
               const uint32_t ad = a_slot16 + static_cast<uint32_t>(
-                  ((p.tap_off[t][1] + 1) * (IG_HALO_TW + 2) + p.tap_off[t][0] + 1) * 8);
+                  (p.tap_off[t][1] + 1) * (IG_HALO_TW + 2) + p.tap_off[t][0] + 1) * row16;
               const uint32_t bd = st16 + static_cast<uint32_t>(u) * (b_bytes >> 4);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint64_t da = dhi_a | static_cast<uint64_t>(ad + 2u * k);
-                const uint64_t db = dhi | static_cast<uint64_t>(bd + 2u * k);
-                if (elect_one_sync()) umma_bf16(d_tmem, da, db, idesc, accum);
-                accum = 1u;
+                if (k < ksteps) {
+                  const uint64_t da = dhi_a | static_cast<uint64_t>(ad + 2u * k);
+                  const uint64_t db = dhi | static_cast<uint64_t>(bd + 2u * k);
+                  if (elect_one_sync()) umma_bf16(d_tmem, da, db, idesc, accum);
+                  accum = 1u;
+                }
               }
             }
             if (elect_one_sync()) umma_commit(&empty_bar[s]);
@@ -495,10 +545,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 // Fixed (non-pipeline) shared memory of a configuration (host side).
-inline size_t igemm_fixed_smem(int cw, int has_mask, int n_total, int a_slots = 0) {
+inline size_t igemm_fixed_smem(int cw, int has_mask, int n_total, int a_slots = 0, int sw = 128) {
   const size_t stg = 128 * static_cast<size_t>(cw) * 2;
-  return 2048 + static_cast<size_t>(a_slots) * IG_HALO_SLOT + 2 * stg + (has_mask ? 2 * stg : 0) +
-         (2 * IG_MAX_STAGES + 2 * IG_MAX_ASLOTS + 6) * 8 + 16 +
+  return 2048 + static_cast<size_t>(a_slots) * ig_halo_slot(sw) + 2 * stg + (has_mask ? 2 * stg : 0) +
+         (2 * IG_MAX_STAGES + 2 * IG_MAX_ASLOTS + 7) * 8 + 16 +
          static_cast<size_t>(n_total) * 4 + 64;
 }
 inline size_t igemm_stage_bytes(int bk, int n_tile, int tps) {
