@@ -219,7 +219,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (halo) {
           // per k-chunk: one halo tile of the input, then (unless resident) the nine weight tiles
           for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(&aempty_bar[sa], pha ^ 1u, 0x900u + sa);
+            mbar_wait_warp(&aempty_bar[sa], pha ^ 1u, 0x900u + sa);
             if (elect_one_sync()) {
               mbar_expect_tx(&afull_bar[sa], halo_bytes);
               tma_load_5d(&tmA, &afull_bar[sa], aring + sa * halo_slot, kc * p.bk, org[0] - 1,
@@ -229,7 +229,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (++sa == p.a_slots) { sa = 0; pha ^= 1u; }
             for (int t0 = 0; t0 < (p.resident_b ? 0 : 9); t0 += p.tps) {
               const int nsub = (9 - t0) < p.tps ? (9 - t0) : p.tps;
-              mbar_wait(&empty_bar[s], ph ^ 1u, 0x100u + s);
+              mbar_wait_warp(&empty_bar[s], ph ^ 1u, 0x100u + s);
               uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
               if (elect_one_sync()) {
                 mbar_expect_tx(&full_bar[s], b_bytes * nsub);
@@ -246,7 +246,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int si = 0; si < s_iters; ++si) {
           const int it0 = si * p.tps;
           const int nsub = (k_iters - it0) < p.tps ? (k_iters - it0) : p.tps;
-          mbar_wait(&empty_bar[s], ph ^ 1u, 0x100u + s);
+          mbar_wait_warp(&empty_bar[s], ph ^ 1u, 0x100u + s);
           uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
           if (elect_one_sync()) mbar_expect_tx(&full_bar[s], sub_tx * nsub);
           for (int u = 0; u < nsub; ++u) {
@@ -279,11 +279,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int acc = 0;
     uint32_t aph = 0;
     if (p.resident_b) {
-      mbar_wait(wfull_bar, 0u, 0xb00u);
+      mbar_wait_warp(wfull_bar, 0u, 0xb00u);
       tc_fence_after();
     }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      mbar_wait(&tempty_bar[acc], aph ^ 1u, 0x200u + acc);
+      mbar_wait_warp(&tempty_bar[acc], aph ^ 1u, 0x200u + acc);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
       uint32_t accum = 0;
@@ -291,24 +291,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const uint64_t dhi_a = umma_smem_desc(0u, 0u, static_cast<uint32_t>((IG_HALO_TW + 2) * sw), sw);
         const uint32_t w16 = smem_u32(smem) >> 4, b16 = b_bytes >> 4, row16 = static_cast<uint32_t>(sw) >> 4;
         for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait(&afull_bar[sa], pha, 0xa00u + sa);
+          mbar_wait_warp(&afull_bar[sa], pha, 0xa00u + sa);
           tc_fence_after();
           const uint32_t a_slot16 = smem_u32(aring + sa * halo_slot) >> 4;
           for (int t = 0; t < 9; ++t) {
             const uint32_t ad = a_slot16 + static_cast<uint32_t>(
                 (p.tap_off[t][1] + 1) * (IG_HALO_TW + 2) + p.tap_off[t][0] + 1) * row16;
             const uint32_t bd = w16 + static_cast<uint32_t>(t * kchunks + kc) * b16;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (k < ksteps) {
-                const uint64_t da = dhi_a | static_cast<uint64_t>(ad + 2u * k);
-                const uint64_t db = dhi | static_cast<uint64_t>(bd + 2u * k);
-                if (elect_one_sync()) umma_bf16(d_tmem, da, db, idesc, accum);
-                accum = 1u;
-              }
-            }
+umma_bf16_x4_elect(d_tmem, dhi_a | static_cast<uint64_t>(ad), dhi | static_cast<uint64_t>(bd), idesc,
+                               accum, static_cast<uint32_t>(ksteps));
+            accum = 1u;
           }
-          if (elect_one_sync()) umma_commit(&aempty_bar[sa]);
+          umma_commit_elect(&aempty_bar[sa]);
           __syncwarp();
           if (++sa == p.a_slots) { sa = 0; pha ^= 1u; }
         }
@@ -316,12 +310,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const uint64_t dhi_a = umma_smem_desc(0u, 0u, static_cast<uint32_t>((IG_HALO_TW + 2) * sw), sw);
         const uint32_t row16 = static_cast<uint32_t>(sw) >> 4;
         for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait(&afull_bar[sa], pha, 0xa00u + sa);
+          mbar_wait_warp(&afull_bar[sa], pha, 0xa00u + sa);
           tc_fence_after();
           const uint32_t a_slot16 = smem_u32(aring + sa * halo_slot) >> 4;
           for (int t0 = 0; t0 < 9; t0 += p.tps) {
             const int nsub = (9 - t0) < p.tps ? (9 - t0) : p.tps;
-            mbar_wait(&full_bar[s], ph, 0x300u + s);
+            mbar_wait_warp(&full_bar[s], ph, 0x300u + s);
             tc_fence_after();
             const uint32_t st16 = smem_u32(smem + static_cast<size_t>(s) * stage_bytes) >> 4;
             for (int u = 0; u < nsub; ++u) {
@@ -330,21 +324,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               const uint32_t ad = a_slot16 + static_cast<uint32_t>(
                   (p.tap_off[t][1] + 1) * (IG_HALO_TW + 2) + p.tap_off[t][0] + 1) * row16;
               const uint32_t bd = st16 + static_cast<uint32_t>(u) * (b_bytes >> 4);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (k < ksteps) {
-                  const uint64_t da = dhi_a | static_cast<uint64_t>(ad + 2u * k);
-                  const uint64_t db = dhi | static_cast<uint64_t>(bd + 2u * k);
-                  if (elect_one_sync()) umma_bf16(d_tmem, da, db, idesc, accum);
-                  accum = 1u;
-                }
-              }
+umma_bf16_x4_elect(d_tmem, dhi_a | static_cast<uint64_t>(ad), dhi | static_cast<uint64_t>(bd), idesc,
+                               accum, static_cast<uint32_t>(ksteps));
+            accum = 1u;
             }
-            if (elect_one_sync()) umma_commit(&empty_bar[s]);
+            umma_commit_elect(&empty_bar[s]);
             __syncwarp();
             if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
-          if (elect_one_sync()) umma_commit(&aempty_bar[sa]);  // halo tile consumed by all 9 taps
+          umma_commit_elect(&aempty_bar[sa]);  // halo tile consumed by all 9 taps
           __syncwarp();
           if (++sa == p.a_slots) { sa = 0; pha ^= 1u; }
         }
@@ -352,7 +340,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int si = 0; si < (halo ? 0 : s_iters); ++si) {
         const int it0 = si * p.tps;
         const int nsub = (k_iters - it0) < p.tps ? (k_iters - it0) : p.tps;
-        mbar_wait(&full_bar[s], ph, 0x300u + s);
+        mbar_wait_warp(&full_bar[s], ph, 0x300u + s);
         tc_fence_after();
         const uint32_t st16 = smem_u32(smem + static_cast<size_t>(s) * stage_bytes) >> 4;
         // descriptors are computed in warp-uniform code (uniform registers); each MMA is
@@ -360,21 +348,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int u = 0; u < nsub; ++u) {
           const uint32_t ad = st16 + static_cast<uint32_t>(u) * sub16;
           const uint32_t bd = ad + a16;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (k < ksteps) {
-              const uint64_t da = dhi | static_cast<uint64_t>(ad + 2u * k);
-              const uint64_t db = dhi | static_cast<uint64_t>(bd + 2u * k);
-              if (elect_one_sync()) umma_bf16(d_tmem, da, db, idesc, accum);
-              accum = 1u;
-            }
-          }
+umma_bf16_x4_elect(d_tmem, dhi | static_cast<uint64_t>(ad), dhi | static_cast<uint64_t>(bd), idesc,
+                               accum, static_cast<uint32_t>(ksteps));
+            accum = 1u;
         }
-        if (elect_one_sync()) umma_commit(&empty_bar[s]);  // frees the slot once these MMAs retire
+        umma_commit_elect(&empty_bar[s]);  // frees the slot once these MMAs retire
         __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
-      if (elect_one_sync()) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      umma_commit_elect(&tfull_bar[acc]);  // accumulator complete -> epilogue
       __syncwarp();
       if (++acc == 2) { acc = 0; aph ^= 1u; }
     }

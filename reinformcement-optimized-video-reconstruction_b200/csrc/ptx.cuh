@@ -80,6 +80,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
   }
 }
 
+// Warp-converged wait: one lane polls, the warp reconverges. Keeps the surrounding loop
+// warp-uniform in the compiler's eyes (a per-lane polling loop makes every loop-carried value
+// look divergent and forces vector registers + R2UR in front of each tcgen05.mma).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, unsigned code) {
+  if ((threadIdx.x & 31u) == 0u) mbar_wait(bar, parity, code);
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA: tiled tensor loads, global -> shared, completion on an mbarrier
 // ---------------------------------------------------------------------------------------------
@@ -132,6 +140,53 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same, issued by the elected lane of a converged warp: elect.sync and the predicated MMA sit in
+// one asm block so that no branch is generated and ptxas can keep the (warp-uniform) operands in
+// uniform registers. All 32 lanes must execute this with identical arguments.
+__device__ __forceinline__ void umma_bf16_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// One (tap, k-chunk) sub-tile = `ksteps` (1, 2 or 4) K=16 MMAs whose descriptors advance by 32
+// bytes (2 x 16-byte units). Issuing them from a single asm block keeps the compiler-generated
+// glue (register moves into the uniform file) to once per sub-tile instead of once per MMA.
+__device__ __forceinline__ void umma_bf16_x4_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                                   uint32_t idesc, uint32_t accumulate,
+                                                   uint32_t ksteps) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa, pt, p1, p2;\n\t"
+      ".reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "setp.eq.u32 pt, 0, 0;\n\t"
+      "setp.gt.u32 p1, %5, 1;\n\t"
+      "setp.gt.u32 p2, %5, 2;\n\t"
+      "and.pred p1, p1, pe;\n\t"
+      "and.pred p2, p2, pe;\n\t"
+      "add.u64 a1, %1, 2;\n\tadd.u64 b1, %2, 2;\n\t"
+      "add.u64 a2, %1, 4;\n\tadd.u64 b2, %2, 4;\n\t"
+      "add.u64 a3, %1, 6;\n\tadd.u64 b3, %2, 6;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t"
+      "@p1 tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, pt;\n\t"
+      "@p2 tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, pt;\n\t"
+      "@p2 tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, pt;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(ksteps)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
+          smem_u32(bar))
       : "memory");
 }
 // mbarrier arrives once every tcgen05.mma issued so far by this thread has retired.

@@ -173,16 +173,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (j < n_mma) {
             const uint64_t bd = dhi_b | static_cast<uint64_t>(bk16 + j * mma_b16);
             const uint32_t id = (j == n_mma - 1) ? idesc_last : idesc_full;
-            if (elect_one_sync()) umma_bf16(tmem_base + j * mma_cols, ad, bd, id, accum);
+            umma_bf16_elect(tmem_base + j * mma_cols, ad, bd, id, accum);
           }
         }
         accum = 1u;
       }
-      if (elect_one_sync()) umma_commit(&empty_bar[s]);
+      umma_commit_elect(&empty_bar[s]);
       __syncwarp();
       if (++s == p.stages) { s = 0; ph ^= 1u; }
     }
-    if (elect_one_sync()) umma_commit(done_bar);
+    umma_commit_elect(done_bar);
     __syncwarp();
   } else {
     const int quarter = warp & 3;
