@@ -46,7 +46,8 @@ int rovr_unpack_nhwc_to_nchw(const void* src, int ld, float* dst, int B, int H, 
 /* ---- weight repacking (fp32 parameter -> bf16 K-major GEMM operand) ------------------------- */
 /* Conv2d 3x3 weight [Cout][Cin][3][3] -> [Cout][9][cin_pad] */
 int rovr_repack_conv3x3_fprop(const float* w, void* wk, int Cout, int Cin, int cin_pad, void* stream);
-/* Conv2d 3x3 weight -> [cin_pad][9][Cout] (rows >= Cin are zero) for the data gradient */
+/* Conv2d 3x3 weight -> [cin_pad][9][Cout] with the taps flipped (t -> 8 - t; rows >= Cin are zero):
+ * the data gradient is then the forward kernel applied to dy with these weights */
 int rovr_repack_conv3x3_dgrad(const float* w, void* wk, int Cout, int Cin, int cin_pad, void* stream);
 /* ConvTranspose2d 2x2 weight [Cin][Cout][2][2] -> [4*Cout][Cin] (row = q*Cout+co, q = 2*ky+kx) */
 int rovr_repack_convT2x2_fprop(const float* w, void* wk, int Cin, int Cout, void* stream);

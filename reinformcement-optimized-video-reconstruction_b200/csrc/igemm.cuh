@@ -32,6 +32,8 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 // warps 2..5 = epilogue.
 #pragma once
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace rovr {
@@ -81,6 +83,8 @@ struct IgemmParams {
   int halo;               // 1: Conv2d 3x3 with the input patch loaded once per k-chunk (see below)
   int a_slots;            // halo mode: depth of the A (halo tile) ring
   int resident_b;         // halo mode: all weight tiles stay in shared memory for the whole kernel
+  unsigned stage_begin_mask;  // halo mode, bit t: tap t is the first sub-tile of a weight stage
+  unsigned stage_end_mask;    // halo mode, bit t: tap t is the last sub-tile of a weight stage
   int bias_mod;           // bias index = n % bias_mod
   int shuf_cout;          // pixel-shuffle: channels per quadrant
   const float* bias;      // may be null
@@ -268,12 +272,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    // The whole warp walks the pipeline with warp-uniform control flow (so that addresses and
-    // descriptors live in uniform registers); lane 0 alone issues tcgen05.mma / tcgen05.commit.
+    // The whole warp walks the pipeline with warp-uniform control flow; waits are done by one
+    // lane + __syncwarp, and every (tap, k-chunk) sub-tile is issued by one asm block
+    // (umma_tap<KS>) whose elected lane fires KS tcgen05.mma with 32-byte descriptor steps.
     const uint32_t idesc = umma_idesc_bf16(128, p.n_tile, 0, 0);
-    const uint64_t dhi = umma_smem_desc(0u, 0u, 8u * sw, sw);  // descriptor minus the address
+    const uint64_t dkm = umma_smem_desc(0u, 0u, 8u * sw, sw);  // K-major, dense rows
+    const uint32_t b_hi = static_cast<uint32_t>(dkm >> 32);
+    const uint32_t a_hi_dense = b_hi;
+    const uint32_t a_hi_halo =
+        static_cast<uint32_t>(umma_smem_desc(0u, 0u, static_cast<uint32_t>((IG_HALO_TW + 2) * sw), sw) >> 32);
     const int ksteps = p.bk >> 4;
-    const uint32_t sub16 = sub_bytes >> 4, a16 = a_bytes >> 4;
+    const uint32_t sub16 = sub_bytes >> 4, a16 = a_bytes >> 4, b16 = b_bytes >> 4;
+    const uint32_t row16 = static_cast<uint32_t>(sw) >> 4;
     int s = 0, sa = 0;
     uint32_t ph = 0, pha = 0;
     int acc = 0;
@@ -282,84 +292,68 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait_warp(wfull_bar, 0u, 0xb00u);
       tc_fence_after();
     }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      mbar_wait_warp(&tempty_bar[acc], aph ^ 1u, 0x200u + acc);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
-      uint32_t accum = 0;
-      if (halo && p.resident_b) {
-        const uint64_t dhi_a = umma_smem_desc(0u, 0u, static_cast<uint32_t>((IG_HALO_TW + 2) * sw), sw);
-        const uint32_t w16 = smem_u32(smem) >> 4, b16 = b_bytes >> 4, row16 = static_cast<uint32_t>(sw) >> 4;
-        for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait_warp(&afull_bar[sa], pha, 0xa00u + sa);
-          tc_fence_after();
-          const uint32_t a_slot16 = smem_u32(aring + sa * halo_slot) >> 4;
-          for (int t = 0; t < 9; ++t) {
-            const uint32_t ad = a_slot16 + static_cast<uint32_t>(
-                (p.tap_off[t][1] + 1) * (IG_HALO_TW + 2) + p.tap_off[t][0] + 1) * row16;
-            const uint32_t bd = w16 + static_cast<uint32_t>(t * kchunks + kc) * b16;
-umma_bf16_x4_elect(d_tmem, dhi_a | static_cast<uint64_t>(ad), dhi | static_cast<uint64_t>(bd), idesc,
-                               accum, static_cast<uint32_t>(ksteps));
-            accum = 1u;
+    auto tile_loop = [&](auto ks_tag) {
+      constexpr int KS = decltype(ks_tag)::value;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait_warp(&tempty_bar[acc], aph ^ 1u, 0x200u + acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
+        uint32_t accum = 0;
+        if (halo) {
+          const uint32_t w16 = smem_u32(smem) >> 4;
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait_warp(&afull_bar[sa], pha, 0xa00u + sa);
+            tc_fence_after();
+            const uint32_t a_slot16 = smem_u32(aring + sa * halo_slot) >> 4;
+            uint32_t bd = w16 + static_cast<uint32_t>(kc) * b16;  // resident: tile (t, kc) = t*kchunks + kc
+            const uint32_t bstep = p.resident_b ? static_cast<uint32_t>(kchunks) * b16 : b16;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              if (!p.resident_b && ((p.stage_begin_mask >> t) & 1u)) {
+                mbar_wait_warp(&full_bar[s], ph, 0x300u + s);
+                tc_fence_after();
+                bd = smem_u32(smem + static_cast<size_t>(s) * stage_bytes) >> 4;
+              }
+              // tap t = (dy, dx) views the halo tile (dy*10 + dx) rows further on
+              umma_tap<KS>(d_tmem, a_slot16 + static_cast<uint32_t>((t / 3) * (IG_HALO_TW + 2) + (t % 3)) * row16,
+                           a_hi_halo, bd, b_hi, idesc, accum);
+              accum = 1u;
+              bd += bstep;
+              if (!p.resident_b && ((p.stage_end_mask >> t) & 1u)) {
+                umma_commit_elect(&empty_bar[s]);
+                __syncwarp();
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
+              }
+            }
+            umma_commit_elect(&aempty_bar[sa]);  // halo tile consumed by all nine taps
+            __syncwarp();
+            if (++sa == p.a_slots) { sa = 0; pha ^= 1u; }
           }
-          umma_commit_elect(&aempty_bar[sa]);
-          __syncwarp();
-          if (++sa == p.a_slots) { sa = 0; pha ^= 1u; }
-        }
-      } else if (halo) {
-        const uint64_t dhi_a = umma_smem_desc(0u, 0u, static_cast<uint32_t>((IG_HALO_TW + 2) * sw), sw);
-        const uint32_t row16 = static_cast<uint32_t>(sw) >> 4;
-        for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait_warp(&afull_bar[sa], pha, 0xa00u + sa);
-          tc_fence_after();
-          const uint32_t a_slot16 = smem_u32(aring + sa * halo_slot) >> 4;
-          for (int t0 = 0; t0 < 9; t0 += p.tps) {
-            const int nsub = (9 - t0) < p.tps ? (9 - t0) : p.tps;
+        } else {
+          for (int si = 0; si < s_iters; ++si) {
+            const int it0 = si * p.tps;
+            const int nsub = (k_iters - it0) < p.tps ? (k_iters - it0) : p.tps;
             mbar_wait_warp(&full_bar[s], ph, 0x300u + s);
             tc_fence_after();
             const uint32_t st16 = smem_u32(smem + static_cast<size_t>(s) * stage_bytes) >> 4;
             for (int u = 0; u < nsub; ++u) {
-              const int t = t0 + u;
-              // first halo row of this tap's view: (dy + 1) * 10 + (dx + 1); 8 x 16-byte units per row
-              const uint32_t ad = a_slot16 + static_cast<uint32_t>(
-                  (p.tap_off[t][1] + 1) * (IG_HALO_TW + 2) + p.tap_off[t][0] + 1) * row16;
-              const uint32_t bd = st16 + static_cast<uint32_t>(u) * (b_bytes >> 4);
-umma_bf16_x4_elect(d_tmem, dhi_a | static_cast<uint64_t>(ad), dhi | static_cast<uint64_t>(bd), idesc,
-                               accum, static_cast<uint32_t>(ksteps));
-            accum = 1u;
+              const uint32_t ad = st16 + static_cast<uint32_t>(u) * sub16;
+              umma_tap<KS>(d_tmem, ad, a_hi_dense, ad + a16, b_hi, idesc, accum);
+              accum = 1u;
             }
-            umma_commit_elect(&empty_bar[s]);
+            umma_commit_elect(&empty_bar[s]);  // frees the slot once these MMAs retire
             __syncwarp();
             if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
-          umma_commit_elect(&aempty_bar[sa]);  // halo tile consumed by all 9 taps
-          __syncwarp();
-          if (++sa == p.a_slots) { sa = 0; pha ^= 1u; }
         }
-      }
-      for (int si = 0; si < (halo ? 0 : s_iters); ++si) {
-        const int it0 = si * p.tps;
-        const int nsub = (k_iters - it0) < p.tps ? (k_iters - it0) : p.tps;
-        mbar_wait_warp(&full_bar[s], ph, 0x300u + s);
-        tc_fence_after();
-        const uint32_t st16 = smem_u32(smem + static_cast<size_t>(s) * stage_bytes) >> 4;
-        // descriptors are computed in warp-uniform code (uniform registers); each MMA is
-        // individually guarded by elect.sync, the form ptxas lowers without register moves
-        for (int u = 0; u < nsub; ++u) {
-          const uint32_t ad = st16 + static_cast<uint32_t>(u) * sub16;
-          const uint32_t bd = ad + a16;
-umma_bf16_x4_elect(d_tmem, dhi | static_cast<uint64_t>(ad), dhi | static_cast<uint64_t>(bd), idesc,
-                               accum, static_cast<uint32_t>(ksteps));
-            accum = 1u;
-        }
-        umma_commit_elect(&empty_bar[s]);  // frees the slot once these MMAs retire
+        umma_commit_elect(&tfull_bar[acc]);  // accumulator complete -> epilogue
         __syncwarp();
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        if (++acc == 2) { acc = 0; aph ^= 1u; }
       }
-      umma_commit_elect(&tfull_bar[acc]);  // accumulator complete -> epilogue
-      __syncwarp();
-      if (++acc == 2) { acc = 0; aph ^= 1u; }
-    }
+    };
+    if (ksteps == 4) tile_loop(std::integral_constant<int, 4>{});
+    else if (ksteps == 2) tile_loop(std::integral_constant<int, 2>{});
+    else tile_loop(std::integral_constant<int, 1>{});
   } else {
     // ================================ epilogue ====================================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read

@@ -181,6 +181,61 @@ __device__ __forceinline__ void umma_bf16_x4_elect(uint32_t d_tmem, uint64_t ade
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(ksteps)
       : "memory");
 }
+// One (tap, k-chunk) sub-tile: KS (1, 2 or 4) K=16 MMAs whose descriptors advance by 32 bytes.
+// Descriptors are passed as 32-bit halves (the high word is loop-invariant, the low word is
+// "address >> 4" and never carries out of its 14-bit field), which lets ptxas do the per-MMA
+// arithmetic with a handful of integer adds and register moves instead of 64-bit chains.
+template <int KS>
+__device__ __forceinline__ void umma_tap(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                         uint32_t b_hi, uint32_t idesc, uint32_t accumulate);
+template <>
+__device__ __forceinline__ void umma_tap<1>(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                            uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa;\n\t.reg .b64 a0, b0;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %6, 0;\n\t"
+      "mov.b64 a0, {%1, %2};\n\tmov.b64 b0, {%3, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a0, b0, %5, pa;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void umma_tap<2>(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                            uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 a0, b0, a1, b1;\n\t.reg .b32 l1, m1;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %6, 0;\n\tsetp.eq.u32 pt, 0, 0;\n\t"
+      "add.u32 l1, %1, 2;\n\tadd.u32 m1, %3, 2;\n\t"
+      "mov.b64 a0, {%1, %2};\n\tmov.b64 b0, {%3, %4};\n\t"
+      "mov.b64 a1, {l1, %2};\n\tmov.b64 b1, {m1, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a0, b0, %5, pa;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %5, pt;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void umma_tap<4>(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                            uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 a0, b0, a1, b1, a2, b2, a3, b3;\n\t"
+      ".reg .b32 l1, l2, l3, m1, m2, m3;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %6, 0;\n\tsetp.eq.u32 pt, 0, 0;\n\t"
+      "add.u32 l1, %1, 2;\n\tadd.u32 l2, %1, 4;\n\tadd.u32 l3, %1, 6;\n\t"
+      "add.u32 m1, %3, 2;\n\tadd.u32 m2, %3, 4;\n\tadd.u32 m3, %3, 6;\n\t"
+      "mov.b64 a0, {%1, %2};\n\tmov.b64 b0, {%3, %4};\n\t"
+      "mov.b64 a1, {l1, %2};\n\tmov.b64 b1, {m1, %4};\n\t"
+      "mov.b64 a2, {l2, %2};\n\tmov.b64 b2, {m2, %4};\n\t"
+      "mov.b64 a3, {l3, %2};\n\tmov.b64 b3, {m3, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a0, b0, %5, pa;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %5, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %5, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %5, pt;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"

@@ -248,7 +248,8 @@ extern "C" int rovr_unpack_nhwc_to_nchw(const void* src, int ld, float* dst, int
 }
 
 static int repack(const float* w, void* wk, int d0, int d1, int d2, long long s0, long long s1,
-                  long long s2, int v0, int v2, void* stream) {
+                  long long s2, int v0, int v2, void* stream, long long off = 0) {
+  w += off;
   if (int rc = ensure_device()) return rc;
   const long long n = 1ll * d0 * d1 * d2;
   repack_weights_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0,
@@ -263,8 +264,9 @@ extern "C" int rovr_repack_conv3x3_fprop(const float* w, void* wk, int Cout, int
 }
 extern "C" int rovr_repack_conv3x3_dgrad(const float* w, void* wk, int Cout, int Cin, int cin_pad,
                                          void* stream) {
-  // dst[ci][t][co] = w[co][ci][t]
-  return repack(w, wk, cin_pad, 9, Cout, 9, 1, 1ll * Cin * 9, Cin, Cout, stream);
+  // dst[ci][t][co] = w[co][ci][8 - t]: the 180-degree tap flip of the transposed convolution is
+  // baked into the packing, so dgrad runs the forward kernel unchanged (same tap geometry)
+  return repack(w, wk, cin_pad, 9, Cout, 9, -1, 1ll * Cin * 9, Cin, Cout, stream, 8);
 }
 extern "C" int rovr_repack_convT2x2_fprop(const float* w, void* wk, int Cin, int Cout, void* stream) {
   // dst[q][co][ci] = w[ci][co][q]
