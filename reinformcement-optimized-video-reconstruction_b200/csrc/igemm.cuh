@@ -29,8 +29,8 @@
 //             The ReLU mask of dgrad (the forward activation at the same coordinates) is
 //             prefetched by TMA into smem the same way.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue.
+// Warp roles (192 threads): warps 0..3 = epilogue, warp 4 = TMA producer,
+// warp 5 = TMEM owner + MMA issuer.
 #pragma once
 #include <type_traits>
 
@@ -42,6 +42,11 @@ constexpr int IG_MAX_STAGES = 8;
 constexpr int IG_MAX_TAPS = 9;
 constexpr int IG_THREADS = 192;
 constexpr int IG_EPI_THREADS = 128;
+// Warp roles. The four epilogue warps must be warps whose id % 4 covers the four TMEM lane
+// quarters, so each SM sub-partition hosts one of them; the MMA issuer gets the HIGHEST warp id
+// because the sub-partition arbiter favours higher warp ids, and the single-thread MMA issue
+// stream is the latency-critical path of the kernel.
+constexpr int IG_WARP_TMA = 4, IG_WARP_MMA = 5;
 // Halo mode (3x3 convolutions with Cin % 64 == 0): the M tile is an 8 x 16 pixel patch and its
 // (8+2) x (16+2) halo is fetched ONCE per 64-channel chunk (180 rows x 128 B). The nine taps are
 // nine K-major views of that one tile: tap (dy, dx) starts (dy*10 + dx) rows further on, each
@@ -169,7 +174,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int k_iters = p.ntaps * kchunks;
   const int s_iters = (k_iters + p.tps - 1) / p.tps;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == IG_WARP_TMA && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
@@ -190,7 +195,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     mbar_init(wfull_bar, 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+  if (warp == IG_WARP_MMA) tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
   for (int i = threadIdx.x; i < p.n_total; i += IG_THREADS)
     sbias[i] = p.bias ? p.bias[i % p.bias_mod] : 0.f;
   tc_fence_before();
@@ -198,7 +203,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == IG_WARP_TMA) {
     // ================================ TMA producer ================================
     {
       if (p.resident_b) {  // all weight tiles, once: tile index = t * kchunks + kc
@@ -270,7 +275,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == IG_WARP_MMA) {
     // ================================ MMA issuer ==================================
     // The whole warp walks the pipeline with warp-uniform control flow; waits are done by one
     // lane + __syncwarp, and every (tap, k-chunk) sub-tile is issued by one asm block
@@ -358,7 +363,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ================================ epilogue ====================================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
     const int m = quarter * 32 + lane;
-    const bool elected = (threadIdx.x == 64);
+    const bool elected = (threadIdx.x == 0);
     const int nblk = p.n_tile / p.cw;
     const int chunks = p.cw >> 4;
     int acc = 0;
@@ -514,7 +519,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == IG_WARP_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }

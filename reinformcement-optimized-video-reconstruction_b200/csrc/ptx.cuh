@@ -80,11 +80,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
   }
 }
 
-// Warp-converged wait: one lane polls, the warp reconverges. Keeps the surrounding loop
-// warp-uniform in the compiler's eyes (a per-lane polling loop makes every loop-carried value
-// look divergent and forces vector registers + R2UR in front of each tcgen05.mma).
+// Wait used by the single-warp producer / MMA roles. Every lane polls: measured on B200, letting
+// one lane poll and parking the other 31 at __syncwarp() made the MMA issue stream ~1.8x slower
+// (the lone poller is slow to observe the phase flip), so all 32 lanes spin and then reconverge.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, unsigned code) {
-  if ((threadIdx.x & 31u) == 0u) mbar_wait(bar, parity, code);
+  mbar_wait(bar, parity, code);
   __syncwarp();
 }
 
