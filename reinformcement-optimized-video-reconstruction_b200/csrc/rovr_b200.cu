@@ -19,6 +19,7 @@
 #include "norm.cuh"
 #include "tail.cuh"
 #include "wgrad.cuh"
+#include "wgrad_halo.cuh"
 
 using namespace rovr;
 
@@ -96,6 +97,7 @@ static void init_device() {
   g_dev.encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   g_dev.ok = 1;
 }
 static int ensure_device() {
