@@ -59,10 +59,14 @@ int rovr_repack_convT2x2_dgrad(const float* w, void* wk, int Cin, int Cout, void
  * rovr/policy_net_1.py:19-47,61-81; rovr/policy_net_2.py:42-54. Cin, Cout multiples of 16. */
 int rovr_conv3x3_fprop(const void* x, int x_ld, const void* wk, const float* bias, void* y, int y_ld,
                        int B, int H, int W, int Cin, int Cout, int relu, void* stream);
-/* dx = conv3x3^T(dy); if mask != NULL, dx *= (mask > 0) (ReLU of the producer of x). */
+/* dx = conv3x3^T(dy); if mask != NULL, dx *= (mask > 0) (ReLU of the producer of x).
+ * If colsum != NULL it receives sum over pixels of dx[pixel][c] for c < colsum_cols <= Cin (fp32) —
+ * the bias gradient of the layer that produced those channels of x — computed in the epilogue;
+ * ws >= rovr_dgrad_colsum_workspace(B,H,W,Cin). */
+size_t rovr_dgrad_colsum_workspace(int B, int H, int W, int C);
 int rovr_conv3x3_dgrad(const void* dy, int dy_ld, const void* wk_d, void* dx, int dx_ld,
                        const void* mask, int mask_ld, int B, int H, int W, int Cin, int Cout,
-                       void* stream);
+                       float* colsum, int colsum_cols, void* ws, size_t ws_bytes, void* stream);
 size_t rovr_conv3x3_wgrad_workspace(int B, int H, int W, int Cin, int Cout);
 /* dw[Cout][cin_keep][3][3] (fp32) = sum_pixels dy (x) x_shifted; Cin is the padded channel count
  * of x, cin_keep <= Cin the true one. */
@@ -78,7 +82,7 @@ int rovr_convT2x2_fprop(const void* x, int x_ld, const void* wk, const float* bi
                         int B, int H, int W, int Cin, int Cout, int relu, void* stream);
 int rovr_convT2x2_dgrad(const void* dy, int dy_ld, const void* wk_d, void* dx, int dx_ld,
                         const void* mask, int mask_ld, int B, int H, int W, int Cin, int Cout,
-                        void* stream);
+                        float* colsum, int colsum_cols, void* ws, size_t ws_bytes, void* stream);
 size_t rovr_convT2x2_wgrad_workspace(int B, int H, int W, int Cin, int Cout);
 int rovr_convT2x2_wgrad(const void* dy, int dy_ld, const void* x, int x_ld, float* dw, int B, int H,
                         int W, int Cin, int Cout, void* ws, size_t ws_bytes, void* stream);

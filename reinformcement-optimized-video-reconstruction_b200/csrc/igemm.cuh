@@ -94,6 +94,9 @@ struct IgemmParams {
   int shuf_cout;          // pixel-shuffle: channels per quadrant
   const float* bias;      // may be null
   float* out_f32;         // non-null: direct fp32 epilogue (plain mode) instead of the TMA store
+  float* colsum_partial;  // non-null: per-(M tile, lane quarter) column sums of the bf16 output,
+                          // [m_tiles * 4][n_total] fp32 — the bias gradient of the layer that
+                          // consumes this gradient tensor, reduced afterwards in a fixed order
 };
 
 // ---- TMA store / bulk-group helpers ------------------------------------------------------------
@@ -459,6 +462,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       long long gb = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles_n;
+        uint32_t my_valid = 0xffffffffu;
+        if (p.colsum_partial) {  // which rows of this tile are real output pixels
+          int mt = tile / p.n_tiles_n, mm = m;
+          bool v = m < rows;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int pj = (mt % p.ntile[j]) * p.boxM[j] + (mm % p.boxM[j]);
+            mt /= p.ntile[j];
+            mm /= p.boxM[j];
+            v = v && (pj < p.dimM[j]);
+          }
+          my_valid = __ballot_sync(0xffffffffu, v);
+        }
         mbar_wait(&tfull_bar[acc], aph, 0x400u + acc);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
@@ -500,6 +516,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
           epi_bar_sync();
+          if (p.colsum_partial && lane < (p.cw >> 1)) {
+            // this warp sums its 32 rows of the staged (bf16-rounded) block, two columns per lane;
+            // bank-conflict free: for a fixed row the 32 lanes read 32 consecutive words
+            float s0 = 0.f, s1 = 0.f;
+            for (int r = 0; r < 32; ++r) {
+              if ((my_valid >> r) & 1u) {
+                const uint32_t u = *reinterpret_cast<const uint32_t*>(
+                    stg + swz_off(quarter * 32 + r, lane >> 2, epi_rowb) + (lane & 3) * 4);
+                s0 += bf16_lo(u);
+                s1 += bf16_hi(u);
+              }
+            }
+            const long long prow = static_cast<long long>(tile / p.n_tiles_n) * 4 + quarter;
+            *reinterpret_cast<float2*>(p.colsum_partial + prow * p.n_total + nglb + 2 * lane) =
+                make_float2(s0, s1);
+          }
           if (elected) {
             int c[5];
             block_coords(gb, c);

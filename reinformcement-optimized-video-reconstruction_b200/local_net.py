@@ -160,39 +160,33 @@ class _LocalNetFunction(torch.autograd.Function):
         # ---- conv7 (its bias gradient came out of the tail kernel) ----
         ops.conv3x3_wgrad(g7, a["cat7"], G["conv7.weight"])
         gcat7 = el(a["cat7"])
-        ops.conv3x3_dgrad(g7, wd("conv7"), gcat7, mask=a["cat7"])
+        ops.conv3x3_dgrad(g7, wd("conv7"), gcat7, mask=a["cat7"], colsum=G["upconv3.bias"])
         # ---- upconv3 ----
         gu3 = gcat7[..., :64]
         ops.convT2x2_wgrad(gu3, a["y6"], G["upconv3.weight"])
-        ops.colsum(gu3, G["upconv3.bias"])
         g6 = el(a["y6"])
-        ops.convT2x2_dgrad(gu3, wd("upconv3", "up"), g6, mask=a["y6"])
+        ops.convT2x2_dgrad(gu3, wd("upconv3", "up"), g6, mask=a["y6"], colsum=G["conv6.bias"])
         # ---- conv6 ----
         ops.conv3x3_wgrad(g6, a["cat6"], G["conv6.weight"])
-        ops.colsum(g6, G["conv6.bias"])
         gcat6 = el(a["cat6"])
-        ops.conv3x3_dgrad(g6, wd("conv6"), gcat6, mask=a["cat6"])
+        ops.conv3x3_dgrad(g6, wd("conv6"), gcat6, mask=a["cat6"], colsum=G["upconv2.bias"])
         # ---- upconv2 ----
         gu2 = gcat6[..., :128]
         ops.convT2x2_wgrad(gu2, a["y5"], G["upconv2.weight"])
-        ops.colsum(gu2, G["upconv2.bias"])
         g5 = el(a["y5"])
-        ops.convT2x2_dgrad(gu2, wd("upconv2", "up"), g5, mask=a["y5"])
+        ops.convT2x2_dgrad(gu2, wd("upconv2", "up"), g5, mask=a["y5"], colsum=G["conv5.bias"])
         # ---- conv5 ----
         ops.conv3x3_wgrad(g5, a["cat5"], G["conv5.weight"])
-        ops.colsum(g5, G["conv5.bias"])
         gcat5 = el(a["cat5"])
-        ops.conv3x3_dgrad(g5, wd("conv5"), gcat5, mask=a["cat5"])
+        ops.conv3x3_dgrad(g5, wd("conv5"), gcat5, mask=a["cat5"], colsum=G["upconv1.bias"])
         # ---- upconv1 ----
         gu1 = gcat5[..., :256]
         ops.convT2x2_wgrad(gu1, a["x4"], G["upconv1.weight"])
-        ops.colsum(gu1, G["upconv1.bias"])
         g4 = el(a["x4"])
-        ops.convT2x2_dgrad(gu1, wd("upconv1", "up"), g4, mask=a["x4"])
+        ops.convT2x2_dgrad(gu1, wd("upconv1", "up"), g4, mask=a["x4"], colsum=G["conv4.bias"])
         net._bucket_ready(0, dec_flat)
         # ---- conv4 ----
         ops.conv3x3_wgrad(g4, a["p3"], G["conv4.weight"])
-        ops.colsum(g4, G["conv4.bias"])
         gp3 = el(a["p3"])
         ops.conv3x3_dgrad(g4, wd("conv4"), gp3)
         g3 = torch.empty((B, H // 4, W // 4, 256), dtype=bf, device=dev)

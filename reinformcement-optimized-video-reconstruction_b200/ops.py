@@ -151,7 +151,17 @@ def conv3x3_fprop(x, wk, bias, y, relu=True):
     return y
 
 
-def conv3x3_dgrad(dy, wk_d, dx, mask=None):
+def _colsum_ws(colsum, B, H, W, C, device):
+    if colsum is None:
+        return _vp(0), 0, _vp(0), 0
+    _f32(colsum, "colsum")
+    assert 0 < colsum.numel() <= C
+    ws = workspace(N.lib.rovr_dgrad_colsum_workspace(B, H, W, C), device)
+    return _ptr(colsum), colsum.numel(), _ptr(ws), ws.numel()
+
+
+def conv3x3_dgrad(dy, wk_d, dx, mask=None, colsum=None):
+    """dx = conv^T(dy) [* (mask > 0)]; colsum (fp32 [Cin]) optionally receives sum_pixels dx."""
     B, H, W, Cout, dy_ld = _act(dy, "dy")
     Bx, Hx, Wx, Cin, dx_ld = _act(dx, "dx")
     assert (B, H, W) == (Bx, Hx, Wx) and wk_d.shape == (Cin, 9 * Cout), (dy.shape, dx.shape, wk_d.shape)
@@ -159,8 +169,9 @@ def conv3x3_dgrad(dy, wk_d, dx, mask=None):
     if mask is not None:
         Bm, Hm, Wm, Cm, mask_ld = _act(mask, "mask")
         assert (Bm, Hm, Wm, Cm) == (B, H, W, Cin)
+    cs, ncs, ws, wsn = _colsum_ws(colsum, B, H, W, Cin, dy.device)
     _launch("rovr_conv3x3_dgrad", _ptr(dy), dy_ld, _ptr(wk_d), _ptr(dx), dx_ld, _ptr(mask), mask_ld,
-           B, H, W, Cin, Cout, _stream())
+           B, H, W, Cin, Cout, cs, ncs, ws, wsn, _stream())
     return dx
 
 
@@ -193,7 +204,7 @@ def convT2x2_fprop(x, wk, bias, y, relu=True):
     return y
 
 
-def convT2x2_dgrad(dy, wk_d, dx, mask=None):
+def convT2x2_dgrad(dy, wk_d, dx, mask=None, colsum=None):
     By, Hy, Wy, Cout, dy_ld = _act(dy, "dy")
     B, H, W, Cin, dx_ld = _act(dx, "dx")
     assert (By, Hy, Wy) == (B, 2 * H, 2 * W) and wk_d.shape == (Cin, 4 * Cout)
@@ -202,8 +213,9 @@ def convT2x2_dgrad(dy, wk_d, dx, mask=None):
     if mask is not None:
         Bm, Hm, Wm, Cm, mask_ld = _act(mask, "mask")
         assert (Bm, Hm, Wm, Cm) == (B, H, W, Cin)
+    cs, ncs, ws, wsn = _colsum_ws(colsum, B, H, W, Cin, dy.device)
     _launch("rovr_convT2x2_dgrad", _ptr(dy), dy_ld, _ptr(wk_d), _ptr(dx), dx_ld, _ptr(mask), mask_ld,
-           B, H, W, Cin, Cout, _stream())
+           B, H, W, Cin, Cout, cs, ncs, ws, wsn, _stream())
     return dx
 
 

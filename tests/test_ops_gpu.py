@@ -98,10 +98,17 @@ def test_conv3x3_dgrad(B, H, W, Cin, Cout):
     xmask = _rand_act((B, H, W, Cin), g, dev, relu=True)
     wd = ops.repack_conv3x3(w, for_dgrad=True)
     dx = torch.empty((B, H, W, Cin), dtype=BF, device=dev)
-    ops.conv3x3_dgrad(dy, wd, dx, mask=xmask)
+    colsum = torch.full((Cin,), 123.0, device=dev)
+    ops.conv3x3_dgrad(dy, wd, dx, mask=xmask, colsum=colsum)
     torch.cuda.synchronize()
     ref = F.conv_transpose2d(_nchw(dy), w.to(BF).float(), padding=1) * (_nchw(xmask) > 0)
     _report(f"conv3x3_dgrad{(B, H, W, Cin, Cout)}", _nchw(dx), ref, 1e-2)
+    # fused bias gradient = column sums of the stored (bf16) gradient
+    _report("conv3x3_dgrad.colsum", colsum, dx.float().sum(dim=(0, 1, 2)), 1e-3)
+    half = torch.full((Cin // 2,), 5.0, device=dev)  # only the first half of the channels (upconv bias)
+    ops.conv3x3_dgrad(dy, wd, dx, mask=xmask, colsum=half)
+    torch.cuda.synchronize()
+    _report("conv3x3_dgrad.colsum[:half]", half, dx.float().sum(dim=(0, 1, 2))[: Cin // 2], 1e-3)
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", CONV_SHAPES)
@@ -159,10 +166,12 @@ def test_convT2x2_dgrad(B, H, W, Cin, Cout):
     xmask = _rand_act((B, H, W, Cin), g, dev, relu=True)
     wd = ops.repack_convT2x2(w, for_dgrad=True)
     dx = torch.empty((B, H, W, Cin), dtype=BF, device=dev)
-    ops.convT2x2_dgrad(dy, wd, dx, mask=xmask)
+    colsum = torch.full((Cin,), 123.0, device=dev)
+    ops.convT2x2_dgrad(dy, wd, dx, mask=xmask, colsum=colsum)
     torch.cuda.synchronize()
     ref = F.conv2d(_nchw(dy), w.to(BF).float(), stride=2) * (_nchw(xmask) > 0)
     _report(f"convT2x2_dgrad{(B, H, W, Cin, Cout)}", _nchw(dx), ref, 1e-2)
+    _report("convT2x2_dgrad.colsum", colsum, dx.float().sum(dim=(0, 1, 2)), 1e-3)
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", CONVT_SHAPES)
