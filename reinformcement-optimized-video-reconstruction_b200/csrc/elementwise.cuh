@@ -214,21 +214,26 @@ __global__ void sum_partials_kernel(const float* __restrict__ partial, int n, fl
 // ~30x faster than one thread per column.
 __global__ void __launch_bounds__(256)
 reduce_rows_kernel(const float* __restrict__ partial, int nrows, int row_stride, int ncols,
-                   float* __restrict__ out, int accumulate) {
+                   float* __restrict__ out, int accumulate, int rows_per_chunk = 0,
+                   int out_stride = 0) {
+  // blockIdx.y selects a chunk of rows (two-stage reduction of very tall partial buffers);
+  // with gridDim.y == 1 the whole buffer is reduced straight into `out`.
   __shared__ float sred[8][33];
   const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + cl;
+  const int r_begin = rows_per_chunk > 0 ? blockIdx.y * rows_per_chunk : 0;
+  const int r_end = rows_per_chunk > 0 ? min(nrows, r_begin + rows_per_chunk) : nrows;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (j < ncols) {
     const float* p = partial + j;
-    int r = rg;
-    for (; r + 24 < nrows; r += 32) {
+    int r = r_begin + rg;
+    for (; r + 24 < r_end; r += 32) {
       a0 += __ldg(p + static_cast<long long>(r) * row_stride);
       a1 += __ldg(p + static_cast<long long>(r + 8) * row_stride);
       a2 += __ldg(p + static_cast<long long>(r + 16) * row_stride);
       a3 += __ldg(p + static_cast<long long>(r + 24) * row_stride);
     }
-    for (; r < nrows; r += 8) a0 += __ldg(p + static_cast<long long>(r) * row_stride);
+    for (; r < r_end; r += 8) a0 += __ldg(p + static_cast<long long>(r) * row_stride);
   }
   sred[rg][cl] = (a0 + a1) + (a2 + a3);
   __syncthreads();
@@ -236,7 +241,8 @@ reduce_rows_kernel(const float* __restrict__ partial, int nrows, int row_stride,
     float s = 0.f;
 #pragma unroll
     for (int g = 0; g < 8; ++g) s += sred[g][cl];
-    out[j] = accumulate ? out[j] + s : s;
+    float* o = out + static_cast<long long>(blockIdx.y) * out_stride + j;
+    *o = accumulate ? *o + s : s;
   }
 }
 
