@@ -29,8 +29,8 @@
 //             The ReLU mask of dgrad (the forward activation at the same coordinates) is
 //             prefetched by TMA into smem the same way.
 //
-// Warp roles (192 threads): warps 0..3 = epilogue, warp 4 = TMA producer,
-// warp 5 = TMEM owner + MMA issuer.
+// Warp roles (320 threads): warps 0..7 = two epilogue groups, warp 8 = TMA producer,
+// warp 9 = TMEM owner + MMA issuer.
 #pragma once
 #include <type_traits>
 
@@ -40,13 +40,13 @@ namespace rovr {
 
 constexpr int IG_MAX_STAGES = 8;
 constexpr int IG_MAX_TAPS = 9;
-constexpr int IG_THREADS = 192;
+constexpr int IG_THREADS = 320;
 constexpr int IG_EPI_THREADS = 128;
 // Warp roles. The four epilogue warps must be warps whose id % 4 covers the four TMEM lane
 // quarters, so each SM sub-partition hosts one of them; the MMA issuer gets the HIGHEST warp id
 // because the sub-partition arbiter favours higher warp ids, and the single-thread MMA issue
 // stream is the latency-critical path of the kernel.
-constexpr int IG_WARP_TMA = 4, IG_WARP_MMA = 5;
+constexpr int IG_WARP_TMA = 8, IG_WARP_MMA = 9;
 // Halo mode (3x3 convolutions with Cin % 64 == 0): the M tile is an 8 x 16 pixel patch and its
 // (8+2) x (16+2) halo is fetched ONCE per 64-channel chunk (180 rows x 128 B). The nine taps are
 // nine K-major views of that one tile: tap (dy, dx) starts (dy*10 + dx) rows further on, each
@@ -93,6 +93,8 @@ struct IgemmParams {
   int bias_mod;           // bias index = n % bias_mod
   int shuf_cout;          // pixel-shuffle: channels per quadrant
   const float* bias;      // may be null
+  const __nv_bfloat16* mask;  // non-null: out *= (mask > 0); same pixel space as the output
+  long long mstride[4];   // mask element stride per tiled dim
   float* out_f32;         // non-null: direct fp32 epilogue (plain mode) instead of the TMA store
   float* colsum_partial;  // non-null: per-(M tile, lane quarter) column sums of the bf16 output,
                           // [m_tiles * 4][n_total] fp32 — the bias gradient of the layer that
@@ -159,8 +161,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* aring = smem + front_bytes;                                           // halo tiles
   aring += (1024u - (smem_u32(aring) & 1023u)) & 1023u;                          // swizzle alignment
   uint8_t* stg_base = aring + (halo ? p.a_slots * halo_slot : 0);                // 2 staging tiles
-  uint8_t* msk_base = stg_base + 2 * stg_bytes;                                  // 2 mask tiles
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(msk_base + (p.has_mask ? 2 * stg_bytes : 0));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + 2 * stg_bytes);
   uint64_t* empty_bar = full_bar + IG_MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + IG_MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -181,7 +182,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
-    if (p.has_mask) tma_prefetch_desc(&tmMask);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -364,17 +364,32 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     else tile_loop(std::integral_constant<int, 1>{});
   } else {
     // ================================ epilogue ====================================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    // Two groups of four warps. Group g drains accumulator stage g — every other tile of this
+    // CTA — so two tiles are in their epilogue at once (thin-K layers are epilogue-bound).
+    //   pass 1: TMEM -> registers (thread = output row) -> bias / ReLU -> bf16 -> swizzled smem;
+    //   pass 2 (dgrad only): each warp re-reads its 32 staged rows with a coalescing-friendly
+    //           mapping (one 16-byte chunk per lane, 32/cpr rows per instruction), applies the ReLU
+    //           mask fetched from global memory with the same mapping (full 128-byte lines,
+    //           prefetched into registers before the accumulator is even ready) and accumulates
+    //           the per-column sums that become the bias gradient;
+    //   then one TMA store per 64-channel block (ragged tiles are clipped by the TMA unit).
+    const int grp = warp >> 2;
+    const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
-    const bool elected = (threadIdx.x == 0);
+    const bool elected = (quarter == 0 && lane == 0);
     const int nblk = p.n_tile / p.cw;
     const int chunks = p.cw >> 4;
-    int acc = 0;
+    uint8_t* stg = stg_base + grp * stg_bytes;
+    const int acc = grp;
     uint32_t aph = 0;
+    const int cpr = epi_rowb >> 4;        // 16-byte chunks per staged row: 8 / 4 / 2
+    const int rpi = 32 / cpr;             // rows covered by one warp instruction in pass 2
+    const int my_c = lane % cpr, my_r = lane / cpr;
+    const bool pass2 = (p.mask != nullptr) || (p.colsum_partial != nullptr);
 
     if (p.out_f32 != nullptr) {
       // ---- direct fp32 epilogue (small GEMMs whose consumer wants fp32) ----
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x) {
         const int nt = tile % p.n_tiles_n;
         int mt = tile / p.n_tiles_n;
         bool valid = m < rows;
@@ -417,138 +432,206 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        if (++acc == 2) { acc = 0; aph ^= 1u; }
+        aph ^= 1u;
       }
     } else {
-      // ---- bf16 epilogue: TMEM -> regs -> swizzled smem staging -> TMA store ----
-      // gb counts column blocks handled by this CTA; staging / mask buffers are gb & 1.
-      const int my_tiles = (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                           static_cast<int>(gridDim.x);
-      const long long total_blocks = static_cast<long long>(my_tiles) * nblk;
-      const uint32_t mask_tx = static_cast<uint32_t>(rows) * epi_rowb;
-
-      // coordinates of column block `g` (in this CTA's sequence)
-      auto block_coords = [&](long long g, int* c) {
-        const int tile = static_cast<int>(blockIdx.x) + static_cast<int>(g / nblk) * static_cast<int>(gridDim.x);
-        const int cb = static_cast<int>(g % nblk);
-        const int nt = tile % p.n_tiles_n;
-        int mt = tile / p.n_tiles_n;
+      // Per-lane geometry of the pass-2 rows (fixed for the whole kernel): local pixel coordinates
+      // packed 4 x 8 bit, and the mask offset of the row inside a tile in 16-byte units.
+      uint32_t lpack[8], loff16[8], rowok = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          c[1 + j] = (mt % p.ntile[j]) * p.boxM[j];
-          mt /= p.ntile[j];
-        }
-        const int n0 = nt * p.n_tile + cb * p.cw;
-        if (p.epi_mode == IG_EPI_PIXSHUF) {
-          const int q = n0 / p.shuf_cout;
-          c[0] = n0 - q * p.shuf_cout;
-          c[1] += q & 1;
-          c[3] += q >> 1;
-        } else {
-          c[0] = n0;
-        }
-      };
-      auto issue_mask = [&](long long g) {
-        int c[5];
-        block_coords(g, c);
-        const int sb = static_cast<int>(g & 1);
-        mbar_expect_tx(&mfull_bar[sb], mask_tx);
-        tma_load_5d(&tmMask, &mfull_bar[sb], msk_base + sb * stg_bytes, c[0], c[1], c[2], c[3], c[4]);
-      };
-      if (p.has_mask && elected) {
-        if (total_blocks > 0) issue_mask(0);
-        if (total_blocks > 1) issue_mask(1);
-      }
-      long long gb = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles_n;
-        uint32_t my_valid = 0xffffffffu;
-        if (p.colsum_partial) {  // which rows of this tile are real output pixels
-          int mt = tile / p.n_tiles_n, mm = m;
-          bool v = m < rows;
+      for (int i = 0; i < 8; ++i) {
+        lpack[i] = 0; loff16[i] = 0;
+        if (pass2 && i < cpr) {
+          int mm = quarter * 32 + i * rpi + my_r;
+          if (mm < rows) rowok |= 1u << i;
+          long long off = 0;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int pj = (mt % p.ntile[j]) * p.boxM[j] + (mm % p.boxM[j]);
-            mt /= p.ntile[j];
+            const int lj = mm % p.boxM[j];
             mm /= p.boxM[j];
-            v = v && (pj < p.dimM[j]);
+            lpack[i] |= static_cast<uint32_t>(lj) << (8 * j);
+            off += static_cast<long long>(lj) * p.mstride[j];
           }
-          my_valid = __ballot_sync(0xffffffffu, v);
+          loff16[i] = static_cast<uint32_t>(off >> 3);
         }
+      }
+      const uint4* mask16 = reinterpret_cast<const uint4*>(p.mask);
+      // tile geometry: origin, validity bits of this lane's pass-2 rows, mask base (16-byte units)
+      auto tile_setup = [&](int tile, int* org, uint32_t& vbits, long long& mbase16) {
+        int mt = tile / p.n_tiles_n;
+        long long base = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          org[j] = (mt % p.ntile[j]) * p.boxM[j];
+          mt /= p.ntile[j];
+          base += static_cast<long long>(org[j]) * p.mstride[j];
+        }
+        mbase16 = base >> 3;
+        vbits = 0;
+        if (pass2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            bool v = (rowok >> i) & 1u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              v = v && (org[j] + static_cast<int>((lpack[i] >> (8 * j)) & 255u) < p.dimM[j]);
+            vbits |= (v ? 1u : 0u) << i;
+          }
+        }
+      };
+      auto mask_fetch = [&](uint4* mreg, uint32_t vbits, long long mbase16, int nglb) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          mreg[i] = make_uint4(0, 0, 0, 0);
+          if (i < cpr && ((vbits >> i) & 1u))
+            mreg[i] = __ldg(mask16 + mbase16 + loff16[i] + (nglb >> 3) + my_c);
+        }
+      };
+      const int tstep = 2 * static_cast<int>(gridDim.x);
+      int tile = static_cast<int>(blockIdx.x) + grp * static_cast<int>(gridDim.x);
+      int org[4] = {0, 0, 0, 0};
+      uint32_t vbits = 0;
+      long long mbase16 = 0;
+      uint4 mreg[8];
+      if (tile < total_tiles) {
+        tile_setup(tile, org, vbits, mbase16);
+        if (p.mask != nullptr) mask_fetch(mreg, vbits, mbase16, (tile % p.n_tiles_n) * p.n_tile);
+      }
+      while (tile < total_tiles) {
+        const int nt = tile % p.n_tiles_n;
+        const int tile_m = tile / p.n_tiles_n;
+        const int ntile_next = tile + tstep;
+        int org_n[4] = {0, 0, 0, 0};
+        uint32_t vbits_n = 0;
+        long long mbase16_n = 0;
         mbar_wait(&tfull_bar[acc], aph, 0x400u + acc);
         tc_fence_after();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                               static_cast<uint32_t>(acc * p.n_tile);
-        for (int cb = 0; cb < nblk; ++cb, ++gb) {
-          const int sb = static_cast<int>(gb & 1);
-          uint8_t* stg = stg_base + sb * stg_bytes;
-          const uint8_t* msk = msk_base + sb * stg_bytes;
-          if (p.has_mask) mbar_wait(&mfull_bar[sb], static_cast<uint32_t>((gb >> 1) & 1), 0x800u + sb);
-          if (elected) bulk_wait_read<1>();  // the store that last read staging[sb] has drained
-          epi_bar_sync();
-          const int nloc = cb * p.cw;            // column offset inside the tile
-          const int nglb = nt * p.n_tile + nloc;  // global column (bias index)
-          for (int ch = 0; ch < chunks; ++ch) {
-            uint32_t v[16];
-            tmem_ld16(t_row + static_cast<uint32_t>(nloc + ch * 16), v);
-            tmem_ld_wait();
-            float f[16];
+        for (int cb = 0; cb < nblk; ++cb) {
+          const int nloc = cb * p.cw;
+          const int nglb = nt * p.n_tile + nloc;
+          // (b) staging buffer free again? (the previous TMA store of this group has read it)
+          if (elected) bulk_wait_read<0>();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+          // (c) pass 1
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                 static_cast<uint32_t>(acc * p.n_tile + nloc);
+          // (a) ReLU-mask values of the NEXT column block (possibly of the next tile) straight into
+          // registers: their DRAM latency hides behind this block's two passes
+          uint4 mnext[8];
+          if (cb + 1 < nblk) {
+            if (p.mask != nullptr) mask_fetch(mnext, vbits, mbase16, nglb + p.cw);
+          } else if (ntile_next < total_tiles) {
+            tile_setup(ntile_next, org_n, vbits_n, mbase16_n);
+            if (p.mask != nullptr) mask_fetch(mnext, vbits_n, mbase16_n, (ntile_next % p.n_tiles_n) * p.n_tile);
+          }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              f[j] = __uint_as_float(v[j]) + sbias[nglb + ch * 16 + j];
-              if (p.relu) f[j] = fmaxf(f[j], 0.f);
-            }
-            const uint32_t o0 = swz_off(m, ch * 2, epi_rowb), o1 = swz_off(m, ch * 2 + 1, epi_rowb);
-            if (p.has_mask) {
-              const uint4 m0 = *reinterpret_cast<const uint4*>(msk + o0);
-              const uint4 m1 = *reinterpret_cast<const uint4*>(msk + o1);
-              const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          for (int h = 0; h < 2; ++h) {  // two 32-column halves keep the live registers down
+            if (2 * h < chunks) {
+              uint32_t v[2][16];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (!(bf16_lo(mw[j]) > 0.f)) f[2 * j] = 0.f;
-                if (!(bf16_hi(mw[j]) > 0.f)) f[2 * j + 1] = 0.f;
+              for (int c2 = 0; c2 < 2; ++c2)
+                if (2 * h + c2 < chunks) tmem_ld16(t_row + static_cast<uint32_t>((2 * h + c2) * 16), v[c2]);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c2 = 0; c2 < 2; ++c2) {
+                const int ch = 2 * h + c2;
+                if (ch < chunks) {
+                  float f[16];
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    f[j] = __uint_as_float(v[c2][j]) + sbias[nglb + ch * 16 + j];
+                    if (p.relu) f[j] = fmaxf(f[j], 0.f);
+                  }
+                  *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2, epi_rowb)) =
+                      make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                 pack_bf16x2(f[6], f[7]));
+                  *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2 + 1, epi_rowb)) =
+                      make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                                 pack_bf16x2(f[14], f[15]));
+                }
               }
             }
-            *reinterpret_cast<uint4*>(stg + o0) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                                             pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-            *reinterpret_cast<uint4*>(stg + o1) = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
-                                                             pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+          }
+          if (cb == nblk - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          if (pass2) {
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            // (d) pass 2: mask + column sums on 16-byte chunks
+            float cs[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cs[j] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (i < cpr) {
+                const int r = quarter * 32 + i * rpi + my_r;
+                uint4* sp = reinterpret_cast<uint4*>(stg + swz_off(r, my_c, epi_rowb));
+                uint4 q = *sp;
+                uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                if (p.mask != nullptr) {
+                  const uint32_t mw[4] = {mreg[i].x, mreg[i].y, mreg[i].z, mreg[i].w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    if (!(bf16_lo(mw[j]) > 0.f)) w[j] &= 0xFFFF0000u;
+                    if (!(bf16_hi(mw[j]) > 0.f)) w[j] &= 0x0000FFFFu;
+                  }
+                  *sp = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                if ((vbits >> i) & 1u) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    cs[2 * j] += bf16_lo(w[j]);
+                    cs[2 * j + 1] += bf16_hi(w[j]);
+                  }
+                }
+              }
+            }
+            if (p.colsum_partial != nullptr) {
+              for (int o = cpr; o < 32; o <<= 1) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], o);
+              }
+              if (lane < cpr) {
+                float4* dst = reinterpret_cast<float4*>(
+                    p.colsum_partial + (static_cast<long long>(tile_m) * 4 + quarter) * p.n_total + nglb + lane * 8);
+                dst[0] = make_float4(cs[0], cs[1], cs[2], cs[3]);
+                dst[1] = make_float4(cs[4], cs[5], cs[6], cs[7]);
+              }
+            }
           }
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
-          epi_bar_sync();
-          if (p.colsum_partial && lane < (p.cw >> 1)) {
-            // this warp sums its 32 rows of the staged (bf16-rounded) block, two columns per lane;
-            // bank-conflict free: for a fixed row the 32 lanes read 32 consecutive words
-            float s0 = 0.f, s1 = 0.f;
-            for (int r = 0; r < 32; ++r) {
-              if ((my_valid >> r) & 1u) {
-                const uint32_t u = *reinterpret_cast<const uint32_t*>(
-                    stg + swz_off(quarter * 32 + r, lane >> 2, epi_rowb) + (lane & 3) * 4);
-                s0 += bf16_lo(u);
-                s1 += bf16_hi(u);
-              }
-            }
-            const long long prow = static_cast<long long>(tile / p.n_tiles_n) * 4 + quarter;
-            *reinterpret_cast<float2*>(p.colsum_partial + prow * p.n_total + nglb + 2 * lane) =
-                make_float2(s0, s1);
-          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
           if (elected) {
             int c[5];
-            block_coords(gb, c);
+            c[1] = org[0]; c[2] = org[1]; c[3] = org[2]; c[4] = org[3];
+            if (p.epi_mode == IG_EPI_PIXSHUF) {
+              const int q = nglb / p.shuf_cout;
+              c[0] = nglb - q * p.shuf_cout;
+              c[1] += q & 1;
+              c[3] += q >> 1;
+            } else {
+              c[0] = nglb;
+            }
             tma_store_5d(&tmOut, stg, c[0], c[1], c[2], c[3], c[4]);
             bulk_commit();
-            if (p.has_mask && gb + 2 < total_blocks) issue_mask(gb + 2);  // mask[sb] is free again
+          }
+          if (p.mask != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mreg[i] = mnext[i];
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        if (++acc == 2) { acc = 0; aph ^= 1u; }
+        aph ^= 1u;
+        tile = ntile_next;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) org[j] = org_n[j];
+        vbits = vbits_n;
+        mbase16 = mbase16_n;
       }
       if (elected) bulk_wait_all<0>();
     }
   }
-
   tc_fence_before();
   __syncthreads();
   if (warp == IG_WARP_MMA) {
@@ -559,8 +642,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
 // Fixed (non-pipeline) shared memory of a configuration (host side).
 inline size_t igemm_fixed_smem(int cw, int has_mask, int n_total, int a_slots = 0, int sw = 128) {
+  (void)has_mask;  // the ReLU mask no longer lives in shared memory
   const size_t stg = 128 * static_cast<size_t>(cw) * 2;
-  return 2048 + static_cast<size_t>(a_slots) * ig_halo_slot(sw) + 2 * stg + (has_mask ? 2 * stg : 0) +
+  return 2048 + static_cast<size_t>(a_slots) * ig_halo_slot(sw) + 2 * stg +
          (2 * IG_MAX_STAGES + 2 * IG_MAX_ASLOTS + 7) * 8 + 16 +
          static_cast<size_t>(n_total) * 4 + 64;
 }
