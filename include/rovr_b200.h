@@ -54,6 +54,10 @@ int rovr_repack_convT2x2_fprop(const float* w, void* wk, int Cin, int Cout, void
 /* ConvTranspose2d 2x2 weight -> [Cin][4*Cout] */
 int rovr_repack_convT2x2_dgrad(const float* w, void* wk, int Cin, int Cout, void* stream);
 
+/* nn.Linear / Conv2d 1x1 weight [N][K] -> bf16 [n_pad][k_pad], or transposed [k_pad][n_pad] */
+int rovr_repack_linear(const float* w, void* wk, int N, int K, int n_pad, int k_pad, int transpose,
+                       void* stream);
+
 /* ---- Conv2d 3x3, padding 1 (+bias, +ReLU) ---------------------------------------------------
  * Replaces nn.Conv2d(k=3,p=1) + F.relu: rovr/local_net.py:12-18,26,31,36,52-68;
  * rovr/policy_net_1.py:19-47,61-81; rovr/policy_net_2.py:42-54. Cin, Cout multiples of 16. */
@@ -92,6 +96,14 @@ int rovr_convT2x2_wgrad(const void* dy, int dy_ld, const void* x, int x_ld, floa
 int rovr_gemm_bf16(const void* x, int x_ld, const void* wk, const float* bias, void* y_bf16,
                    float* y_f32, int y_ld, int M, int N, int K, int relu, void* stream);
 
+/* weight gradient of the same: dw[n_keep][k_keep] (fp32, dense) = sum_m dy[m][n] x[m][k] over bf16
+ * row-major operands (N, K multiples of 16 are the padded widths). Used for 1x1 convolutions
+ * (rovr/policy_net_1.py:46,48) and the attention / feed-forward projections
+ * (rovr/common_layers.py:58,70,84-85). */
+size_t rovr_gemm_wgrad_workspace(long long M, int N, int K);
+int rovr_gemm_wgrad(const void* dy, int dy_ld, const void* x, int x_ld, float* dw, long long M, int N,
+                    int n_keep, int K, int k_keep, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- max pooling -----------------------------------------------------------------------------
  * nn.MaxPool2d: rovr/local_net.py:21,53-55; rovr/policy_net_1.py:29; rovr/policy_net_2.py:45-58. */
 int rovr_maxpool_fwd(const void* x, int x_ld, void* y, int y_ld, int B, int H, int W, int C, int kh,
@@ -115,6 +127,92 @@ int rovr_tail_bwd(const void* y7, const float* w8, const float* out, const float
                   const float* target, float mse_scale, const float* gloss, void* g7, float* dw8,
                   float* db8, float* db7, void* ws, size_t ws_bytes, int B, int H, int W,
                   void* stream);
+
+/* ---- train-mode BatchNorm2d (+ReLU) on NHWC bf16 ----------------------------------------------
+ * nn.BatchNorm2d in training mode followed by F.relu: rovr/policy_net_1.py:20-49,61-81;
+ * rovr/policy_net_2.py:43-55. x is the convolution output (bias included), y the activation.
+ * Batch statistics over npix = B*H*W pixels; running_mean / running_var (momentum, unbiased
+ * variance) and num_batches_tracked (int64) are updated in place when non-NULL. Channels
+ * >= c_valid are zero padding: y is written as 0 there and they carry no statistics.
+ * mean / rstd (fp32 [C]) are saved for the backward pass. ws >= rovr_bn_workspace(C). */
+size_t rovr_bn_workspace(int C);
+int rovr_bn_train_fwd(const void* x, int x_ld, void* y, int y_ld, long long npix, int C, int c_valid,
+                      const float* gamma, const float* beta, float eps, float momentum,
+                      float* running_mean, float* running_var, long long* num_batches_tracked,
+                      float* mean, float* rstd, int relu, void* ws, size_t ws_bytes, void* stream);
+/* dx = dBN(dy * (y > 0)); dgamma / dbeta fp32 [c_valid]. */
+int rovr_bn_train_bwd(const void* dy, int dy_ld, const void* y, int y_ld, const void* x, int x_ld,
+                      void* dx, int dx_ld, long long npix, int C, int c_valid, const float* gamma,
+                      const float* mean, const float* rstd, float* dgamma, float* dbeta, int relu,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* ---- LayerNorm over the last dim of fp32 rows [rows][E] ---------------------------------------
+ * nn.LayerNorm: rovr/common_layers.py:59,63,71-72,75-76,86,90. y_f32 and / or y_bf16 may be NULL. */
+int rovr_layernorm_fwd(const float* x, long long rows, int E, float eps, const float* gamma,
+                       const float* beta, float* y_f32, void* y_bf16, float* mean, float* rstd,
+                       void* stream);
+size_t rovr_layernorm_workspace(int E);
+int rovr_layernorm_bwd(const float* g, const float* x, long long rows, int E, const float* gamma,
+                       const float* mean, const float* rstd, float* dx, int accumulate, float* dgamma,
+                       float* dbeta, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- fp32 nn.Linear for small batches (weight-read-bound GEMV family) ---------------------------
+ * rovr/policy_net_1.py:54-57,94; rovr/policy_net_2.py:63-69,79; rovr/resnet_extractor.py:9,46;
+ * rovr/action_lstm.py:13-14,33,35. w is the PyTorch [N][K] weight. */
+int rovr_linear_f32_fwd(const float* x, int x_ld, const float* w, const float* bias, float* y, int y_ld,
+                        int M, int N, int K, int accumulate, void* stream);
+size_t rovr_linear_f32_dgrad_workspace(int M, int N, int K);
+/* dx[M][K] (dense) = dy[M][N] . w[N][K] */
+int rovr_linear_f32_dgrad(const float* dy, int dy_ld, const float* w, float* dx, int M, int N, int K,
+                          int accumulate, void* ws, size_t ws_bytes, void* stream);
+/* dw[N][K] = dy^T x, db[N] = column sums of dy (db may be NULL) */
+int rovr_linear_f32_wgrad(const float* dy, int dy_ld, const float* x, int x_ld, float* dw, float* db,
+                          int M, int N, int K, void* stream);
+
+/* ---- standardisation (x - mean) / (std_unbiased + eps_add) along one strided dimension -----------
+ * per-sample over 400 features (eps 0): rovr/policy_net_1.py:91-93; over the batch dim (eps .001):
+ * rovr/policy_net_2.py:104-106. Element (o, i) lives at o*outer_stride + i*inner_stride. */
+int rovr_standardize_fwd(const float* x, float* y, float* sig, int outer, int len, long long outer_stride,
+                         long long inner_stride, float eps_add, void* stream);
+int rovr_standardize_bwd(const float* g, const float* y, const float* sig, float* dx, int outer, int len,
+                         long long outer_stride, long long inner_stride, float eps_add, void* stream);
+
+/* ---- policy heads on logits [b][n], n <= 32, b <= 1024 --------------------------------------------
+ * mask_std: in-place scatter of 0 at target[b][tk] (int64; tk may be 0), then if standardize
+ * out = (l - mean(dim=1)[no keepdim]) / (std(dim=1) + 0.1) exactly as rovr/policy_net_2.py:121-122 /
+ * rovr/policy_net_1.py:100 broadcast it (b == 1 or b == n only). */
+int rovr_head_mask_std_fwd(float* logits, const long long* target, int tk, float* out, float* sig, int b,
+                           int n, int standardize, void* stream);
+int rovr_head_mask_std_bwd(const float* g, const float* logits, const float* out, const float* sig,
+                           const long long* target, int tk, float* dl, int b, int n, int standardize,
+                           void* stream);
+/* probs = softmax((logits - log(expo)) / tau) — F.gumbel_softmax(hard=False) with the Exp(1) draw
+ * `expo` supplied by the caller. mode 0: probs only; 1: idx[b] = argmax, val = log p_max
+ * (rovr/policy_net_1.py:102-103); 2: idx[b][2] = top-2, val = (log p1 + log p2)/2 + 0.69314
+ * (rovr/policy_net_2.py:100-102); 3: val = log p[action[b]] (policy_net_1.py:114);
+ * 4: val = log(p[a0] p[a1])/2 + 0.69314 for action[b][2] (policy_net_2.py:139-141). */
+int rovr_head_gumbel_fwd(const float* logits, const float* expo, float tau, float* probs, int b, int n,
+                         int mode, const long long* action, long long* idx, float* val, void* stream);
+int rovr_head_gumbel_bwd(const float* probs, const float* gval, float tau, int b, int n, int mode,
+                         const long long* action, float* dl, void* stream);
+
+/* ---- nn.LSTMCell pointwise part (rovr/action_lstm.py:33); gates = W_ih x + b_ih + W_hh h + b_hh,
+ * order i, f, g, o; act [B][4*Hd] receives the activated gates for the backward pass. */
+int rovr_lstm_pointwise_fwd(const float* gates, const float* c_prev, float* h, float* c, float* act,
+                            int B, int Hd, void* stream);
+int rovr_lstm_pointwise_bwd(const float* act, const float* c_prev, const float* c, const float* dh,
+                            const float* dc, float* dgates, float* dc_prev, int B, int Hd, void* stream);
+
+/* ---- small data movers ----------------------------------------------------------------------
+ * NHWC bf16 -> rows [B][C*H*W] fp32 in NCHW order (nn.Flatten / rearrange 'b c h w -> b (c h w)':
+ * rovr/policy_net_2.py:59; rovr/policy_net_1.py:90) and back (zero-padding channels to cpad). */
+int rovr_flatten_nhwc(const void* src, int ld, float* dst, int dst_ld, int B, int HW, int C, void* stream);
+int rovr_unflatten_nhwc(const float* src, int src_ld, void* dst, int ld, int B, int HW, int C, int cpad,
+                        void* stream);
+/* dst[r][c] (+)= scale * src[r][c] on fp32 row-strided matrices (torch.cat / slicing of feature rows,
+ * rovr/policy_net_2.py:92; rovr/action_lstm.py:31). */
+int rovr_copy2d_f32(const float* src, int src_ld, float* dst, int dst_ld, int rows, int cols, float scale,
+                    int accumulate, void* stream);
 
 /* ---- bias gradient: out[c] = sum over pixels of g[pixel][c]; C even, C <= 512 ------------------ */
 size_t rovr_colsum_workspace(int C);

@@ -36,6 +36,9 @@ SIGNATURES = {
     "rovr_repack_conv3x3_dgrad": (_i, [_p, _p, _i, _i, _i, _p]),
     "rovr_repack_convT2x2_fprop": (_i, [_p, _p, _i, _i, _p]),
     "rovr_repack_convT2x2_dgrad": (_i, [_p, _p, _i, _i, _p]),
+    "rovr_repack_linear": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "rovr_gemm_wgrad_workspace": (_sz, [_ll, _i, _i]),
+    "rovr_gemm_wgrad": (_i, [_p, _i, _p, _i, _p, _ll, _i, _i, _i, _i, _p, _sz, _p]),
     "rovr_conv3x3_fprop": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "rovr_dgrad_colsum_workspace": (_sz, [_i, _i, _i, _i]),
     "rovr_conv3x3_dgrad": (_i, [_p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _sz, _p]),
@@ -51,6 +54,27 @@ SIGNATURES = {
     "rovr_tail_workspace": (_sz, [_i, _i, _i]),
     "rovr_tail_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _p]),
     "rovr_tail_bwd": (_i, [_p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _p]),
+    "rovr_bn_workspace": (_sz, [_i]),
+    "rovr_bn_train_fwd": (_i, [_p, _i, _p, _i, _ll, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
+    "rovr_bn_train_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _i, _ll, _i, _i, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
+    "rovr_layernorm_fwd": (_i, [_p, _ll, _i, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "rovr_layernorm_workspace": (_sz, [_i]),
+    "rovr_layernorm_bwd": (_i, [_p, _p, _ll, _i, _p, _p, _p, _p, _i, _p, _p, _p, _sz, _p]),
+    "rovr_linear_f32_fwd": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "rovr_linear_f32_dgrad_workspace": (_sz, [_i, _i, _i]),
+    "rovr_linear_f32_dgrad": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _p, _sz, _p]),
+    "rovr_linear_f32_wgrad": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _p]),
+    "rovr_standardize_fwd": (_i, [_p, _p, _p, _i, _i, _ll, _ll, _f, _p]),
+    "rovr_standardize_bwd": (_i, [_p, _p, _p, _p, _i, _i, _ll, _ll, _f, _p]),
+    "rovr_head_mask_std_fwd": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _p]),
+    "rovr_head_mask_std_bwd": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _p]),
+    "rovr_head_gumbel_fwd": (_i, [_p, _p, _f, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "rovr_head_gumbel_bwd": (_i, [_p, _p, _f, _i, _i, _i, _p, _p, _p]),
+    "rovr_lstm_pointwise_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
+    "rovr_lstm_pointwise_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
+    "rovr_flatten_nhwc": (_i, [_p, _i, _p, _i, _i, _i, _i, _p]),
+    "rovr_unflatten_nhwc": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _p]),
+    "rovr_copy2d_f32": (_i, [_p, _i, _p, _i, _i, _i, _f, _i, _p]),
     "rovr_colsum_workspace": (_sz, [_i]),
     "rovr_colsum": (_i, [_p, _i, _ll, _i, _p, _p, _sz, _p]),
 }

@@ -17,6 +17,7 @@
 #include "elementwise.cuh"
 #include "igemm.cuh"
 #include "norm.cuh"
+#include "policy.cuh"
 #include "tail.cuh"
 #include "wgrad.cuh"
 #include "wgrad_halo.cuh"
@@ -279,6 +280,14 @@ extern "C" int rovr_repack_convT2x2_dgrad(const float* w, void* wk, int Cin, int
   return repack(w, wk, Cin, 4, Cout, 1ll * Cout * 4, 1, 4, Cin, Cout, stream);
 }
 
+// nn.Linear / 1x1-conv weight [N][K] fp32 -> bf16 [n_pad][k_pad] (transpose = 0) or its transpose
+// [k_pad][n_pad] (transpose = 1, the operand of the data gradient), zero padded.
+extern "C" int rovr_repack_linear(const float* w, void* wk, int N, int K, int n_pad, int k_pad,
+                                  int transpose, void* stream) {
+  if (transpose) return repack(w, wk, k_pad, 1, n_pad, 1, 0, K, K, N, stream);
+  return repack(w, wk, n_pad, 1, k_pad, K, 0, 1, N, K, stream);
+}
+
 #include "api_igemm.inc"
 #include "api_wgrad.inc"
 
@@ -327,6 +336,11 @@ extern "C" int rovr_maxpool_bwd(const void* x, int x_ld, const void* gp, int gp_
 // ------------------------------------------------------------------------------------------------
 #include "api_tail.inc"
 
+
+// ------------------------------------------------------------------------------------------------
+// normalisation, fp32 linear layers, policy heads, LSTM
+// ------------------------------------------------------------------------------------------------
+#include "api_policy.inc"
 
 // ------------------------------------------------------------------------------------------------
 // bias gradient
