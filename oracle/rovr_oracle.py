@@ -209,13 +209,29 @@ def _bn_train(sd, name, t, eps=1e-5):
     return F.batch_norm(t, None, None, sd[name + ".weight"], sd[name + ".bias"], True, 0.0, eps)
 
 
-def pn1_unet(sd, x):
-    """rovr/policy_net_1.py:60-84: LocalNet-shaped U-Net at half width with BN after every conv."""
+def _storage(bf16):
+    """(activation round-trip, weight round-trip) emulating where the B200 path stores bf16: the packed
+    input, conv / upconv weights, every raw convolution output, every post-ReLU activation and
+    every activation gradient. Identity functions when bf16 is False."""
+    if not bf16:
+        return (lambda t, g=True: t), (lambda p: p)
+    return (lambda t, g=True: _RoundTrip.apply(t, g)), \
+           (lambda p: p + (p.to(torch.bfloat16).to(torch.float32) - p).detach())
+
+
+def pn1_unet(sd, x, bf16=False):
+    """rovr/policy_net_1.py:60-84: LocalNet-shaped U-Net at half width with BN after every conv.
+    bf16=True emulates the bf16 storage points of the B200 path (fp32 arithmetic otherwise)."""
+    rt, wq = _storage(bf16)
+    x = rt(x, False)
+
     def cbr(conv, bn, t, pad=1):
-        return F.relu(_bn_train(sd, bn, F.conv2d(t, sd[conv + ".weight"], sd[conv + ".bias"], padding=pad)))
+        raw = rt(F.conv2d(t, wq(sd[conv + ".weight"]), sd[conv + ".bias"], padding=pad))
+        return rt(F.relu(_bn_train(sd, bn, raw)))
 
     def ubr(up, bn, t):
-        return F.relu(_bn_train(sd, bn, F.conv_transpose2d(t, sd[up + ".weight"], sd[up + ".bias"], stride=2)))
+        raw = rt(F.conv_transpose2d(t, wq(sd[up + ".weight"]), sd[up + ".bias"], stride=2))
+        return rt(F.relu(_bn_train(sd, bn, raw)))
 
     e1 = cbr("conv1", "bn1", x)
     e2 = cbr("conv2", "bn2", F.max_pool2d(e1, 2))
@@ -229,9 +245,9 @@ def pn1_unet(sd, x):
     return F.max_pool2d(d, 2)                                          # :82
 
 
-def pn1_compute_logits(sd, image, context):
+def pn1_compute_logits(sd, image, context, bf16=False):
     """rovr/policy_net_1.py:86-94: flatten 400, per-sample standardise (unbiased std, NO eps), fc."""
-    feat = pn1_unet(sd, torch.cat([image, context], dim=1)).flatten(1)
+    feat = pn1_unet(sd, torch.cat([image, context], dim=1), bf16).flatten(1)
     feat = (feat - feat.mean(dim=1, keepdim=True)) / feat.std(dim=1, keepdim=True)
     return F.linear(feat, sd["fc_final.weight"], sd["fc_final.bias"])
 
@@ -243,9 +259,9 @@ def gumbel_softmax_with_noise(logits, tau, expo):
     return F.softmax((logits - expo.log()) / tau, dim=1)
 
 
-def pn1_forward(sd, image, context, is_critic, expo=None):
+def pn1_forward(sd, image, context, is_critic, expo=None, bf16=False):
     """rovr/policy_net_1.py:96-105. Actor: valid for b == 1 only (mean(dim=1) has no keepdim)."""
-    logits = pn1_compute_logits(sd, image, context)
+    logits = pn1_compute_logits(sd, image, context, bf16)
     if is_critic:
         return logits.squeeze(1)
     logits = (logits - logits.mean(dim=1)) / (logits.std(dim=(1,), keepdim=True) + 0.1)
@@ -254,9 +270,9 @@ def pn1_forward(sd, image, context, is_critic, expo=None):
     return mx.indices, mx.values.log()
 
 
-def pn1_logprob(sd, image, context, action, expo):
+def pn1_logprob(sd, image, context, action, expo, bf16=False):
     """rovr/policy_net_1.py:107-114: gumbel-softmax on the UN-standardised logits, gather, log."""
-    logits = pn1_compute_logits(sd, image, context)
+    logits = pn1_compute_logits(sd, image, context, bf16)
     probs = gumbel_softmax_with_noise(logits, 0.5, expo)
     return probs.gather(1, action[:, None]).log().squeeze(1)
 
@@ -264,11 +280,15 @@ def pn1_logprob(sd, image, context, action, expo):
 # ------------------------------------------------------------------------------------------------
 # Policy network 2
 # ------------------------------------------------------------------------------------------------
-def pn2_video_conv(sd, image):
+def pn2_video_conv(sd, image, bf16=False):
     """rovr/policy_net_2.py:41-60: 4 x [conv3x3 + BN + ReLU + pool] on [b,1,160,160] -> [b,1024]."""
+    rt, wq = _storage(bf16)
+    image = rt(image, False)
+
     def cbr(i, t):
         c, b = f"video_conv.{i}", f"video_conv.{i + 1}"
-        return F.relu(_bn_train(sd, b, F.conv2d(t, sd[c + ".weight"], sd[c + ".bias"], padding=1)))
+        raw = rt(F.conv2d(t, wq(sd[c + ".weight"]), sd[c + ".bias"], padding=1))
+        return rt(F.relu(_bn_train(sd, b, raw)))
 
     t = F.max_pool2d(cbr(0, image), 8, 8)
     t = F.max_pool2d(cbr(4, t), 4, 4)
@@ -296,11 +316,11 @@ def pn2_masked_logits(sd, stacked, target):
     return (logits - logits.mean(dim=1)) / (logits.std(dim=(1,), keepdim=True) + 0.1)
 
 
-def pn2_forward(sd, image, context, target, is_critic, extra=None, expo=None):
+def pn2_forward(sd, image, context, target, is_critic, extra=None, expo=None, bf16=False):
     """rovr/policy_net_2.py:81-108."""
     if is_critic:
         image = image[:, None]
-    stacked = torch.cat([pn2_video_conv(sd, image), context.squeeze(1)], dim=1)
+    stacked = torch.cat([pn2_video_conv(sd, image, bf16), context.squeeze(1)], dim=1)
     if extra is not None:
         return pn2_masked_logits(sd, stacked, target)
     if not is_critic:
@@ -313,9 +333,9 @@ def pn2_forward(sd, image, context, target, is_critic, extra=None, expo=None):
     return pn2_final_fc(sd, (stacked - mean) / (std + 0.001)).squeeze(1)
 
 
-def pn2_logprob(sd, image, context, target, action, expo):
+def pn2_logprob(sd, image, context, target, action, expo, bf16=False):
     """rovr/policy_net_2.py:127-141."""
-    stacked = torch.cat([pn2_video_conv(sd, image[:, None]), context.squeeze(1)], dim=1)
+    stacked = torch.cat([pn2_video_conv(sd, image[:, None], bf16), context.squeeze(1)], dim=1)
     logits = pn2_final_fc(sd, stacked).scatter(1, target.to(torch.int64), 0.0)
     probs = gumbel_softmax_with_noise(logits, 0.7, expo)
     pair = (probs[:, :, None] * probs[:, None, :]).flatten(1)

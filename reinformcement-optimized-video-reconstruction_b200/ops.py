@@ -333,3 +333,267 @@ def colsum(g, out):
     ws = workspace(N.lib.rovr_colsum_workspace(C), g.device)
     _launch("rovr_colsum", _ptr(g), ld, B * H * W, C, _ptr(out), _ptr(ws), ws.numel(), _stream())
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# linear / 1x1-conv operand packing and tensor-core weight gradient
+# ---------------------------------------------------------------------------------------------
+def repack_linear(w, transpose=False):
+    """fp32 [N, K] (or [N, K, 1, 1]) -> bf16 [pad16(N), pad16(K)], or transposed [pad16(K), pad16(N)]."""
+    w = w.reshape(w.shape[0], -1)
+    _f32(w, "linear weight")
+    Nn, K = w.shape
+    n_pad, k_pad = pad16(Nn), pad16(K)
+    shape = (k_pad, n_pad) if transpose else (n_pad, k_pad)
+    wk = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
+    _launch("rovr_repack_linear", _ptr(w), _ptr(wk), Nn, K, n_pad, k_pad, int(transpose), _stream())
+    return wk
+
+
+def gemm_wgrad(dy, x, dw):
+    """dw[n_keep, k_keep] (fp32) = dy[M, N]^T @ x[M, K] on tensor cores; dy, x bf16 row-major."""
+    assert dy.dim() == 2 and x.dim() == 2 and dy.shape[0] == x.shape[0]
+    assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and dy.stride(1) == 1 and x.stride(1) == 1
+    M, Nn = dy.shape
+    K = x.shape[1]
+    dw2 = dw.reshape(dw.shape[0], -1)
+    _f32(dw2, "dw")
+    need = N.lib.rovr_gemm_wgrad_workspace(M, Nn, K)
+    if need == 0:
+        raise N.RovrError("gemm_wgrad_workspace: " + N.last_error())
+    ws = workspace(need, dy.device)
+    _launch("rovr_gemm_wgrad", _ptr(dy), dy.stride(0), _ptr(x), x.stride(0), _ptr(dw2), M, Nn, dw2.shape[0],
+            K, dw2.shape[1], _ptr(ws), ws.numel(), _stream())
+    return dw
+
+
+# ---------------------------------------------------------------------------------------------
+# BatchNorm (train mode) + ReLU, LayerNorm
+# ---------------------------------------------------------------------------------------------
+def bn_train_fwd(x, y, gamma, beta, c_valid, eps, momentum, running_mean, running_var, nbt, relu=True):
+    """Returns (mean, rstd) fp32 [C]; writes y. x / y: NHWC bf16 views with the same shape."""
+    B, H, W, C, x_ld = _act(x, "x")
+    _, _, _, Cy, y_ld = _act(y, "y")
+    assert Cy == C
+    mean = torch.empty(C, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(C, dtype=torch.float32, device=x.device)
+    ws = workspace(N.lib.rovr_bn_workspace(C), x.device)
+    _launch("rovr_bn_train_fwd", _ptr(x), x_ld, _ptr(y), y_ld, B * H * W, C, c_valid, _ptr(gamma), _ptr(beta),
+            ctypes.c_float(eps), ctypes.c_float(momentum), _ptr(running_mean), _ptr(running_var), _ptr(nbt),
+            _ptr(mean), _ptr(rstd), int(relu), _ptr(ws), ws.numel(), _stream())
+    return mean, rstd
+
+
+def bn_train_bwd(dy, y, x, dx, gamma, mean, rstd, c_valid, dgamma, dbeta, relu=True):
+    B, H, W, C, dy_ld = _act(dy, "dy")
+    _, _, _, _, y_ld = _act(y, "y")
+    _, _, _, _, x_ld = _act(x, "x")
+    _, _, _, _, dx_ld = _act(dx, "dx")
+    ws = workspace(N.lib.rovr_bn_workspace(C), x.device)
+    _launch("rovr_bn_train_bwd", _ptr(dy), dy_ld, _ptr(y), y_ld, _ptr(x), x_ld, _ptr(dx), dx_ld, B * H * W, C,
+            c_valid, _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dgamma), _ptr(dbeta), int(relu), _ptr(ws),
+            ws.numel(), _stream())
+    return dx
+
+
+def layernorm_fwd(x, gamma, beta, eps, want_f32=True, want_bf16=True):
+    """x fp32 [..., E] contiguous. Returns (y_f32 | None, y_bf16 | None, mean, rstd)."""
+    _f32(x, "x")
+    E = x.shape[-1]
+    rows = x.numel() // E
+    yf = torch.empty_like(x) if want_f32 else None
+    yb = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    _launch("rovr_layernorm_fwd", _ptr(x), rows, E, ctypes.c_float(eps), _ptr(gamma), _ptr(beta), _ptr(yf),
+            _ptr(yb), _ptr(mean), _ptr(rstd), _stream())
+    return yf, yb, mean, rstd
+
+
+def layernorm_bwd(g, x, gamma, mean, rstd, dx, accumulate=False, dgamma=None, dbeta=None):
+    _f32(g, "g")
+    _f32(x, "x")
+    E = x.shape[-1]
+    rows = x.numel() // E
+    ws = workspace(N.lib.rovr_layernorm_workspace(E), x.device)
+    _launch("rovr_layernorm_bwd", _ptr(g), _ptr(x), rows, E, _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx),
+            int(accumulate), _ptr(dgamma), _ptr(dbeta), _ptr(ws), ws.numel(), _stream())
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------
+# fp32 linear (small batch)
+# ---------------------------------------------------------------------------------------------
+def _rows(t, name):
+    if t.dtype != torch.float32 or not t.is_cuda or t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a 2-D CUDA fp32 tensor with unit column stride")
+    return t.shape[0], t.shape[1], t.stride(0)
+
+
+def linear_f32_fwd(x, w, bias, out=None, accumulate=False):
+    M, K, x_ld = _rows(x, "x")
+    _f32(w, "w")
+    Nn = w.shape[0]
+    assert w.shape == (Nn, K), (w.shape, x.shape)
+    if out is None:
+        out = torch.empty((M, Nn), dtype=torch.float32, device=x.device)
+    _, _, y_ld = _rows(out, "out")
+    _launch("rovr_linear_f32_fwd", _ptr(x), x_ld, _ptr(w), _ptr(bias), _ptr(out), y_ld, M, Nn, K,
+            int(accumulate), _stream())
+    return out
+
+
+def linear_f32_dgrad(dy, w, dx=None, accumulate=False):
+    M, Nn, dy_ld = _rows(dy, "dy")
+    _f32(w, "w")
+    K = w.shape[1]
+    assert w.shape[0] == Nn
+    if dx is None:
+        dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
+    assert dx.is_contiguous() and dx.shape == (M, K)
+    ws = workspace(N.lib.rovr_linear_f32_dgrad_workspace(M, Nn, K), dy.device)
+    _launch("rovr_linear_f32_dgrad", _ptr(dy), dy_ld, _ptr(w), _ptr(dx), M, Nn, K, int(accumulate), _ptr(ws),
+            ws.numel(), _stream())
+    return dx
+
+
+def linear_f32_wgrad(dy, x, dw, db=None):
+    M, Nn, dy_ld = _rows(dy, "dy")
+    _, K, x_ld = _rows(x, "x")
+    _f32(dw, "dw")
+    assert dw.shape == (Nn, K)
+    _launch("rovr_linear_f32_wgrad", _ptr(dy), dy_ld, _ptr(x), x_ld, _ptr(dw), _ptr(db), M, Nn, K, _stream())
+    return dw
+
+
+# ---------------------------------------------------------------------------------------------
+# standardisation and policy heads
+# ---------------------------------------------------------------------------------------------
+def standardize_fwd(x, dim, eps_add):
+    """(x - mean) / (std_unbiased + eps_add) along `dim` of a contiguous 2-D fp32 tensor."""
+    _f32(x, "x")
+    R, C = x.shape
+    outer, length, so, si = (R, C, C, 1) if dim == 1 else (C, R, 1, C)
+    y = torch.empty_like(x)
+    sig = torch.empty(outer, dtype=torch.float32, device=x.device)
+    _launch("rovr_standardize_fwd", _ptr(x), _ptr(y), _ptr(sig), outer, length, so, si,
+            ctypes.c_float(eps_add), _stream())
+    return y, sig
+
+
+def standardize_bwd(g, y, sig, dim, eps_add):
+    _f32(g, "g")
+    R, C = y.shape
+    outer, length, so, si = (R, C, C, 1) if dim == 1 else (C, R, 1, C)
+    dx = torch.empty_like(y)
+    _launch("rovr_standardize_bwd", _ptr(g), _ptr(y), _ptr(sig), _ptr(dx), outer, length, so, si,
+            ctypes.c_float(eps_add), _stream())
+    return dx
+
+
+def _idx(t, name):
+    if t is None:
+        return None
+    if t.dtype != torch.int64 or not t.is_cuda or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous CUDA int64 tensor")
+    return t
+
+
+def head_mask_std_fwd(logits, target, standardize):
+    """In-place scatter of 0 at `target` [b, tk] (or None) on `logits`, then the reference's
+    keepdim-less standardisation. Returns (out | None, sig | None)."""
+    _f32(logits, "logits")
+    b, n = logits.shape
+    target = _idx(target, "target")
+    tk = 0 if target is None else target.shape[1]
+    out = torch.empty_like(logits) if standardize else None
+    sig = torch.empty(b, dtype=torch.float32, device=logits.device) if standardize else None
+    _launch("rovr_head_mask_std_fwd", _ptr(logits), _ptr(target), tk, _ptr(out), _ptr(sig), b, n,
+            int(standardize), _stream())
+    return out, sig
+
+
+def head_mask_std_bwd(g, logits, out, sig, target, standardize):
+    _f32(g, "g")
+    b, n = logits.shape
+    tk = 0 if target is None else target.shape[1]
+    dl = torch.empty_like(logits)
+    _launch("rovr_head_mask_std_bwd", _ptr(g), _ptr(logits), _ptr(out), _ptr(sig), _ptr(target), tk, _ptr(dl),
+            b, n, int(standardize), _stream())
+    return dl
+
+
+def head_gumbel_fwd(logits, expo, tau, mode, action=None):
+    """Returns (probs, idx | None, val | None); see rovr_head_gumbel_fwd for the modes."""
+    _f32(logits, "logits")
+    _f32(expo, "expo")
+    b, n = logits.shape
+    probs = torch.empty_like(logits)
+    idx = val = None
+    if mode in (1, 2):
+        idx = torch.empty((b,) if mode == 1 else (b, 2), dtype=torch.int64, device=logits.device)
+    if mode != 0:
+        val = torch.empty(b, dtype=torch.float32, device=logits.device)
+    action = _idx(action, "action")
+    _launch("rovr_head_gumbel_fwd", _ptr(logits), _ptr(expo), ctypes.c_float(tau), _ptr(probs), b, n, mode,
+            _ptr(action), _ptr(idx), _ptr(val), _stream())
+    return probs, idx, val
+
+
+def head_gumbel_bwd(probs, gval, tau, mode, action):
+    _f32(gval, "gval")
+    b, n = probs.shape
+    dl = torch.empty_like(probs)
+    _launch("rovr_head_gumbel_bwd", _ptr(probs), _ptr(gval), ctypes.c_float(tau), b, n, mode, _ptr(action),
+            _ptr(dl), _stream())
+    return dl
+
+
+# ---------------------------------------------------------------------------------------------
+# LSTM pointwise, data movers
+# ---------------------------------------------------------------------------------------------
+def lstm_pointwise_fwd(gates, c_prev, save_act=True):
+    _f32(gates, "gates")
+    _f32(c_prev, "c_prev")
+    B, Hd = c_prev.shape
+    h = torch.empty_like(c_prev)
+    c = torch.empty_like(c_prev)
+    act = torch.empty_like(gates) if save_act else None
+    _launch("rovr_lstm_pointwise_fwd", _ptr(gates), _ptr(c_prev), _ptr(h), _ptr(c), _ptr(act), B, Hd, _stream())
+    return h, c, act
+
+
+def lstm_pointwise_bwd(act, c_prev, c, dh, dc):
+    B, Hd = c_prev.shape
+    dgates = torch.empty_like(act)
+    dc_prev = torch.empty_like(c_prev)
+    _launch("rovr_lstm_pointwise_bwd", _ptr(act), _ptr(c_prev), _ptr(c), _ptr(dh), _ptr(dc), _ptr(dgates),
+            _ptr(dc_prev), B, Hd, _stream())
+    return dgates, dc_prev
+
+
+def flatten_nhwc(x, C, out, col_off=0):
+    """out[b, col_off + c*H*W + p] = x[b, p, c] for c < C (NCHW flatten order)."""
+    B, H, W, _, ld = _act(x, "x")
+    _, _, out_ld = _rows(out, "out")
+    dst = out[:, col_off:]
+    _launch("rovr_flatten_nhwc", _ptr(x), ld, _ptr(dst), out_ld, B, H * W, C, _stream())
+    return out
+
+
+def unflatten_nhwc(rows, C, out, col_off=0):
+    """out[b, p, c] = rows[b, col_off + c*H*W + p] for c < C, zero for the padding channels."""
+    B, H, W, cpad, ld = _act(out, "out")
+    _, _, src_ld = _rows(rows, "rows")
+    src = rows[:, col_off:]
+    _launch("rovr_unflatten_nhwc", _ptr(src), src_ld, _ptr(out), ld, B, H * W, C, cpad, _stream())
+    return out
+
+
+def copy2d_f32(src, dst, scale=1.0, accumulate=False):
+    r, c, s_ld = _rows(src, "src")
+    r2, c2, d_ld = _rows(dst, "dst")
+    assert (r, c) == (r2, c2)
+    _launch("rovr_copy2d_f32", _ptr(src), s_ld, _ptr(dst), d_ld, r, c, ctypes.c_float(scale), int(accumulate),
+            _stream())
+    return dst
