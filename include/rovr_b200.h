@@ -214,6 +214,35 @@ int rovr_unflatten_nhwc(const float* src, int src_ld, void* dst, int ld, int B, 
 int rovr_copy2d_f32(const float* src, int src_ld, float* dst, int dst_ld, int rows, int cols, float scale,
                     int accumulate, void* stream);
 
+/* ---- ResNet-50 frame-feature extractor helpers ---------------------------------------------------
+ * torchvision resnet50 children[:-1] + Linear(2048, 768) as used by rovr/resnet_extractor.py:5-67.
+ * Convolutions run on rovr_conv3x3_fprop / rovr_gemm_bf16 with eval-mode BatchNorm folded in. */
+/* wf[Cout][K] = w * gamma/sqrt(var+eps), bf[Cout] = beta - mean*gamma/sqrt(var+eps) (frozen + eval
+ * trunk, rovr/resnet_extractor.py:11-14) */
+int rovr_fold_bn(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
+                 float eps, float* wf, float* bf, int Cout, int K, void* stream);
+/* 7x7 stride-2 pad-3 stem: NCHW fp32 [B][3][H][W] -> [B*Ho*Wo][kpad] bf16, k = c*49 + r*7 + s;
+ * quantise != 0 applies the ToPILImage -> ToTensor uint8 round trip of rovr/resnet_extractor.py:18-23 */
+int rovr_stem_im2col(const float* src, void* dst, int B, int H, int W, int kpad, int quantise, void* stream);
+/* nn.MaxPool2d(k, s, pad) with -inf padding (resnet50.maxpool = 3, 2, 1) */
+int rovr_maxpool_pad_fwd(const void* x, int x_ld, void* y, int y_ld, int B, int H, int W, int C, int k, int s,
+                         int pad, void* stream);
+/* y[b][oy][ox] = x[b][oy*s][ox*s]: the sampling pattern of a stride-s convolution */
+int rovr_subsample(const void* x, int x_ld, void* y, int y_ld, int B, int H, int W, int C, int s, void* stream);
+/* out = relu(a + b), dense bf16 (bottleneck residual join) */
+int rovr_add_relu(const void* a, const void* b, void* out, long long n, void* stream);
+/* AdaptiveAvgPool2d(1): NHWC bf16 [B][HW][C] -> fp32 [B][C] */
+int rovr_avgpool(const void* x, int ld, float* out, int B, int HW, int C, void* stream);
+/* feature rows [n][ch*tile*tile] fp32 <-> mosaics [nb][ch][side][side] at (slot/per_row*tile,
+ * slot%per_row*tile) (rovr/resnet_extractor.py:30-40,49-55); batch / slot (int64 [n]) may be NULL
+ * (row r -> mosaic r / slots_per_mosaic, slot r % slots_per_mosaic). gather != 0 reads tiles back. */
+int rovr_mosaic_paste(const float* feat, float* mosaic, const long long* batch, const long long* slot, int n,
+                      int slots_per_mosaic, int ch, int tile, int per_row, int side, int gather, void* stream);
+/* ToPILImage -> transforms.Resize((Ho, Wo)) -> ToTensor of rovr/resnet_extractor.py:18-23: PIL's
+ * two-pass 8-bit bilinear (antialiased) resampler; tmp holds BC*H*Wo floats. */
+int rovr_resize_antialias(const float* src, float* dst, float* tmp, int BC, int H, int W, int Ho, int Wo,
+                          void* stream);
+
 /* ---- bias gradient: out[c] = sum over pixels of g[pixel][c]; C even, C <= 512 ------------------ */
 size_t rovr_colsum_workspace(int C);
 int rovr_colsum(const void* g, int ld, long long npix, int C, float* out, void* ws, size_t ws_bytes,

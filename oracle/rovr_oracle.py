@@ -493,3 +493,40 @@ def localnet_step_bf16_storage(sd, x, context, target):
     loss = F.mse_loss(y, target)
     loss.backward()
     return y.detach(), loss.detach(), {k: leaf[k].grad for k in LOCALNET_LIVE}
+
+
+# ------------------------------------------------------------------------------------------------
+# ResNet-50 frame-feature extractor (third-party arithmetic: torchvision.models.resnet50 and PIL via
+# torchvision.transforms, exactly what rovr/resnet_extractor.py:8,18-23 calls)
+# ------------------------------------------------------------------------------------------------
+def resnet_randomise_bn(module, seed):
+    """Deterministic non-trivial BatchNorm affine + running statistics, so that eval-mode folding is
+    exercised and activations stay O(1) through the 16 residual blocks (default init has mean 0 /
+    var 1 / gamma 1, which lets the residual stream grow by orders of magnitude)."""
+    g = torch.Generator().manual_seed(seed)
+    for m in module.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            c = m.num_features
+            with torch.no_grad():
+                m.weight.copy_(0.5 + 0.5 * torch.rand(c, generator=g))
+                m.bias.copy_(0.2 * (torch.rand(c, generator=g) - 0.5))
+                m.running_mean.copy_(0.2 * (torch.rand(c, generator=g) - 0.5))
+                m.running_var.copy_(2.0 + 4.0 * torch.rand(c, generator=g))
+
+
+def resnet_extractor_forward(resnet_seq, linear_w, linear_b, x):
+    """rovr/resnet_extractor.py:25-47: per frame ToPILImage -> Resize((224,224)) -> ToTensor, the
+    ResNet-50 trunk (children[:-1]) at batch 1, Linear(2048, 768) -> 3x16x16 tile pasted at
+    (s // 5 * 16, s % 5 * 16) of a zero [b,3,80,80] map. resnet_seq must be in eval mode."""
+    import torchvision.transforms as transforms
+    prep = transforms.Compose([transforms.ToPILImage(), transforms.Resize((224, 224)), transforms.ToTensor()])
+    b, s_len = x.shape[0], x.shape[1]
+    fmap = torch.zeros((b, 3, 80, 80))
+    for bi in range(b):
+        for s in range(s_len):
+            f = prep(x[bi, s]).unsqueeze(0)
+            feat = resnet_seq(f)
+            tile = F.linear(feat.view(-1), linear_w, linear_b).view(3, 16, 16)
+            r, c = s // 5 * 16, s % 5 * 16
+            fmap[bi, :, r:r + 16, c:c + 16] = tile
+    return fmap

@@ -75,6 +75,14 @@ SIGNATURES = {
     "rovr_flatten_nhwc": (_i, [_p, _i, _p, _i, _i, _i, _i, _p]),
     "rovr_unflatten_nhwc": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _p]),
     "rovr_copy2d_f32": (_i, [_p, _i, _p, _i, _i, _i, _f, _i, _p]),
+    "rovr_fold_bn": (_i, [_p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _p]),
+    "rovr_stem_im2col": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "rovr_maxpool_pad_fwd": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_subsample": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_add_relu": (_i, [_p, _p, _p, _ll, _p]),
+    "rovr_avgpool": (_i, [_p, _i, _p, _i, _i, _i, _p]),
+    "rovr_mosaic_paste": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_resize_antialias": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "rovr_colsum_workspace": (_sz, [_i]),
     "rovr_colsum": (_i, [_p, _i, _ll, _i, _p, _p, _sz, _p]),
 }

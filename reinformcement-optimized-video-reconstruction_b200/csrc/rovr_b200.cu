@@ -18,6 +18,7 @@
 #include "igemm.cuh"
 #include "norm.cuh"
 #include "policy.cuh"
+#include "resnet.cuh"
 #include "tail.cuh"
 #include "wgrad.cuh"
 #include "wgrad_halo.cuh"
@@ -341,6 +342,7 @@ extern "C" int rovr_maxpool_bwd(const void* x, int x_ld, const void* gp, int gp_
 // normalisation, fp32 linear layers, policy heads, LSTM
 // ------------------------------------------------------------------------------------------------
 #include "api_policy.inc"
+#include "api_resnet.inc"
 
 // ------------------------------------------------------------------------------------------------
 // bias gradient

@@ -597,3 +597,83 @@ def copy2d_f32(src, dst, scale=1.0, accumulate=False):
     _launch("rovr_copy2d_f32", _ptr(src), s_ld, _ptr(dst), d_ld, r, c, ctypes.c_float(scale), int(accumulate),
             _stream())
     return dst
+
+
+# ---------------------------------------------------------------------------------------------
+# ResNet-50 frame-feature extractor helpers
+# ---------------------------------------------------------------------------------------------
+def fold_bn(w, gamma, beta, mean, var, eps):
+    """(w * s, beta - mean * s) with s = gamma / sqrt(var + eps); w fp32 [Cout, ...]."""
+    _f32(w, "w")
+    cout = w.shape[0]
+    K = w.numel() // cout
+    wf = torch.empty_like(w)
+    bf = torch.empty(cout, dtype=torch.float32, device=w.device)
+    _launch("rovr_fold_bn", _ptr(w), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(var), ctypes.c_float(eps),
+            _ptr(wf), _ptr(bf), cout, K, _stream())
+    return wf, bf
+
+
+def stem_im2col(x, kpad=160, quantise=True):
+    """NCHW fp32 [B,3,H,W] -> ([B*Ho*Wo, kpad] bf16, Ho, Wo) for the 7x7 s2 p3 stem."""
+    _f32(x, "x")
+    B, C, H, W = x.shape
+    assert C == 3
+    Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    out = torch.empty((B * Ho * Wo, kpad), dtype=torch.bfloat16, device=x.device)
+    _launch("rovr_stem_im2col", _ptr(x), _ptr(out), B, H, W, kpad, int(quantise), _stream())
+    return out, Ho, Wo
+
+
+def maxpool_pad_fwd(x, k, s, pad):
+    B, H, W, C, ld = _act(x, "x")
+    Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
+    y = torch.empty((B, Ho, Wo, C), dtype=torch.bfloat16, device=x.device)
+    _launch("rovr_maxpool_pad_fwd", _ptr(x), ld, _ptr(y), C, B, H, W, C, k, s, pad, _stream())
+    return y
+
+
+def subsample(x, s):
+    B, H, W, C, ld = _act(x, "x")
+    Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+    y = torch.empty((B, Ho, Wo, C), dtype=torch.bfloat16, device=x.device)
+    _launch("rovr_subsample", _ptr(x), ld, _ptr(y), C, B, H, W, C, s, _stream())
+    return y
+
+
+def add_relu(a, b, out=None):
+    assert a.shape == b.shape and a.is_contiguous() and b.is_contiguous() and a.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty_like(a)
+    _launch("rovr_add_relu", _ptr(a), _ptr(b), _ptr(out), a.numel(), _stream())
+    return out
+
+
+def avgpool(x):
+    B, H, W, C, ld = _act(x, "x")
+    out = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    _launch("rovr_avgpool", _ptr(x), ld, _ptr(out), B, H * W, C, _stream())
+    return out
+
+
+def mosaic_paste(feat, mosaic, batch=None, slot=None, slots_per_mosaic=1, tile=16, per_row=5, gather=False):
+    """feat [n, ch*tile*tile] fp32 <-> mosaic [nb, ch, side, side] fp32 (in place on `mosaic`, or on
+    `feat` when gather=True)."""
+    _f32(feat, "feat")
+    _f32(mosaic, "mosaic")
+    n = feat.shape[0]
+    nb, ch, side, _ = mosaic.shape
+    assert feat.shape[1] == ch * tile * tile
+    _launch("rovr_mosaic_paste", _ptr(feat), _ptr(mosaic), _ptr(_idx(batch, "batch")), _ptr(_idx(slot, "slot")), n,
+            slots_per_mosaic, ch, tile, per_row, side, int(gather), _stream())
+    return feat if gather else mosaic
+
+
+def resize_antialias(x, Ho, Wo):
+    """ToPILImage -> Resize((Ho, Wo)) -> ToTensor on NCHW fp32 [B,C,H,W] (PIL's 8-bit bilinear)."""
+    _f32(x, "x")
+    B, C, H, W = x.shape
+    out = torch.empty((B, C, Ho, Wo), dtype=torch.float32, device=x.device)
+    tmp = torch.empty((B, C, H, Wo), dtype=torch.float32, device=x.device)
+    _launch("rovr_resize_antialias", _ptr(x), _ptr(out), _ptr(tmp), B * C, H, W, Ho, Wo, _stream())
+    return out

@@ -265,7 +265,46 @@ def gen_action_lstm():
     print("action_lstm.npz", len(out), "arrays")
 
 
+def resnet_reference_module(cls):
+    """ResnetFeatureExtractor(pretrained=False) with seeded default init, deterministic BatchNorm
+    statistics, trunk in eval mode and frozen (what pretrained=True sets up, rovr/resnet_extractor.py:11-14;
+    the pretrained weights themselves need a download)."""
+    torch.manual_seed(0)
+    m = quiet(cls, pretrained=False)
+    O.resnet_randomise_bn(m.resnet, 61)
+    m.resnet.eval()
+    for p in m.resnet.parameters():
+        p.requires_grad = False
+    return m
+
+
+def resnet_inputs():
+    g = torch.Generator().manual_seed(62)
+    return {"a": torch.rand((1, 3, 3, 48, 64), generator=g),        # Resize up, non-square
+            "b": torch.rand((1, 2, 3, 224, 224), generator=g),      # Resize is the identity
+            "c": torch.rand((1, 1, 3, 256, 256), generator=g)}      # the dataset's frame size (down-sampling)
+
+
+def gen_resnet():
+    import warnings
+    warnings.filterwarnings("ignore")
+    from resnet_extractor import ResnetFeatureExtractor
+    m = resnet_reference_module(ResnetFeatureExtractor)
+    out = {"keys": np.array(list(m.state_dict().keys()))}
+    for tag, x in resnet_inputs().items():
+        m.zero_grad()
+        y = m(x)
+        (y ** 2).sum().backward()
+        out[f"{tag}/y"] = y.detach().numpy()
+        grad_digest(f"{tag}/linear.weight", m.linear.weight.grad, out)
+        grad_digest(f"{tag}/linear.bias", m.linear.bias.grad, out)
+        # the preprocessing of the first frame (PIL path), to pin the GPU resampler
+        out[f"{tag}/prep0"] = m.preprocessing(x[0, 0]).numpy()[:, ::7, ::5].copy()
+    np.savez_compressed(os.path.join(HERE, "resnet.npz"), **out)
+    print("resnet.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["localnet", "pn1", "pn2", "common", "action_lstm"]
+    which = sys.argv[1:] or ["localnet", "pn1", "pn2", "common", "action_lstm", "resnet"]
     for w in which:
         globals()["gen_" + w]()

@@ -281,3 +281,35 @@ def test_action_lstm_matches_reference(golden_dir):
         y, hx, cx = O.action_lstm_step(sd, action, new_tensor, hx, cx)
         assert np.allclose(y.numpy(), G[f"step{step}/y"], rtol=1e-4, atol=1e-5)
         assert np.allclose(hx.numpy(), G[f"step{step}/hx"], rtol=1e-4, atol=1e-5)
+
+
+def _resnet_oracle_module():
+    """Same recipe as tests/golden/make_golden.py::resnet_reference_module, built from torchvision
+    directly (the reference file only wraps it): seeded init, deterministic BN statistics, eval."""
+    import warnings
+    import torchvision.models as models
+    warnings.filterwarnings("ignore")
+    torch.manual_seed(0)
+    net = models.resnet50(pretrained=False)
+    linear = torch.nn.Linear(2048, 768)
+    seq = torch.nn.Sequential(*(list(net.children())[:-1]))
+    O.resnet_randomise_bn(seq, 61)
+    seq.eval()
+    return seq, linear
+
+
+def _resnet_inputs():
+    g = torch.Generator().manual_seed(62)
+    return {"a": torch.rand((1, 3, 3, 48, 64), generator=g), "b": torch.rand((1, 2, 3, 224, 224), generator=g),
+            "c": torch.rand((1, 1, 3, 256, 256), generator=g)}
+
+
+def test_resnet_extractor_matches_reference(golden_dir):
+    G = _load(golden_dir, "resnet.npz")
+    seq, linear = _resnet_oracle_module()
+    x = _resnet_inputs()["a"]
+    with torch.no_grad():
+        y = O.resnet_extractor_forward(seq, linear.weight, linear.bias, x)
+    assert np.allclose(y.numpy(), G["a/y"], rtol=1e-4, atol=1e-5)
+    keys = ["resnet." + k for k in seq.state_dict().keys()] + ["linear.weight", "linear.bias"]
+    assert keys == list(G["keys"])

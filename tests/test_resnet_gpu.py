@@ -1,0 +1,156 @@
+"""GPU parity of the ResnetFeatureExtractor drop-in against fixtures produced by the unmodified
+reference class (tests/golden/make_golden.py::gen_resnet: seeded weights, eval + frozen trunk as
+with pretrained=True) and of its helper kernels against PyTorch.
+
+Tolerance: bf16 tensor-core trunk (53 convolutions) -> 2e-2 L2-relative on the feature map and on
+the gradients of `linear`; the GPU resampler must reproduce PIL's 8-bit output exactly.
+"""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import rovr_oracle as O
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def _dev():
+    import _native
+    _native.require_device()
+    return torch.device("cuda:0")
+
+
+def _rel(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    return ((got - ref).norm() / (ref.norm() + 1e-20)).item()
+
+
+def _inputs():
+    g = torch.Generator().manual_seed(62)
+    return {"a": torch.rand((1, 3, 3, 48, 64), generator=g), "b": torch.rand((1, 2, 3, 224, 224), generator=g),
+            "c": torch.rand((1, 1, 3, 256, 256), generator=g)}
+
+
+def _module(dev):
+    from resnet_extractor import ResnetFeatureExtractor
+    warnings.filterwarnings("ignore")
+    torch.manual_seed(0)
+    m = ResnetFeatureExtractor(pretrained=False)
+    O.resnet_randomise_bn(m.resnet, 61)
+    m.resnet.eval()
+    for p in m.resnet.parameters():
+        p.requires_grad = False
+    return m.to(dev)
+
+
+def test_resnet_helpers():
+    import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((2, 14, 18, 64), generator=g).to(dev).to(BF)
+    xn = x.float().permute(0, 3, 1, 2)
+    y = ops.maxpool_pad_fwd(x, 3, 2, 1)
+    assert torch.equal(y.float().permute(0, 3, 1, 2), F.max_pool2d(xn, 3, 2, 1))
+    s = ops.subsample(x, 2)
+    assert torch.equal(s, x[:, ::2, ::2].contiguous())
+    b = torch.randn((2, 14, 18, 64), generator=g).to(dev).to(BF)
+    r = ops.add_relu(x, b)
+    assert torch.equal(r, F.relu(x.float() + b.float()).to(BF))
+    a = ops.avgpool(x)
+    assert _rel(a, xn.mean(dim=(2, 3))) < 1e-5
+    # BN folding
+    w = torch.randn((32, 16, 3, 3), generator=g).to(dev)
+    gam, bet = torch.rand(32, generator=g).to(dev) + 0.5, torch.randn(32, generator=g).to(dev)
+    mu, var = torch.randn(32, generator=g).to(dev), torch.rand(32, generator=g).to(dev) + 0.5
+    wf, bf = ops.fold_bn(w, gam, bet, mu, var, 1e-5)
+    sc = gam / torch.sqrt(var + 1e-5)
+    assert _rel(wf, w * sc[:, None, None, None]) < 1e-6 and _rel(bf, bet - mu * sc) < 1e-6
+    # stem im2col + GEMM == 7x7 stride-2 pad-3 convolution
+    img = torch.rand((2, 3, 40, 56), generator=g).to(dev)
+    w7 = (torch.randn((64, 3, 7, 7), generator=g) * 0.1).to(dev)
+    cols, Ho, Wo = ops.stem_im2col(img, 160, quantise=False)
+    wk = ops.repack_linear(w7.reshape(64, -1), False)
+    out = ops.gemm_bf16(cols, wk, None, relu=False).view(2, Ho, Wo, 64)
+    ref = F.conv2d(img.to(BF).float(), w7.to(BF).float(), stride=2, padding=3)
+    assert _rel(out.float().permute(0, 3, 1, 2), ref) < 1e-2
+    # mosaic paste / gather
+    feat = torch.randn((6, 768), generator=g).to(dev)
+    fmap = torch.zeros((2, 3, 80, 80), device=dev)
+    ops.mosaic_paste(feat, fmap, slots_per_mosaic=3)
+    for r_ in range(6):
+        bi, s_ = r_ // 3, r_ % 3
+        assert torch.equal(fmap[bi, :, s_ // 5 * 16:s_ // 5 * 16 + 16, s_ % 5 * 16:s_ % 5 * 16 + 16], feat[r_].view(3, 16, 16))
+    back = torch.empty_like(feat)
+    ops.mosaic_paste(back, fmap, slots_per_mosaic=3, gather=True)
+    assert torch.equal(back, feat)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_resize_matches_pil(golden_dir, tag):
+    """ToPILImage -> Resize((224,224)) -> ToTensor on the GPU == the reference's host PIL path."""
+    import ops
+    dev = _dev()
+    G = np.load(os.path.join(golden_dir, "resnet.npz"), allow_pickle=False)
+    x = _inputs()[tag][0, :1].to(dev)
+    y = ops.resize_antialias(x.contiguous(), 224, 224)[0].cpu().numpy()[:, ::7, ::5]
+    ref = G[f"{tag}/prep0"]
+    diff = np.abs(y - ref) * 255
+    print(f"resize[{tag}]: max diff {diff.max():.3f} levels, mismatching {float((diff > 0.5).mean()):.4%}")
+    assert diff.max() < 0.5, "GPU resampler differs from PIL's 8-bit output"
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_resnet_extractor_vs_reference_golden(golden_dir, tag):
+    dev = _dev()
+    G = np.load(os.path.join(golden_dir, "resnet.npz"), allow_pickle=False)
+    m = _module(dev)
+    assert list(m.state_dict().keys()) == list(G["keys"])
+    x = _inputs()[tag].to(dev)
+    y = m(x)
+    (y ** 2).sum().backward()
+    ref = torch.from_numpy(G[f"{tag}/y"])
+    r = _rel(y, ref)
+    print(f"resnet[{tag}] feature map l2-rel {r:.3e}")
+    assert y.shape == (1, 3, 80, 80) and r < 2e-2
+    S = x.shape[1]
+    used = torch.zeros(80, 80, dtype=torch.bool)
+    for s in range(S):
+        used[s // 5 * 16:s // 5 * 16 + 16, s % 5 * 16:s % 5 * 16 + 16] = True
+    assert float(y[0, :, ~used.to(dev)].abs().sum()) == 0.0, "pixels outside the pasted tiles must stay zero"
+    for name in ("linear.weight", "linear.bias"):
+        g = dict(m.named_parameters())[name].grad.cpu()
+        key = f"{tag}/{name}"
+        gn = float(G[f"gnorm/{key}"])
+        assert abs(float(g.double().norm()) - gn) < 3e-2 * gn, name
+        if f"gfull/{key}" in G:
+            assert _rel(g, torch.from_numpy(G[f"gfull/{key}"])) < 3e-2, name
+        else:
+            idx = torch.from_numpy(G[f"gidx/{key}"])
+            refv = torch.from_numpy(G[f"gval/{key}"])
+            assert _rel(g.reshape(-1)[idx], refv) < 3e-2, name
+    assert all(p.grad is None for p in m.resnet.parameters())
+
+
+def test_resnet_encode_insert_extract(golden_dir):
+    dev = _dev()
+    m = _module(dev)
+    x = _inputs()["b"].to(dev)
+    fmap = m(x).detach()
+    tile = m.encode(x[0, 1])
+    assert tile.shape == (3, 16, 16) and _rel(tile, fmap[0, :, 0:16, 16:32]) < 1e-3
+    enc = torch.zeros((1, 3, 80, 80), device=dev)
+    enc = m.insert_encoded_frame_batch(torch.tensor([[7]]), x[:, 0], enc)
+    assert _rel(enc[0, :, 16:32, 32:48], fmap[0, :, 0:16, 0:16]) < 1e-3
+    patches = m.extract_patch([[0, 1]], fmap)
+    assert patches.shape == (1, 2, 3, 16, 16) and torch.equal(patches[0, 1], fmap[0, :, 0:16, 16:32])
+    with pytest.raises(NotImplementedError):
+        m.resnet.train()
+        m(x)
+    with pytest.raises(RuntimeError):
+        m.resnet.eval()
+        m(x.cpu())
