@@ -243,6 +243,35 @@ int rovr_mosaic_paste(const float* feat, float* mosaic, const long long* batch, 
 int rovr_resize_antialias(const float* src, float* dst, float* tmp, int BC, int H, int W, int Ho, int Wo,
                           void* stream);
 
+/* ---- attention blocks (rovr/common_layers.py:54-118) -----------------------------------------------
+ * batched GEMM on the tcgen05 engine: y[i2][i1][m][n] = sum_k a[i2][i1][m][k] * b[i2][i1][n][k]
+ * (QK^T, PV and their gradients; i1 = head, i2 = batch element). Strides in elements, multiples
+ * of 8; exactly one of y_bf16 / y_f32 is non-NULL. K, N multiples of 16; b holds n_rows_b <= N rows per
+ * matrix (output columns beyond them are zero: key-token padding). */
+int rovr_gemm_batched_bf16(const void* a, long long a_ld, long long a_s1, long long a_s2, const void* b,
+                           long long b_ld, long long b_s1, long long b_s2, void* y_bf16, float* y_f32,
+                           long long y_ld, long long y_s1, long long y_s2, int M, int N, int n_rows_b, int K,
+                           int n1, int n2, void* stream);
+/* out[i2][i1][c][r] = in[i2][i1][r][c], columns r in [R, r_pad) zero-filled (per-head operand transposes) */
+int rovr_transpose_bf16(const void* in, long long in_ld, long long in_s1, long long in_s2, void* out,
+                        long long out_ld, long long out_s1, long long out_s2, int R, int C, int r_pad, int n1,
+                        int n2, void* stream);
+/* P = softmax_t(scale * s) over t < T of fp32 rows [rows][t_pad] -> bf16 (zero in the padding) */
+int rovr_softmax_fwd(const float* s, void* p, long long rows, int T, int t_pad, float scale, void* stream);
+/* dS = scale * P * (dP - sum_t dP P) */
+int rovr_softmax_bwd(const float* dp, const void* p, void* ds, long long rows, int T, int t_pad, float scale,
+                     void* stream);
+/* exact GELU on bf16 (F.gelu, rovr/common_layers.py:91) and its gradient */
+int rovr_gelu_fwd(const void* h, void* a, long long n, void* stream);
+int rovr_gelu_bwd(const void* da, const void* h, void* dh, long long n, void* stream);
+int rovr_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
+/* positional encodings (rovr/common_layers.py:7-52): out[b][p][j] = x + w1[j]*(p % n1) + b1[j]
+ * [+ w2[j]*(p / n1) + b2[j]] with w, b the weight / bias of Linear(1, D); grad: which = 0 -> (w1, b1),
+ * 1 -> (w2, b2) */
+int rovr_posenc_add(const float* x, float* out, const float* w1, const float* b1, const float* w2,
+                    const float* b2, int B, int P, int D, int n1, void* stream);
+int rovr_posenc_grad(const float* g, int B, int P, int D, int n1, int which, float* gw, float* gb, void* stream);
+
 /* ---- bias gradient: out[c] = sum over pixels of g[pixel][c]; C even, C <= 512 ------------------ */
 size_t rovr_colsum_workspace(int C);
 int rovr_colsum(const void* g, int ld, long long npix, int C, float* out, void* ws, size_t ws_bytes,

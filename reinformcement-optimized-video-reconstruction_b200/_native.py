@@ -83,6 +83,15 @@ SIGNATURES = {
     "rovr_avgpool": (_i, [_p, _i, _p, _i, _i, _i, _p]),
     "rovr_mosaic_paste": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "rovr_resize_antialias": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "rovr_gemm_batched_bf16": (_i, [_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _p, _p, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_transpose_bf16": (_i, [_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _i, _i, _i, _i, _i, _p]),
+    "rovr_softmax_fwd": (_i, [_p, _p, _ll, _i, _i, _f, _p]),
+    "rovr_softmax_bwd": (_i, [_p, _p, _p, _ll, _i, _i, _f, _p]),
+    "rovr_gelu_fwd": (_i, [_p, _p, _ll, _p]),
+    "rovr_gelu_bwd": (_i, [_p, _p, _p, _ll, _p]),
+    "rovr_cast_f32_bf16": (_i, [_p, _p, _ll, _p]),
+    "rovr_posenc_add": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "rovr_posenc_grad": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "rovr_colsum_workspace": (_sz, [_i]),
     "rovr_colsum": (_i, [_p, _i, _ll, _i, _p, _p, _sz, _p]),
 }

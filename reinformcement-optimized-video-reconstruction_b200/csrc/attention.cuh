@@ -1,0 +1,132 @@
+// attention.cuh — the memory-bound pieces around the tensor-core GEMMs of the attention blocks
+// (rovr/common_layers.py:54-118): per-head operand transposes, the row softmax over key tokens and
+// its gradient, exact GELU and its gradient, fp32 -> bf16 casts. QK^T, PV, their gradients and all
+// projections run on igemm_kernel (rovr_gemm_bf16 / rovr_gemm_batched_bf16 / rovr_gemm_wgrad).
+#pragma once
+#include "ptx.cuh"
+
+namespace rovr {
+
+// out[i2][i1][c][r] = in[i2][i1][r][c] for r < R, c < C; out columns r in [R, r_pad) are zero.
+// 32x32 tiles through shared memory; grid = (ceil(r_pad/32), ceil(C/32), n1*n2).
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long in_ld, long long in_s1,
+                                      long long in_s2, __nv_bfloat16* __restrict__ out, long long out_ld,
+                                      long long out_s1, long long out_s2, int R, int C, int r_pad, int n1) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int i1 = blockIdx.z % n1, i2 = blockIdx.z / n1;
+  const __nv_bfloat16* src = in + i2 * in_s2 + i1 * in_s1;
+  __nv_bfloat16* dst = out + i2 * out_s2 + i1 * out_s1;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < R && c < C) ? src[r * in_ld + c] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (c < C && r < r_pad) dst[c * out_ld + r] = tile[threadIdx.x][j];
+  }
+}
+
+// P[row][t] = softmax_t(scale * s[row][t]) for t < T, 0 for T <= t < t_pad. One warp per row.
+__global__ void softmax_fwd_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, long long rows,
+                                   int T, int t_pad, float scale) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* sr = s + row * t_pad;
+  float mx = -INFINITY;
+  for (int t = lane; t < T; t += 32) mx = fmaxf(mx, sr[t] * scale);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int t = lane; t < T; t += 32) sum += expf(sr[t] * scale - mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+  for (int t = lane; t < t_pad; t += 32)
+    p[row * t_pad + t] = __float2bfloat16_rn(t < T ? expf(sr[t] * scale - mx) * inv : 0.f);
+}
+// dS = scale * P * (dP - sum_t dP * P)
+__global__ void softmax_bwd_kernel(const float* __restrict__ dp, const __nv_bfloat16* __restrict__ p,
+                                   __nv_bfloat16* __restrict__ ds, long long rows, int T, int t_pad, float scale) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float dot = 0.f;
+  for (int t = lane; t < T; t += 32) dot += dp[row * t_pad + t] * __bfloat162float(p[row * t_pad + t]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  for (int t = lane; t < t_pad; t += 32) {
+    const float v = t < T ? scale * __bfloat162float(p[row * t_pad + t]) * (dp[row * t_pad + t] - dot) : 0.f;
+    ds[row * t_pad + t] = __float2bfloat16_rn(v);
+  }
+}
+
+// exact GELU (F.gelu default, rovr/common_layers.py:91): a = h * Phi(h)
+__global__ void gelu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ a, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = __bfloat162float(h[i]);
+  a[i] = __float2bfloat16_rn(0.5f * x * (1.f + erff(x * 0.70710678118654752f)));
+}
+// dh = da * (Phi(h) + h * phi(h))
+__global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ h,
+                                __nv_bfloat16* __restrict__ dh, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = __bfloat162float(h[i]);
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
+  dh[i] = __float2bfloat16_rn(__bfloat162float(da[i]) * (cdf + x * pdf));
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// out[p][j] = x[b][p][j] + (w1[j] * p1 + b1[j]) + (w2 ? w2[j] * p2 + b2[j] : 0), p1 = p % n1, p2 = p / n1:
+// the learned positional tables of rovr/common_layers.py:7-52 are Linear(1, D) applied to arange(n),
+// i.e. rank-1 in the position index, so they are evaluated on the fly instead of materialised.
+__global__ void posenc_add_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ w1,
+                                  const float* __restrict__ b1, const float* __restrict__ w2,
+                                  const float* __restrict__ b2, long long total, int P, int D, int n1) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int j = static_cast<int>(i % D);
+  const int p = static_cast<int>((i / D) % P);
+  float v = x[i] + w1[j] * static_cast<float>(p % n1) + b1[j];
+  if (w2) v += w2[j] * static_cast<float>(p / n1) + b2[j];
+  out[i] = v;
+}
+// gradients of the two Linear(1, D): gw[j] = sum_{b,p} g * pos(p), gb[j] = sum_{b,p} g. One block per
+// 32 columns, 8 row groups, fixed-order combine.
+__global__ void posenc_grad_kernel(const float* __restrict__ g, long long rows, int P, int D, int n1, int which,
+                                   float* __restrict__ gw, float* __restrict__ gb) {
+  __shared__ float sa[8][33], sb[8][33];
+  const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + cl;
+  float a = 0.f, b = 0.f;
+  if (j < D) {
+    for (long long r = rg; r < rows; r += 8) {
+      const int p = static_cast<int>(r % P);
+      const float pos = static_cast<float>(which == 0 ? p % n1 : p / n1);
+      const float gg = g[r * D + j];
+      a += gg * pos;
+      b += gg;
+    }
+  }
+  sa[rg][cl] = a;
+  sb[rg][cl] = b;
+  __syncthreads();
+  if (rg == 0 && j < D) {
+    float s = 0.f, t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s += sa[k][cl]; t += sb[k][cl]; }
+    gw[j] = s;
+    gb[j] = t;
+  }
+}
+
+}  // namespace rovr

@@ -85,6 +85,8 @@ struct IgemmParams {
   int cw;                 // epilogue column-block width: 16 / 32 / 64 channels
   int relu;
   int has_mask;
+  int b_batched;          // 1: the B operand is a rank-5 map (K, N, d2, d3, d4) whose trailing coordinates are
+                          //    the tile's M-space origin org[1..3] (batched GEMM: one B matrix per head / batch)
   int halo;               // 1: Conv2d 3x3 with the input patch loaded once per k-chunk (see below)
   int a_slots;            // halo mode: depth of the A (halo tile) ring
   int resident_b;         // halo mode: all weight tiles stay in shared memory for the whole kernel
@@ -270,7 +272,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               tma_load_5d(&tmA, &full_bar[s], a_dst, kc * p.bk, org[0] + p.tap_off[t][0],
                           org[1] + p.tap_off[t][1], org[2] + p.tap_off[t][2],
                           org[3] + p.tap_off[t][3]);
-              tma_load_2d(&tmB, &full_bar[s], a_dst + a_bytes, t * p.cin + kc * p.bk, nt * p.n_tile);
+              if (p.b_batched)
+                tma_load_5d(&tmB, &full_bar[s], a_dst + a_bytes, t * p.cin + kc * p.bk, nt * p.n_tile, org[1],
+                            org[2], org[3]);
+              else
+                tma_load_2d(&tmB, &full_bar[s], a_dst + a_bytes, t * p.cin + kc * p.bk, nt * p.n_tile);
             }
           }
           __syncwarp();

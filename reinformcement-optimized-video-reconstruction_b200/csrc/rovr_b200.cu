@@ -19,6 +19,7 @@
 #include "norm.cuh"
 #include "policy.cuh"
 #include "resnet.cuh"
+#include "attention.cuh"
 #include "tail.cuh"
 #include "wgrad.cuh"
 #include "wgrad_halo.cuh"
@@ -343,6 +344,7 @@ extern "C" int rovr_maxpool_bwd(const void* x, int x_ld, const void* gp, int gp_
 // ------------------------------------------------------------------------------------------------
 #include "api_policy.inc"
 #include "api_resnet.inc"
+#include "api_attention.inc"
 
 // ------------------------------------------------------------------------------------------------
 // bias gradient

@@ -677,3 +677,111 @@ def resize_antialias(x, Ho, Wo):
     tmp = torch.empty((B, C, H, Wo), dtype=torch.float32, device=x.device)
     _launch("rovr_resize_antialias", _ptr(x), _ptr(out), _ptr(tmp), B * C, H, W, Ho, Wo, _stream())
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# attention-block helpers
+# ---------------------------------------------------------------------------------------------
+def _bf(t, name):
+    if t.dtype != torch.bfloat16 or not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA bf16 tensor")
+
+
+def gemm_batched(a, b, out):
+    """out[i2, i1, m, n] = sum_k a[i2, i1, m, k] * b[i2, i1, n, k].
+
+    a: bf16 view [n2, n1, M, K], b: bf16 view [n2, n1, Nb, K], out: bf16 or fp32 view [n2, n1, M, N]
+    with Nb <= N (output columns Nb .. N are zero); arbitrary (8-element-aligned) strides on the
+    first three dims, unit stride on the last."""
+    _bf(a, "a")
+    _bf(b, "b")
+    n2, n1, M, K = a.shape
+    Nb, Nn = b.shape[2], out.shape[3]
+    assert b.shape == (n2, n1, Nb, K) and out.shape == (n2, n1, M, Nn) and Nb <= Nn, (a.shape, b.shape, out.shape)
+    assert a.stride(3) == 1 and b.stride(3) == 1 and out.stride(3) == 1
+    yb = _ptr(out) if out.dtype == torch.bfloat16 else _vp(0)
+    yf = _ptr(out) if out.dtype == torch.float32 else _vp(0)
+    _launch("rovr_gemm_batched_bf16", _ptr(a), a.stride(2), a.stride(1), a.stride(0), _ptr(b), b.stride(2),
+            b.stride(1), b.stride(0), yb, yf, out.stride(2), out.stride(1), out.stride(0), M, Nn, Nb, K, n1, n2, _stream())
+    return out
+
+
+def transpose_heads(x, r_pad=None):
+    """x: bf16 view [n2, n1, R, C] (unit stride on C) -> new contiguous [n2, n1, C, r_pad] with
+    out[..., c, r] = x[..., r, c] and zeros for r >= R."""
+    _bf(x, "x")
+    n2, n1, R, C = x.shape
+    r_pad = pad16(R) if r_pad is None else r_pad
+    out = torch.empty((n2, n1, C, r_pad), dtype=torch.bfloat16, device=x.device)
+    assert x.stride(3) == 1
+    _launch("rovr_transpose_bf16", _ptr(x), x.stride(2), x.stride(1), x.stride(0), _ptr(out), out.stride(2),
+            out.stride(1), out.stride(0), R, C, r_pad, n1, n2, _stream())
+    return out
+
+
+def softmax_fwd(s, T, scale):
+    """s: fp32 contiguous [..., t_pad] -> bf16 probabilities, zero for t >= T."""
+    _f32(s, "s")
+    t_pad = s.shape[-1]
+    p = torch.empty(s.shape, dtype=torch.bfloat16, device=s.device)
+    _launch("rovr_softmax_fwd", _ptr(s), _ptr(p), s.numel() // t_pad, T, t_pad, ctypes.c_float(scale), _stream())
+    return p
+
+
+def softmax_bwd(dp, p, T, scale):
+    _f32(dp, "dp")
+    t_pad = p.shape[-1]
+    ds = torch.empty_like(p)
+    _launch("rovr_softmax_bwd", _ptr(dp), _ptr(p), _ptr(ds), p.numel() // t_pad, T, t_pad, ctypes.c_float(scale),
+            _stream())
+    return ds
+
+
+def gelu_fwd(h):
+    _bf(h, "h")
+    assert h.is_contiguous()
+    a = torch.empty_like(h)
+    _launch("rovr_gelu_fwd", _ptr(h), _ptr(a), h.numel(), _stream())
+    return a
+
+
+def gelu_bwd(da, h):
+    assert da.is_contiguous() and h.is_contiguous()
+    dh = torch.empty_like(h)
+    _launch("rovr_gelu_bwd", _ptr(da), _ptr(h), _ptr(dh), h.numel(), _stream())
+    return dh
+
+
+def cast_bf16(x):
+    _f32(x, "x")
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _launch("rovr_cast_f32_bf16", _ptr(x), _ptr(out), x.numel(), _stream())
+    return out
+
+
+def colsum_rows(g, out):
+    """out[c] = sum_m g[m, c] for a bf16 [M, C] matrix of any even width (512-column slabs)."""
+    _bf(g, "g")
+    M, C = g.shape
+    assert out.numel() == C and g.stride(1) == 1
+    for c0 in range(0, C, 512):
+        c1 = min(C, c0 + 512)
+        colsum(g[:, c0:c1].unflatten(0, (1, 1, M)), out[c0:c1])
+    return out
+
+
+def posenc_add(x, w1, b1, n1, w2=None, b2=None):
+    _f32(x, "x")
+    B, P, D = x.shape
+    out = torch.empty_like(x)
+    _launch("rovr_posenc_add", _ptr(x), _ptr(out), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), B, P, D, n1, _stream())
+    return out
+
+
+def posenc_grad(g, n1, which):
+    _f32(g, "g")
+    B, P, D = g.shape
+    gw = torch.empty(D, dtype=torch.float32, device=g.device)
+    gb = torch.empty(D, dtype=torch.float32, device=g.device)
+    _launch("rovr_posenc_grad", _ptr(g), B, P, D, n1, which, _ptr(gw), _ptr(gb), _stream())
+    return gw, gb
