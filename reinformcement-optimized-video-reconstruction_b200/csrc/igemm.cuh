@@ -388,10 +388,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint8_t* stg = stg_base + grp * stg_bytes;
     const int acc = grp;
     uint32_t aph = 0;
-    const int cpr = epi_rowb >> 4;        // 16-byte chunks per staged row: 8 / 4 / 2
-    const int rpi = 32 / cpr;             // rows covered by one warp instruction in pass 2
-    const int my_c = lane % cpr, my_r = lane / cpr;
-    const bool pass2 = (p.mask != nullptr) || (p.colsum_partial != nullptr);
+    const int cpr = epi_rowb >> 4;        // 16-byte chunks per output row of a block: 8 / 4 / 2
 
     if (p.out_f32 != nullptr) {
       // ---- direct fp32 epilogue (small GEMMs whose consumer wants fp32) ----
@@ -441,95 +438,84 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         aph ^= 1u;
       }
     } else {
-      // Per-lane geometry of the pass-2 rows (fixed for the whole kernel): local pixel coordinates
-      // packed 4 x 8 bit, and the mask offset of the row inside a tile in 16-byte units.
-      uint32_t lpack[8], loff16[8], rowok = 0;
+      // ---- bf16 epilogue: TMEM -> registers (thread = output row) -> bias / ReLU -> bf16 ->
+      // [ReLU mask of dgrad] -> swizzled smem -> TMA store, one 64-channel block at a time.
+      // The mask is read straight from global memory by the thread that owns the row (16-byte
+      // loads of its own 128-byte channel segment, issued one block ahead so their latency hides
+      // behind the previous block) and applied on the packed bf16 pairs. The fused bias gradient
+      // (column sums of the stored values) is a reduce-scatter across the 32 rows of the warp done
+      // with shuffles, 16 columns at a time. Nothing is re-read from shared memory.
+      int lrow[4];
+      {
+        int mm = m;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        lpack[i] = 0; loff16[i] = 0;
-        if (pass2 && i < cpr) {
-          int mm = quarter * 32 + i * rpi + my_r;
-          if (mm < rows) rowok |= 1u << i;
-          long long off = 0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int lj = mm % p.boxM[j];
-            mm /= p.boxM[j];
-            lpack[i] |= static_cast<uint32_t>(lj) << (8 * j);
-            off += static_cast<long long>(lj) * p.mstride[j];
-          }
-          loff16[i] = static_cast<uint32_t>(off >> 3);
+        for (int j = 0; j < 4; ++j) {
+          lrow[j] = mm % p.boxM[j];
+          mm /= p.boxM[j];
         }
       }
-      const uint4* mask16 = reinterpret_cast<const uint4*>(p.mask);
-      // tile geometry: origin, validity bits of this lane's pass-2 rows, mask base (16-byte units)
-      auto tile_setup = [&](int tile, int* org, uint32_t& vbits, long long& mbase16) {
+      const bool want_cs = p.colsum_partial != nullptr;
+      const bool want_mask = p.mask != nullptr;
+      const bool has_bias = p.bias != nullptr;
+      // tile geometry: origin, validity of this thread's row, its mask row offset
+      auto tile_setup = [&](int tile, int* org, bool& valid, long long& moff) {
         int mt = tile / p.n_tiles_n;
-        long long base = 0;
+        valid = m < rows;
+        moff = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           org[j] = (mt % p.ntile[j]) * p.boxM[j];
           mt /= p.ntile[j];
-          base += static_cast<long long>(org[j]) * p.mstride[j];
-        }
-        mbase16 = base >> 3;
-        vbits = 0;
-        if (pass2) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            bool v = (rowok >> i) & 1u;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              v = v && (org[j] + static_cast<int>((lpack[i] >> (8 * j)) & 255u) < p.dimM[j]);
-            vbits |= (v ? 1u : 0u) << i;
-          }
+          const int pj = org[j] + lrow[j];
+          valid = valid && (pj < p.dimM[j]);
+          moff += static_cast<long long>(pj) * p.mstride[j];
         }
       };
-      auto mask_fetch = [&](uint4* mreg, uint32_t vbits, long long mbase16, int nglb) {
+      auto mask_fetch = [&](uint4* mreg, bool valid, long long moff, int nglb) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.mask + moff + nglb);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           mreg[i] = make_uint4(0, 0, 0, 0);
-          if (i < cpr && ((vbits >> i) & 1u))
-            mreg[i] = __ldg(mask16 + mbase16 + loff16[i] + (nglb >> 3) + my_c);
+          if (i < cpr && valid) mreg[i] = __ldg(src + i);
         }
       };
       const int tstep = 2 * static_cast<int>(gridDim.x);
       int tile = static_cast<int>(blockIdx.x) + grp * static_cast<int>(gridDim.x);
       int org[4] = {0, 0, 0, 0};
-      uint32_t vbits = 0;
-      long long mbase16 = 0;
+      bool valid = false;
+      long long moff = 0;
       uint4 mreg[8];
       if (tile < total_tiles) {
-        tile_setup(tile, org, vbits, mbase16);
-        if (p.mask != nullptr) mask_fetch(mreg, vbits, mbase16, (tile % p.n_tiles_n) * p.n_tile);
+        tile_setup(tile, org, valid, moff);
+        if (want_mask) mask_fetch(mreg, valid, moff, (tile % p.n_tiles_n) * p.n_tile);
       }
       while (tile < total_tiles) {
         const int nt = tile % p.n_tiles_n;
         const int tile_m = tile / p.n_tiles_n;
         const int ntile_next = tile + tstep;
         int org_n[4] = {0, 0, 0, 0};
-        uint32_t vbits_n = 0;
-        long long mbase16_n = 0;
+        bool valid_n = false;
+        long long moff_n = 0;
         mbar_wait(&tfull_bar[acc], aph, 0x400u + acc);
         tc_fence_after();
         for (int cb = 0; cb < nblk; ++cb) {
           const int nloc = cb * p.cw;
           const int nglb = nt * p.n_tile + nloc;
-          // (b) staging buffer free again? (the previous TMA store of this group has read it)
+          // staging buffer free again? (the previous TMA store of this group has read it)
           if (elected) bulk_wait_read<0>();
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-          // (c) pass 1
-          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                 static_cast<uint32_t>(acc * p.n_tile + nloc);
-          // (a) ReLU-mask values of the NEXT column block (possibly of the next tile) straight into
-          // registers: their DRAM latency hides behind this block's two passes
+          // mask of the NEXT column block (possibly of the next tile)
           uint4 mnext[8];
           if (cb + 1 < nblk) {
-            if (p.mask != nullptr) mask_fetch(mnext, vbits, mbase16, nglb + p.cw);
+            if (want_mask) mask_fetch(mnext, valid, moff, nglb + p.cw);
           } else if (ntile_next < total_tiles) {
-            tile_setup(ntile_next, org_n, vbits_n, mbase16_n);
-            if (p.mask != nullptr) mask_fetch(mnext, vbits_n, mbase16_n, (ntile_next % p.n_tiles_n) * p.n_tile);
+            tile_setup(ntile_next, org_n, valid_n, moff_n);
+            if (want_mask) mask_fetch(mnext, valid_n, moff_n, (ntile_next % p.n_tiles_n) * p.n_tile);
           }
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                 static_cast<uint32_t>(acc * p.n_tile + nloc);
+          float* cs_dst = want_cs ? p.colsum_partial + (static_cast<long long>(tile_m) * 4 + quarter) * p.n_total + nglb
+                                  : nullptr;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {  // two 32-column halves keep the live registers down
             if (2 * h < chunks) {
@@ -542,18 +528,53 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int c2 = 0; c2 < 2; ++c2) {
                 const int ch = 2 * h + c2;
                 if (ch < chunks) {
-                  float f[16];
+                  uint32_t pk[8];
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    f[j] = __uint_as_float(v[c2][j]) + sbias[nglb + ch * 16 + j];
-                    if (p.relu) f[j] = fmaxf(f[j], 0.f);
+                  for (int j = 0; j < 8; ++j) {
+                    float f0 = __uint_as_float(v[c2][2 * j]), f1 = __uint_as_float(v[c2][2 * j + 1]);
+                    if (has_bias) {
+                      f0 += sbias[nglb + ch * 16 + 2 * j];
+                      f1 += sbias[nglb + ch * 16 + 2 * j + 1];
+                    }
+                    if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+                    pk[j] = pack_bf16x2(f0, f1);
                   }
-                  *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2, epi_rowb)) =
-                      make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                                 pack_bf16x2(f[6], f[7]));
-                  *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2 + 1, epi_rowb)) =
-                      make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
-                                 pack_bf16x2(f[14], f[15]));
+                  if (want_mask) {
+                    const uint32_t mw[8] = {mreg[2 * ch].x, mreg[2 * ch].y, mreg[2 * ch].z, mreg[2 * ch].w,
+                                            mreg[2 * ch + 1].x, mreg[2 * ch + 1].y, mreg[2 * ch + 1].z, mreg[2 * ch + 1].w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      __nv_bfloat162 mv;
+                      memcpy(&mv, &mw[j], 4);
+                      pk[j] &= __hgt2_mask(mv, __float2bfloat162_rn(0.f));
+                    }
+                  }
+                  *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2, epi_rowb)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                  *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2 + 1, epi_rowb)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                  if (want_cs) {
+                    // column sums of the STORED values over the warp's 32 rows: reduce-scatter
+                    float w[16];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      w[2 * j] = valid ? bf16_lo(pk[j]) : 0.f;
+                      w[2 * j + 1] = valid ? bf16_hi(pk[j]) : 0.f;
+                    }
+#pragma unroll
+                    for (int st = 0; st < 4; ++st) {
+                      const int off = 16 >> st, n = 8 >> st;
+                      const bool up = (lane & off) != 0;
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) {
+                        if (j < n) {
+                          const float send = up ? w[j] : w[j + n];
+                          const float keep = up ? w[j + n] : w[j];
+                          w[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                      }
+                    }
+                    w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
+                    if ((lane & 1) == 0) cs_dst[ch * 16 + (lane >> 1)] = w[0];
+                  }
                 }
               }
             }
@@ -562,50 +583,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-          }
-          if (pass2) {
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-            // (d) pass 2: mask + column sums on 16-byte chunks
-            float cs[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cs[j] = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (i < cpr) {
-                const int r = quarter * 32 + i * rpi + my_r;
-                uint4* sp = reinterpret_cast<uint4*>(stg + swz_off(r, my_c, epi_rowb));
-                uint4 q = *sp;
-                uint32_t w[4] = {q.x, q.y, q.z, q.w};
-                if (p.mask != nullptr) {
-                  const uint32_t mw[4] = {mreg[i].x, mreg[i].y, mreg[i].z, mreg[i].w};
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    if (!(bf16_lo(mw[j]) > 0.f)) w[j] &= 0xFFFF0000u;
-                    if (!(bf16_hi(mw[j]) > 0.f)) w[j] &= 0x0000FFFFu;
-                  }
-                  *sp = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-                if ((vbits >> i) & 1u) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    cs[2 * j] += bf16_lo(w[j]);
-                    cs[2 * j + 1] += bf16_hi(w[j]);
-                  }
-                }
-              }
-            }
-            if (p.colsum_partial != nullptr) {
-              for (int o = cpr; o < 32; o <<= 1) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], o);
-              }
-              if (lane < cpr) {
-                float4* dst = reinterpret_cast<float4*>(
-                    p.colsum_partial + (static_cast<long long>(tile_m) * 4 + quarter) * p.n_total + nglb + lane * 8);
-                dst[0] = make_float4(cs[0], cs[1], cs[2], cs[3]);
-                dst[1] = make_float4(cs[4], cs[5], cs[6], cs[7]);
-              }
-            }
           }
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
@@ -623,7 +600,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tma_store_5d(&tmOut, stg, c[0], c[1], c[2], c[3], c[4]);
             bulk_commit();
           }
-          if (p.mask != nullptr) {
+          if (want_mask) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) mreg[i] = mnext[i];
           }
@@ -632,8 +609,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tile = ntile_next;
 #pragma unroll
         for (int j = 0; j < 4; ++j) org[j] = org_n[j];
-        vbits = vbits_n;
-        mbase16 = mbase16_n;
+        valid = valid_n;
+        moff = moff_n;
       }
       if (elected) bulk_wait_all<0>();
     }
