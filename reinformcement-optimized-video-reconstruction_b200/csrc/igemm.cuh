@@ -134,6 +134,9 @@ __device__ __forceinline__ uint32_t swz_off(int m, int j, int rowb) {
   return a ^ (((a >> 7) & msk) << 4);
 }
 
+// kPlainEpi: the epilogue has neither a ReLU mask nor fused column sums (every forward launch):
+// their register state disappears and all four 16-column TMEM chunks of a block are fetched at once.
+template <bool kPlainEpi>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmMask,
@@ -454,8 +457,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mm /= p.boxM[j];
         }
       }
-      const bool want_cs = p.colsum_partial != nullptr;
-      const bool want_mask = p.mask != nullptr;
+      const bool want_cs = !kPlainEpi && p.colsum_partial != nullptr;
+      const bool want_mask = !kPlainEpi && p.mask != nullptr;
       const bool has_bias = p.bias != nullptr;
       // tile geometry: origin, validity of this thread's row, its mask row offset
       auto tile_setup = [&](int tile, int* org, bool& valid, long long& moff) {
@@ -516,69 +519,75 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                  static_cast<uint32_t>(acc * p.n_tile + nloc);
           float* cs_dst = want_cs ? p.colsum_partial + (static_cast<long long>(tile_m) * 4 + quarter) * p.n_total + nglb
                                   : nullptr;
+          // G = 16-column chunks fetched from TMEM per wait: all four when registers allow (plain
+          // forward epilogue), two when the ReLU mask / column sums keep more state live
+          auto convert = [&](auto g_tag) {
+            constexpr int G = decltype(g_tag)::value;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {  // two 32-column halves keep the live registers down
-            if (2 * h < chunks) {
-              uint32_t v[2][16];
+            for (int h = 0; h < 4 / G; ++h) {
+              if (G * h < chunks) {
+                uint32_t v[G][16];
 #pragma unroll
-              for (int c2 = 0; c2 < 2; ++c2)
-                if (2 * h + c2 < chunks) tmem_ld16(t_row + static_cast<uint32_t>((2 * h + c2) * 16), v[c2]);
-              tmem_ld_wait();
+                for (int c2 = 0; c2 < G; ++c2)
+                  if (G * h + c2 < chunks) tmem_ld16(t_row + static_cast<uint32_t>((G * h + c2) * 16), v[c2]);
+                tmem_ld_wait();
 #pragma unroll
-              for (int c2 = 0; c2 < 2; ++c2) {
-                const int ch = 2 * h + c2;
-                if (ch < chunks) {
-                  uint32_t pk[8];
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    float f0 = __uint_as_float(v[c2][2 * j]), f1 = __uint_as_float(v[c2][2 * j + 1]);
-                    if (has_bias) {
-                      f0 += sbias[nglb + ch * 16 + 2 * j];
-                      f1 += sbias[nglb + ch * 16 + 2 * j + 1];
-                    }
-                    if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
-                    pk[j] = pack_bf16x2(f0, f1);
-                  }
-                  if (want_mask) {
-                    const uint32_t mw[8] = {mreg[2 * ch].x, mreg[2 * ch].y, mreg[2 * ch].z, mreg[2 * ch].w,
-                                            mreg[2 * ch + 1].x, mreg[2 * ch + 1].y, mreg[2 * ch + 1].z, mreg[2 * ch + 1].w};
+                for (int c2 = 0; c2 < G; ++c2) {
+                  const int ch = G * h + c2;
+                  if (ch < chunks) {
+                    uint32_t pk[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                      __nv_bfloat162 mv;
-                      memcpy(&mv, &mw[j], 4);
-                      pk[j] &= __hgt2_mask(mv, __float2bfloat162_rn(0.f));
+                      float f0 = __uint_as_float(v[c2][2 * j]), f1 = __uint_as_float(v[c2][2 * j + 1]);
+                      if (has_bias) {
+                        f0 += sbias[nglb + ch * 16 + 2 * j];
+                        f1 += sbias[nglb + ch * 16 + 2 * j + 1];
+                      }
+                      if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+                      pk[j] = pack_bf16x2(f0, f1);
                     }
-                  }
-                  *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2, epi_rowb)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                  *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2 + 1, epi_rowb)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                  if (want_cs) {
-                    // column sums of the STORED values over the warp's 32 rows: reduce-scatter
-                    float w[16];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                      w[2 * j] = valid ? bf16_lo(pk[j]) : 0.f;
-                      w[2 * j + 1] = valid ? bf16_hi(pk[j]) : 0.f;
-                    }
-#pragma unroll
-                    for (int st = 0; st < 4; ++st) {
-                      const int off = 16 >> st, n = 8 >> st;
-                      const bool up = (lane & off) != 0;
+                    if (want_mask) {
+                      const uint32_t mw[8] = {mreg[2 * ch].x, mreg[2 * ch].y, mreg[2 * ch].z, mreg[2 * ch].w,
+                                              mreg[2 * ch + 1].x, mreg[2 * ch + 1].y, mreg[2 * ch + 1].z, mreg[2 * ch + 1].w};
 #pragma unroll
                       for (int j = 0; j < 8; ++j) {
-                        if (j < n) {
-                          const float send = up ? w[j] : w[j + n];
-                          const float keep = up ? w[j + n] : w[j];
-                          w[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                        }
+                        __nv_bfloat162 mv;
+                        memcpy(&mv, &mw[j], 4);
+                        pk[j] &= __hgt2_mask(mv, __float2bfloat162_rn(0.f));
                       }
                     }
-                    w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
-                    if ((lane & 1) == 0) cs_dst[ch * 16 + (lane >> 1)] = w[0];
+                    *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2, epi_rowb)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2 + 1, epi_rowb)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    if (want_cs) {
+                      // column sums of the STORED values over the warp's 32 rows: reduce-scatter
+                      float w[16];
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) {
+                        w[2 * j] = valid ? bf16_lo(pk[j]) : 0.f;
+                        w[2 * j + 1] = valid ? bf16_hi(pk[j]) : 0.f;
+                      }
+#pragma unroll
+                      for (int st = 0; st < 4; ++st) {
+                        const int off = 16 >> st, n = 8 >> st;
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                          if (j < n) {
+                            const float send = up ? w[j] : w[j + n];
+                            const float keep = up ? w[j + n] : w[j];
+                            w[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                          }
+                        }
+                      }
+                      w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
+                      if ((lane & 1) == 0) cs_dst[ch * 16 + (lane >> 1)] = w[0];
+                    }
                   }
                 }
               }
             }
-          }
+          };
+          convert(std::integral_constant<int, kPlainEpi ? 4 : 2>{});
           if (cb == nblk - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
