@@ -507,14 +507,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           // staging buffer free again? (the previous TMA store of this group has read it)
           if (elected) bulk_wait_read<0>();
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-          // mask of the NEXT column block (possibly of the next tile)
-          uint4 mnext[8];
-          if (cb + 1 < nblk) {
-            if (want_mask) mask_fetch(mnext, valid, moff, nglb + p.cw);
-          } else if (ntile_next < total_tiles) {
-            tile_setup(ntile_next, org_n, valid_n, moff_n);
-            if (want_mask) mask_fetch(mnext, valid_n, moff_n, (ntile_next % p.n_tiles_n) * p.n_tile);
-          }
+          if (cb + 1 == nblk && ntile_next < total_tiles) tile_setup(ntile_next, org_n, valid_n, moff_n);
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                  static_cast<uint32_t>(acc * p.n_tile + nloc);
           float* cs_dst = want_cs ? p.colsum_partial + (static_cast<long long>(tile_m) * 4 + quarter) * p.n_total + nglb
@@ -587,7 +580,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
             }
           };
-          convert(std::integral_constant<int, kPlainEpi ? 4 : 2>{});
+          convert(std::integral_constant<int, 4>{});
+          // mask of the NEXT column block (possibly of the next tile), straight into the registers
+          // this block has just finished with: the loads fly during the store hand-off below and the
+          // next block's TMEM fetch
+          if (want_mask) {
+            if (cb + 1 < nblk) mask_fetch(mreg, valid, moff, nglb + p.cw);
+            else if (ntile_next < total_tiles) mask_fetch(mreg, valid_n, moff_n, (ntile_next % p.n_tiles_n) * p.n_tile);
+          }
           if (cb == nblk - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -608,10 +608,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             tma_store_5d(&tmOut, stg, c[0], c[1], c[2], c[3], c[4]);
             bulk_commit();
-          }
-          if (want_mask) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) mreg[i] = mnext[i];
           }
         }
         aph ^= 1u;
