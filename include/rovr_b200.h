@@ -108,10 +108,14 @@ int rovr_gemm_wgrad(const void* dy, int dy_ld, const void* x, int x_ld, float* d
  * nn.MaxPool2d: rovr/local_net.py:21,53-55; rovr/policy_net_1.py:29; rovr/policy_net_2.py:45-58. */
 int rovr_maxpool_fwd(const void* x, int x_ld, void* y, int y_ld, int B, int H, int W, int C, int kh,
                      int kw, int sh, int sw, void* stream);
-/* gx = [relu_mask: (x > 0) *] (gskip + maxpool_backward(gp)); gskip may be NULL. */
+/* gx = [relu_mask: (x > 0) *] (gskip + maxpool_backward(gp)); gskip may be NULL. If colsum != NULL
+ * (non-overlapping windows, C <= 256) it receives sum over pixels of gx[pixel][c] (fp32 [C]) — the bias
+ * gradient of the convolution that produced x — from the same pass;
+ * ws >= rovr_maxpool_bwd_colsum_workspace(...). */
+size_t rovr_maxpool_bwd_colsum_workspace(int B, int H, int W, int C, int kh, int kw);
 int rovr_maxpool_bwd(const void* x, int x_ld, const void* gp, int gp_ld, const void* gskip, int gs_ld,
                      void* gx, int gx_ld, int B, int H, int W, int C, int kh, int kw, int sh, int sw,
-                     int relu_mask, void* stream);
+                     int relu_mask, float* colsum, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- LocalNet tail: conv8 1x1 (64->3) + sigmoid (+ fused L2 loss) ------------------------------
  * rovr/local_net.py:39,71; nn.MSELoss of rovr/train_local_net_unet.py:90,107.

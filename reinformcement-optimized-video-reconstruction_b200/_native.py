@@ -50,7 +50,8 @@ SIGNATURES = {
     "rovr_convT2x2_wgrad": (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
     "rovr_gemm_bf16": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "rovr_maxpool_fwd": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
-    "rovr_maxpool_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_maxpool_bwd_colsum_workspace": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "rovr_maxpool_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "rovr_tail_workspace": (_sz, [_i, _i, _i]),
     "rovr_tail_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _p]),
     "rovr_tail_bwd": (_i, [_p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _p]),

@@ -100,12 +100,21 @@ __global__ void maxpool_bwd_tiled_kernel(const __nv_bfloat16* __restrict__ x, in
                                          const __nv_bfloat16* __restrict__ gp, int gp_ld,
                                          const __nv_bfloat16* __restrict__ gskip, int gs_ld,
                                          __nv_bfloat16* __restrict__ gx, int gx_ld, int B, int H,
-                                         int W, int C, int kh, int kw, int relu_mask) {
+                                         int W, int C, int kh, int kw, int relu_mask,
+                                         float* __restrict__ colsum_partial) {
+  // colsum_partial (optional, [gridDim.x][C]): per-block column sums of gx — the bias gradient of
+  // the convolution that produced x — so that no separate pass over gx is needed. Requires
+  // blockDim.x % (C/8) == 0 (every thread of a block keeps the same channel group).
+  __shared__ float scs[8][32][9];
   const int c8 = C >> 3;
   const int Ho = H / kh, Wo = W / kw;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long n = static_cast<long long>(B) * Ho * Wo * c8;
-  if (i >= n) return;
+  float csum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) csum[j] = 0.f;
+  // grid-stride: the stride is a multiple of blockDim.x, hence of C/8, so a thread keeps its channel group
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
   const int cv = static_cast<int>(i % c8);
   long long r = i / c8;
   const int ox = static_cast<int>(r % Wo);
@@ -147,9 +156,118 @@ __global__ void maxpool_bwd_tiled_kernel(const __nv_bfloat16* __restrict__ x, in
         if (arg[j] == dy * kw + dx) g += __bfloat162float(g8[j]);
         if (relu_mask && !(__bfloat162float(x8[j]) > 0.f)) g = 0.f;
         o8[j] = __float2bfloat16_rn(g);
+        csum[j] += g;
       }
       *reinterpret_cast<uint4*>(gx + pix * gx_ld + cv * 8) = o;
     }
+  }
+  if (colsum_partial == nullptr) return;
+  // lanes l, l + c8, l + 2*c8, ... of a warp hold the same channel group: fold them with shuffles,
+  // then the eight warps through shared memory
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 16; o >= c8; o >>= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) csum[j] += __shfl_xor_sync(0xffffffffu, csum[j], o);
+  }
+  if (lane < c8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) scs[warp][lane][j] = csum[j];
+  }
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < C) {
+    const int g8 = threadIdx.x >> 3, e = threadIdx.x & 7;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += scs[w][g8][e];
+    colsum_partial[static_cast<long long>(blockIdx.x) * C + threadIdx.x] = s;
+  }
+}
+
+// 2x2 / stride 2 specialisation of the kernel above (every LocalNet / PolicyNetwork1 pool): all nine
+// 16-byte loads of a window (gp, 4 x, 4 gskip) are issued before anything is consumed, so each
+// thread keeps nine requests in flight instead of one or two.
+__global__ void __launch_bounds__(256)
+maxpool_bwd_2x2_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const __nv_bfloat16* __restrict__ gp,
+                       int gp_ld, const __nv_bfloat16* __restrict__ gskip, int gs_ld,
+                       __nv_bfloat16* __restrict__ gx, int gx_ld, int B, int H, int W, int C, int relu_mask,
+                       float* __restrict__ colsum_partial) {
+  __shared__ float scs[8][32][9];
+  const int c8 = C >> 3;
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long n = static_cast<long long>(B) * Ho * Wo * c8;
+  float csum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) csum[j] = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % c8);
+    long long r = i / c8;
+    const int ox = static_cast<int>(r % Wo);
+    r /= Wo;
+    const int oy = static_cast<int>(r % Ho);
+    const int b = static_cast<int>(r / Ho);
+    const long long pix0 = (static_cast<long long>(b) * H + oy * 2) * W + ox * 2;
+    const long long pix[4] = {pix0, pix0 + 1, pix0 + W, pix0 + W + 1};
+    uint4 xv[4], sk[4];
+    const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gp + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * gp_ld + cv * 8));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) xv[q] = __ldg(reinterpret_cast<const uint4*>(x + pix[q] * x_ld + cv * 8));
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      sk[q] = gskip ? __ldg(reinterpret_cast<const uint4*>(gskip + pix[q] * gs_ld + cv * 8)) : make_uint4(0, 0, 0, 0);
+    const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+    uint32_t o[4][4];
+#pragma unroll
+    for (int wq = 0; wq < 4; ++wq) {            // one bf16 pair at a time
+      float xs[4][2], ss[4][2];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t xw = (&xv[q].x)[wq], sw_ = (&sk[q].x)[wq];
+        xs[q][0] = bf16_lo(xw); xs[q][1] = bf16_hi(xw);
+        ss[q][0] = bf16_lo(sw_); ss[q][1] = bf16_hi(sw_);
+      }
+      const float gg[2] = {bf16_lo(gw[wq]), bf16_hi(gw[wq])};
+      float res[4][2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        int arg = 0;                              // first maximum in window scan order (ATen's rule)
+        float best = xs[0][e];
+#pragma unroll
+        for (int q = 1; q < 4; ++q)
+          if (xs[q][e] > best) { best = xs[q][e]; arg = q; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float g = ss[q][e] + (arg == q ? gg[e] : 0.f);
+          if (relu_mask && !(xs[q][e] > 0.f)) g = 0.f;
+          res[q][e] = g;
+          csum[2 * wq + e] += g;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q][wq] = pack_bf16x2(res[q][0], res[q][1]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<uint4*>(gx + pix[q] * gx_ld + cv * 8) = make_uint4(o[q][0], o[q][1], o[q][2], o[q][3]);
+  }
+  if (colsum_partial == nullptr) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o2 = 16; o2 >= c8; o2 >>= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) csum[j] += __shfl_xor_sync(0xffffffffu, csum[j], o2);
+  }
+  if (lane < c8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) scs[warp][lane][j] = csum[j];
+  }
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < C) {
+    const int g8 = threadIdx.x >> 3, e = threadIdx.x & 7;
+    float s2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s2 += scs[w][g8][e];
+    colsum_partial[static_cast<long long>(blockIdx.x) * C + threadIdx.x] = s2;
+  }
 }
 
 // Generic (possibly overlapping / ragged) backward: one thread per input element vector, gathers

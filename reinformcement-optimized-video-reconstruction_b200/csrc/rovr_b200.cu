@@ -309,23 +309,59 @@ extern "C" int rovr_maxpool_fwd(const void* x, int x_ld, void* y, int y_ld, int 
       kh, kw, sh, sw, Ho, Wo);
   return launch_check("maxpool_fwd");
 }
+extern "C" size_t rovr_maxpool_bwd_colsum_workspace(int B, int H, int W, int C, int kh, int kw) {
+  const long long n = 1ll * B * (H / kh) * (W / kw) * (C / 8);
+  const long long blocks = (n + 255) / 256;
+  return static_cast<size_t>(blocks + 256) * C * sizeof(float);
+}
 extern "C" int rovr_maxpool_bwd(const void* x, int x_ld, const void* gp, int gp_ld,
                                 const void* gskip, int gs_ld, void* gx, int gx_ld, int B, int H,
                                 int W, int C, int kh, int kw, int sh, int sw, int relu_mask,
-                                void* stream) {
+                                float* colsum, void* ws, size_t ws_bytes, void* stream) {
   if (int rc = ensure_device()) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool tiled = (kh == sh && kw == sw && H % kh == 0 && W % kw == 0 && C % 8 == 0 &&
                       x_ld % 8 == 0 && gp_ld % 8 == 0 && gx_ld % 8 == 0 && (gskip == nullptr || gs_ld % 8 == 0));
   if (tiled) {
     const long long n = 1ll * B * (H / kh) * (W / kw) * (C / 8);
-    maxpool_bwd_tiled_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+    int blocks = static_cast<int>((n + 255) / 256);
+    if (colsum != nullptr) blocks = std::min(blocks, 8 * g_dev.sms);   // grid-stride: few, fat partial rows
+    float* partial = nullptr;
+    if (colsum != nullptr) {
+      ROVR_REQUIRE(C <= 256 && 256 % (C / 8) == 0, "maxpool_bwd: fused column sums need C <= 256 and C/8 a power of two");
+      ROVR_REQUIRE(ws != nullptr && ws_bytes >= rovr_maxpool_bwd_colsum_workspace(B, H, W, C, kh, kw),
+                   "maxpool_bwd: column-sum workspace too small");
+      partial = static_cast<float*>(ws);
+    }
+    if (kh == 2 && kw == 2 && (C / 8 <= 32) && 256 % (C / 8) == 0) {
+      blocks = std::min(blocks, 8 * g_dev.sms);
+      maxpool_bwd_2x2_kernel<<<blocks, 256, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(x), x_ld, static_cast<const __nv_bfloat16*>(gp), gp_ld,
+          static_cast<const __nv_bfloat16*>(gskip), gs_ld, static_cast<__nv_bfloat16*>(gx), gx_ld, B, H, W, C,
+          relu_mask, partial);
+    } else
+    maxpool_bwd_tiled_kernel<<<blocks, 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(x), x_ld, static_cast<const __nv_bfloat16*>(gp), gp_ld,
         static_cast<const __nv_bfloat16*>(gskip), gs_ld, static_cast<__nv_bfloat16*>(gx), gx_ld, B,
-        H, W, C, kh, kw, relu_mask);
-    return launch_check("maxpool_bwd_tiled");
+        H, W, C, kh, kw, relu_mask, partial);
+    if (int rc = launch_check("maxpool_bwd_tiled")) return rc;
+    if (colsum == nullptr) return 0;
+    // [blocks][C] -> [chunks][C] -> [C], both stages in a fixed order
+    const int kChunks = 256;
+    if (blocks <= 4 * kChunks) {
+      reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(partial, blocks, C, C, colsum, 0);
+      return launch_check("reduce_rows(pool colsum)");
+    }
+    float* tmp = partial + static_cast<size_t>(blocks) * C;
+    const int rpc = (blocks + kChunks - 1) / kChunks;
+    const int chunks = (blocks + rpc - 1) / rpc;
+    reduce_rows_kernel<<<dim3((C + 31) / 32, chunks), 256, 0, st>>>(partial, blocks, C, C, tmp, 0, rpc, C);
+    if (int rc = launch_check("reduce_rows(pool colsum, stage 1)")) return rc;
+    reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(tmp, chunks, C, C, colsum, 0);
+    return launch_check("reduce_rows(pool colsum, stage 2)");
   }
   ROVR_REQUIRE(gskip == nullptr, "maxpool_bwd: skip gradient only supported for non-overlapping windows");
+  ROVR_REQUIRE(colsum == nullptr, "maxpool_bwd: fused column sums only supported for non-overlapping windows");
   const int Ho = (H - kh) / sh + 1, Wo = (W - kw) / sw + 1;
   const long long n = 1ll * B * H * W * C;
   maxpool_bwd_generic_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(

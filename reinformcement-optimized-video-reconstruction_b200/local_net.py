@@ -190,24 +190,24 @@ class _LocalNetFunction(torch.autograd.Function):
         gp3 = el(a["p3"])
         ops.conv3x3_dgrad(g4, wd("conv4"), gp3)
         g3 = torch.empty((B, H // 4, W // 4, 256), dtype=bf, device=dev)
-        ops.maxpool_bwd(a["cat5"][..., 256:], gp3, g3, 2, gskip=gcat5[..., 256:], relu_mask=True)
+        ops.maxpool_bwd(a["cat5"][..., 256:], gp3, g3, 2, gskip=gcat5[..., 256:], relu_mask=True,
+                        colsum=G["conv3.bias"])             # bias gradient from the same pass over g3
         # ---- conv3 ----
         ops.conv3x3_wgrad(g3, a["p2"], G["conv3.weight"])
-        ops.colsum(g3, G["conv3.bias"])
         gp2 = el(a["p2"])
         ops.conv3x3_dgrad(g3, wd("conv3"), gp2)
         g2 = torch.empty((B, H // 2, W // 2, 128), dtype=bf, device=dev)
-        ops.maxpool_bwd(a["cat6"][..., 128:], gp2, g2, 2, gskip=gcat6[..., 128:], relu_mask=True)
+        ops.maxpool_bwd(a["cat6"][..., 128:], gp2, g2, 2, gskip=gcat6[..., 128:], relu_mask=True,
+                        colsum=G["conv2.bias"])
         # ---- conv2 ----
         ops.conv3x3_wgrad(g2, a["p1"], G["conv2.weight"])
-        ops.colsum(g2, G["conv2.bias"])
         gp1 = el(a["p1"])
         ops.conv3x3_dgrad(g2, wd("conv2"), gp1)
         g1 = torch.empty((B, H, W, 64), dtype=bf, device=dev)
-        ops.maxpool_bwd(a["cat7"][..., 64:], gp1, g1, 2, gskip=gcat7[..., 64:], relu_mask=True)
+        ops.maxpool_bwd(a["cat7"][..., 64:], gp1, g1, 2, gskip=gcat7[..., 64:], relu_mask=True,
+                        colsum=G["conv1.bias"])
         # ---- conv1 (input needs no gradient: no dgrad, as in the reference's autograd graph) ----
         ops.conv3x3_wgrad(g1, a["in16"], G["conv1.weight"])
-        ops.colsum(g1, G["conv1.bias"])
         net._bucket_ready(1, enc_flat)
         net._buckets_wait()
 

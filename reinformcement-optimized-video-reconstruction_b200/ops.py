@@ -270,7 +270,9 @@ def maxpool_fwd(x, y, kernel, stride=None):
     return y
 
 
-def maxpool_bwd(x, gp, gx, kernel, stride=None, gskip=None, relu_mask=True):
+def maxpool_bwd(x, gp, gx, kernel, stride=None, gskip=None, relu_mask=True, colsum=None):
+    """gx = [(x > 0) *] (gskip + maxpool_backward(gp)); colsum (fp32 [C]) optionally receives the
+    per-channel sums of gx (the bias gradient of the layer that produced x) from the same pass."""
     kh, kw = _pair(kernel)
     sh, sw = _pair(stride if stride is not None else kernel)
     B, H, W, C, x_ld = _act(x, "x")
@@ -279,8 +281,14 @@ def maxpool_bwd(x, gp, gx, kernel, stride=None, gskip=None, relu_mask=True):
     gs_ld = 0
     if gskip is not None:
         _, _, _, _, gs_ld = _act(gskip, "gskip")
+    ws, wsn = _vp(0), 0
+    if colsum is not None:
+        _f32(colsum, "colsum")
+        assert colsum.numel() == C
+        wbuf = workspace(N.lib.rovr_maxpool_bwd_colsum_workspace(B, H, W, C, kh, kw), x.device)
+        ws, wsn = _ptr(wbuf), wbuf.numel()
     _launch("rovr_maxpool_bwd", _ptr(x), x_ld, _ptr(gp), gp_ld, _ptr(gskip), gs_ld, _ptr(gx), gx_ld,
-           B, H, W, C, kh, kw, sh, sw, int(relu_mask), _stream())
+           B, H, W, C, kh, kw, sh, sw, int(relu_mask), _ptr(colsum), ws, wsn, _stream())
     return gx
 
 

@@ -240,6 +240,14 @@ def test_maxpool(B, H, W, C, k, s):
     # bf16 ties inside a window can route the gradient to a different (equal-valued) element
     # than ATen only if two equal maxima exist; the inputs are random normals so ties are only at 0
     _report(f"maxpool_bwd{(B, H, W, C, k, s)}", _nchw(gx), ref, 1e-2)
+    if tiled and C <= 256 and 256 % (C // 8) == 0:
+        # fused bias gradient: column sums of gx from the same pass
+        cs = torch.full((C,), 77.0, device=dev)
+        gx2 = torch.empty_like(gx)
+        ops.maxpool_bwd(x, gp, gx2, k, s, gskip=gskip, relu_mask=True, colsum=cs)
+        torch.cuda.synchronize()
+        assert torch.equal(gx2, gx)
+        _report("maxpool_bwd.colsum", cs, ref.sum(dim=(0, 2, 3)), 2e-3)
 
 
 def test_pack_and_unpack():
