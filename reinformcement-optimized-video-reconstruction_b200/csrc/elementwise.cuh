@@ -327,16 +327,19 @@ __global__ void sum_partials_kernel(const float* __restrict__ partial, int n, fl
 }
 
 // out[j] = sum_{r < nrows} partial[r][j]   (fixed order), optional accumulate into out
-// Block = 32 columns x 8 row groups; each thread sums its rows (r = group, group+8, ...) with 4
-// independent accumulators, then the 8 groups are combined in a fixed order: deterministic and
-// ~30x faster than one thread per column.
-__global__ void __launch_bounds__(256)
+// Block = 32 columns x 32 row groups (1024 threads); each thread sums its rows (r = group,
+// group + 32, ...) with 4 independent accumulators, then the 32 groups are combined in a fixed
+// order. These reductions are pure latency (a few hundred KB): the wide block keeps 4 x 1024 loads
+// in flight per 32 columns instead of walking the rows with a handful of threads.
+constexpr int RR_GROUPS = 32;
+constexpr int RR_THREADS = 32 * RR_GROUPS;
+__global__ void __launch_bounds__(RR_THREADS)
 reduce_rows_kernel(const float* __restrict__ partial, int nrows, int row_stride, int ncols,
                    float* __restrict__ out, int accumulate, int rows_per_chunk = 0,
                    int out_stride = 0) {
   // blockIdx.y selects a chunk of rows (two-stage reduction of very tall partial buffers);
   // with gridDim.y == 1 the whole buffer is reduced straight into `out`.
-  __shared__ float sred[8][33];
+  __shared__ float sred[RR_GROUPS][33];
   const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + cl;
   const int r_begin = rows_per_chunk > 0 ? blockIdx.y * rows_per_chunk : 0;
@@ -345,20 +348,20 @@ reduce_rows_kernel(const float* __restrict__ partial, int nrows, int row_stride,
   if (j < ncols) {
     const float* p = partial + j;
     int r = r_begin + rg;
-    for (; r + 24 < r_end; r += 32) {
+    for (; r + 3 * RR_GROUPS < r_end; r += 4 * RR_GROUPS) {
       a0 += __ldg(p + static_cast<long long>(r) * row_stride);
-      a1 += __ldg(p + static_cast<long long>(r + 8) * row_stride);
-      a2 += __ldg(p + static_cast<long long>(r + 16) * row_stride);
-      a3 += __ldg(p + static_cast<long long>(r + 24) * row_stride);
+      a1 += __ldg(p + static_cast<long long>(r + RR_GROUPS) * row_stride);
+      a2 += __ldg(p + static_cast<long long>(r + 2 * RR_GROUPS) * row_stride);
+      a3 += __ldg(p + static_cast<long long>(r + 3 * RR_GROUPS) * row_stride);
     }
-    for (; r < r_end; r += 8) a0 += __ldg(p + static_cast<long long>(r) * row_stride);
+    for (; r < r_end; r += RR_GROUPS) a0 += __ldg(p + static_cast<long long>(r) * row_stride);
   }
   sred[rg][cl] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (rg == 0 && j < ncols) {
     float s = 0.f;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) s += sred[g][cl];
+    for (int g = 0; g < RR_GROUPS; ++g) s += sred[g][cl];
     float* o = out + static_cast<long long>(blockIdx.y) * out_stride + j;
     *o = accumulate ? *o + s : s;
   }

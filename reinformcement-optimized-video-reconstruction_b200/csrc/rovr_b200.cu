@@ -349,15 +349,15 @@ extern "C" int rovr_maxpool_bwd(const void* x, int x_ld, const void* gp, int gp_
     // [blocks][C] -> [chunks][C] -> [C], both stages in a fixed order
     const int kChunks = 256;
     if (blocks <= 4 * kChunks) {
-      reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(partial, blocks, C, C, colsum, 0);
+      reduce_rows_kernel<<<(C + 31) / 32, RR_THREADS, 0, st>>>(partial, blocks, C, C, colsum, 0);
       return launch_check("reduce_rows(pool colsum)");
     }
     float* tmp = partial + static_cast<size_t>(blocks) * C;
     const int rpc = (blocks + kChunks - 1) / kChunks;
     const int chunks = (blocks + rpc - 1) / rpc;
-    reduce_rows_kernel<<<dim3((C + 31) / 32, chunks), 256, 0, st>>>(partial, blocks, C, C, tmp, 0, rpc, C);
+    reduce_rows_kernel<<<dim3((C + 31) / 32, chunks), RR_THREADS, 0, st>>>(partial, blocks, C, C, tmp, 0, rpc, C);
     if (int rc = launch_check("reduce_rows(pool colsum, stage 1)")) return rc;
-    reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(tmp, chunks, C, C, colsum, 0);
+    reduce_rows_kernel<<<(C + 31) / 32, RR_THREADS, 0, st>>>(tmp, chunks, C, C, colsum, 0);
     return launch_check("reduce_rows(pool colsum, stage 2)");
   }
   ROVR_REQUIRE(gskip == nullptr, "maxpool_bwd: skip gradient only supported for non-overlapping windows");
@@ -401,6 +401,6 @@ extern "C" int rovr_colsum(const void* g, int ld, long long npix, int C, float* 
   colsum_partial_kernel<<<grid, threads, threads * 2 * sizeof(float), st>>>(
       static_cast<const __nv_bfloat16*>(g), ld, npix, C, static_cast<float*>(ws));
   if (int rc = launch_check("colsum_partial")) return rc;
-  reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(static_cast<float*>(ws), grid, C, C, out, 0);
+  reduce_rows_kernel<<<(C + 31) / 32, RR_THREADS, 0, st>>>(static_cast<float*>(ws), grid, C, C, out, 0);
   return launch_check("reduce_rows(colsum)");
 }

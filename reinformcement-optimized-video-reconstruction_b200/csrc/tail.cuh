@@ -206,4 +206,36 @@ tail_bwd_kernel(const __nv_bfloat16* __restrict__ y7, const float* __restrict__ 
     partial[static_cast<long long>(blockIdx.x) * TAILB_COLS + i] = sacc[i];
 }
 
+// One launch that reduces the [grid][TAILB_COLS] partial rows of tail_bwd_kernel and routes the
+// three column ranges to their gradients: dW8 (3*64) | db8 (3) | db7 (64, may be NULL).
+__global__ void __launch_bounds__(1024)
+tail_reduce_kernel(const float* __restrict__ partial, int nrows, float* __restrict__ dw8,
+                   float* __restrict__ db8, float* __restrict__ db7) {
+  __shared__ float sred[32][33];
+  const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + cl;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (j < TAILB_COLS) {
+    const float* p = partial + j;
+    int r = rg;
+    for (; r + 96 < nrows; r += 128) {
+      a0 += __ldg(p + static_cast<long long>(r) * TAILB_COLS);
+      a1 += __ldg(p + static_cast<long long>(r + 32) * TAILB_COLS);
+      a2 += __ldg(p + static_cast<long long>(r + 64) * TAILB_COLS);
+      a3 += __ldg(p + static_cast<long long>(r + 96) * TAILB_COLS);
+    }
+    for (; r < nrows; r += 32) a0 += __ldg(p + static_cast<long long>(r) * TAILB_COLS);
+  }
+  sred[rg][cl] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (rg == 0 && j < TAILB_COLS) {
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < 32; ++g) s += sred[g][cl];
+    if (j < 3 * TAIL_C) dw8[j] = s;
+    else if (j < 3 * TAIL_C + 3) db8[j - 3 * TAIL_C] = s;
+    else if (db7) db7[j - 3 * TAIL_C - 3] = s;
+  }
+}
+
 }  // namespace rovr

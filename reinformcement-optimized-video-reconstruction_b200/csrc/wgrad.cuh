@@ -240,8 +240,18 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   const int t = static_cast<int>((i / c_total) % taps);
   const int m = static_cast<int>(i / (static_cast<long long>(c_total) * taps));
   if (c >= c_keep || m >= m_keep) return;
-  float s = 0.f;
-  for (int k = 0; k < n_slices; ++k) s += partial[static_cast<long long>(k) * n + i];
+  // four independent partial sums keep four loads in flight (slices are ~100s of KB apart); the
+  // combination order is fixed, so the result stays bitwise reproducible
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int k = 0;
+  for (; k + 3 < n_slices; k += 4) {
+    s0 += __ldg(partial + static_cast<long long>(k) * n + i);
+    s1 += __ldg(partial + static_cast<long long>(k + 1) * n + i);
+    s2 += __ldg(partial + static_cast<long long>(k + 2) * n + i);
+    s3 += __ldg(partial + static_cast<long long>(k + 3) * n + i);
+  }
+  for (; k < n_slices; ++k) s0 += __ldg(partial + static_cast<long long>(k) * n + i);
+  const float s = (s0 + s1) + (s2 + s3);
   float* dst = grad + m * fs_m + t * fs_t + c * fs_c;
   *dst = accumulate ? (*dst + s) : s;
 }
