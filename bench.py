@@ -215,16 +215,6 @@ def run_cuda(args, rank, local_rank, world):
         loss.backward()
         return loss
 
-    def step_e2e():
-        xd = xh.to(dev, non_blocking=True)
-        cd = ch.to(dev, non_blocking=True)
-        td = th.to(dev, non_blocking=True)
-        net.zero_grad(set_to_none=True)
-        y = net(xd, cd)                                  # the reference-facing call
-        loss = torch.nn.functional.mse_loss(y, td)       # rovr/train_local_net_unet.py:107
-        loss.backward()
-        return float(loss)                               # D2H read of the step's result
-
     def barrier():
         if world > 1:
             dist.barrier()
@@ -249,13 +239,30 @@ def run_cuda(args, rank, local_rank, world):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    # Single GPU: the step (a fixed sequence of ~65 launches) is captured once into a CUDA graph and
+    # replayed; with N > 1 the bucketed NCCL all-reduce overlaps backward from Python hooks, so the
+    # step runs eagerly. The per-kernel CUDA events behind `roofline` / `kernel_classes` always
+    # come from an eager pass over the same K steps (events cannot be read inside a graph replay).
+    graphed = None
+    if world == 1 and not args.no_graph:
+        from local_net import GraphedTrainingStep
+        graphed = GraphedTrainingStep(net, x, c, t)
+        for _ in range(3):
+            graphed()
+        for _ in range(2):      # torch.cuda.graph() empties the allocator cache: refill it before timing eager steps
+            step_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     prof = []
     n0 = _native.lib.rovr_launch_count()
-    ms_total = timed(step_resident, args.steps, profile=prof)
+    ms_eager = timed(step_resident, args.steps, profile=prof)
     launches = _native.lib.rovr_launch_count() - n0
+    if graphed is not None:
+        ms_total = timed(graphed, args.steps)
+        launches = graphed.launches_per_step * args.steps
+    else:
+        ms_total = ms_eager
     clocks = sampler.stop() if rank == 0 else {}
     frames = B_PER_GPU * world * args.steps
     value = frames / (ms_total * 1e-3)
@@ -263,10 +270,25 @@ def run_cuda(args, rank, local_rank, world):
     if args.profile_run:
         ms_e2e, e2e_value = float("nan"), None
     else:
-        for _ in range(2):
-            step_e2e()
-        ms_e2e = timed(step_e2e, args.steps)
+        # end to end through the reference-facing nn.Module call, inputs in pinned HOST memory:
+        # every step copies its own inputs host -> device (DeviceFeeder: the copy of step i+1 is
+        # issued on a side stream before step i is computed) and reads the loss back to the host.
+        from feeder import DeviceFeeder
+
+        def e2e_loop(steps):
+            last = None
+            for xd, cd, td in DeviceFeeder(((xh, ch, th) for _ in range(steps)), dev):
+                net.zero_grad(set_to_none=True)
+                y = net(xd, cd)                                  # the reference-facing call
+                loss = torch.nn.functional.mse_loss(y, td)       # rovr/train_local_net_unet.py:107
+                loss.backward()
+                last = float(loss.detach())                      # D2H read of the step's result
+            return last
+
+        e2e_loop(2)
+        ms_e2e = timed(lambda: e2e_loop(args.steps), 1)
         e2e_value = frames / (ms_e2e * 1e-3)
+        ms_e2e = ms_e2e  # total over args.steps steps
 
     if rank != 0:
         if world > 1:
@@ -333,11 +355,15 @@ def run_cuda(args, rank, local_rank, world):
             "config": {"workload": "LocalNet U-Net fwd+L2+bwd (configs[1]): B=24 frames/GPU, 256x256, "
                                    "synthetic masked clips, random-init weights",
                        "global_batch": B_PER_GPU * world, "parallelism": f"dp{world}",
+                       "launch": ("one CUDA graph per step (GraphedTrainingStep)" if graphed is not None
+                                  else "eager launches"),
+                       "eager_ms_per_step_with_per_kernel_events": ms_eager / args.steps,
                        "l2": "each step streams ~2.5 GB of activations/gradients (>> 126 MB L2); no explicit flush",
                        "precision": "bf16 operands + bf16 activation storage, fp32 accumulate, fp32 master weights/grads"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": (xh.numel() + ch.numel() + th.numel()) * 4, "d2h_bytes_per_step": 4,
-                    "api": "y = LocalNetworkUNetNorm()(frame, context); F.mse_loss(y, target).backward(); float(loss)"},
+                    "api": "for frame, context, target in DeviceFeeder(pinned_host_batches): y = LocalNetworkUNetNorm()"
+                           "(frame, context); F.mse_loss(y, target).backward(); float(loss)"},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
             "clocks": clocks, "roofline": roofline, "kernel_classes": kc,
             "model_tflops": total_flops_per_frame * value / world / 1e12,
@@ -354,6 +380,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph replay")
     ap.add_argument("--profile-run", action="store_true",
                     help="for runs under ncu: skip the e2e and cpu_baseline legs (their numbers are null)")
     args = ap.parse_args()

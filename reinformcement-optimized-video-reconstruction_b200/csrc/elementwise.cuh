@@ -90,6 +90,45 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld
   *reinterpret_cast<uint4*>(y + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * y_ld + cv * 8) = m;
 }
 
+// 2x2 / stride 2 specialisation: the four 16-byte loads of a window are issued together and two
+// windows are processed per thread, so eight requests are in flight per thread.
+__global__ void __launch_bounds__(256)
+maxpool_fwd_2x2_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y, int y_ld,
+                       int B, int H, int W, int C) {
+  const int c8 = C >> 3;
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long n = static_cast<long long>(B) * Ho * Wo * c8;
+  const long long i0 = (static_cast<long long>(blockIdx.x) * blockDim.x * 2) + threadIdx.x;
+  uint4 v[2][4];
+  long long oaddr[2];
+  bool ok[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const long long i = i0 + static_cast<long long>(u) * blockDim.x;
+    ok[u] = i < n;
+    const long long ii = ok[u] ? i : 0;
+    const int cv = static_cast<int>(ii % c8);
+    long long r = ii / c8;
+    const int ox = static_cast<int>(r % Wo);
+    r /= Wo;
+    const int oy = static_cast<int>(r % Ho);
+    const int b = static_cast<int>(r / Ho);
+    const __nv_bfloat16* xb = x + ((static_cast<long long>(b) * H + oy * 2) * W + ox * 2) * x_ld + cv * 8;
+    v[u][0] = __ldg(reinterpret_cast<const uint4*>(xb));
+    v[u][1] = __ldg(reinterpret_cast<const uint4*>(xb + x_ld));
+    v[u][2] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(W) * x_ld));
+    v[u][3] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(W + 1) * x_ld));
+    oaddr[u] = ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * y_ld + cv * 8;
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    max8(v[u][0], v[u][1]);
+    max8(v[u][2], v[u][3]);
+    max8(v[u][0], v[u][2]);
+    if (ok[u]) *reinterpret_cast<uint4*>(y + oaddr[u]) = v[u][0];
+  }
+}
+
 // Backward for non-overlapping windows (stride == kernel, H % kh == 0, W % kw == 0): one thread
 // owns one window x 8 channels, routes the pooled gradient to the first maximum in row-major scan
 // order (ATen's rule), adds the skip-connection gradient arriving at the same tensor, and applies

@@ -303,6 +303,11 @@ extern "C" int rovr_maxpool_fwd(const void* x, int x_ld, void* y, int y_ld, int 
   ROVR_REQUIRE(C % 8 == 0 && x_ld % 8 == 0 && y_ld % 8 == 0, "maxpool_fwd: C and ld must be multiples of 8");
   const int Ho = (H - kh) / sh + 1, Wo = (W - kw) / sw + 1;
   const long long n = 1ll * B * Ho * Wo * (C / 8);
+  if (kh == 2 && kw == 2 && sh == 2 && sw == 2 && H % 2 == 0 && W % 2 == 0) {
+    maxpool_fwd_2x2_kernel<<<static_cast<unsigned>((n + 511) / 512), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), x_ld, static_cast<__nv_bfloat16*>(y), y_ld, B, H, W, C);
+    return launch_check("maxpool_fwd_2x2");
+  }
   maxpool_fwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0,
                        static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), x_ld, static_cast<__nv_bfloat16*>(y), y_ld, B, H, W, C,

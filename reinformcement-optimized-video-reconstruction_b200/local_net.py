@@ -278,3 +278,56 @@ class LocalNetworkUNetNorm(nn.Module):
         """(y_hat, mean((y_hat - target)^2)) with the loss and its gradient fused into the tail
         kernel: the `mse_loss_fn(y_hat, target)` of rovr/train_local_net_unet.py:107."""
         return self._run(x, context, target)
+
+
+class GraphedTrainingStep:
+    """forward + fused L2 loss + backward of a LocalNetworkUNetNorm captured ONCE into a CUDA graph.
+
+    A step is a fixed sequence of ~65 kernel launches of 20-400 us each; replaying it as a graph
+    removes the per-launch CPU cost and the gaps between kernels. Usage:
+
+        step = GraphedTrainingStep(net, frame, context, target)     # captures with these shapes
+        loss = step(frame, context, target)                         # copies into the static inputs, replays
+        # net.<param>.grad now hold this step's gradients (static tensors, overwritten by every replay)
+
+    The bf16 operand copies of the weights are re-packed inside the graph when
+    `repack_weights=True` (training: the optimizer changes the fp32 masters every step); with
+    False they are packed once before capture (inference-style benchmarking with fixed weights).
+    Single-process only: the bucketed NCCL all-reduce of data_parallel.GradientBuckets runs eagerly.
+    """
+
+    def __init__(self, net, x, context, target, repack_weights=False, warmup=2):
+        if net._grad_bucket_hook is not None:
+            raise RuntimeError("GraphedTrainingStep does not capture the data-parallel gradient hooks")
+        self.net = net
+        self.repack_weights = repack_weights
+        self.x, self.context, self.target = x.clone(), context.clone(), target.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):         # allocates the scratch workspace, packs the weights
+                net.zero_grad(set_to_none=True)
+                _, loss = net.forward_with_mse(self.x, self.context, self.target)
+                loss.backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        net.zero_grad(set_to_none=True)
+        if repack_weights:
+            net._packed._cache.clear()
+        import _native
+        n0 = _native.lib.rovr_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.y, self.loss = net.forward_with_mse(self.x, self.context, self.target)
+            self.loss.backward()
+        self.launches_per_step = int(_native.lib.rovr_launch_count() - n0)
+
+    def __call__(self, x=None, context=None, target=None):
+        if x is not None:
+            self.x.copy_(x, non_blocking=True)
+        if context is not None:
+            self.context.copy_(context, non_blocking=True)
+        if target is not None:
+            self.target.copy_(target, non_blocking=True)
+        self.graph.replay()
+        return self.loss

@@ -10,7 +10,7 @@ import json
 try:
     line=[l for l in open('gpurun_out/bench.log') if l.startswith('{')][-1]
     d=json.loads(line)
-    print("value", round(d["value"],1), "ms/step", round(d["ms_per_step"],3), "e2e", d["e2e"]["value"], "clocks", d["clocks"])
+    print("value", round(d["value"],1), "ms/step", round(d["ms_per_step"],3), "eager", round(d["config"].get("eager_ms_per_step_with_per_kernel_events",0),3), "e2e", d["e2e"]["value"], "clocks", d["clocks"])
     print("roofline", {k:(round(v,4) if isinstance(v,float) else v) for k,v in d["roofline"].items() if k in ("achieved","frac","avg_launch_ms")})
     print({k:(round(v["ms_per_step"],3), round(v.get("tflops",0),1)) for k,v in d["kernel_classes"].items()})
     print("model_tflops", round(d["model_tflops"],1), "cpu", d["cpu_baseline"]["value"] if d["cpu_baseline"] else None)

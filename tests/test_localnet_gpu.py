@@ -219,3 +219,49 @@ def test_localnet_full_size_properties():
     torch.cuda.synchronize()
     for n, g in g1.items():
         assert torch.equal(g, dict(net.named_parameters())[n].grad), n
+
+
+def test_graphed_training_step_matches_eager():
+    """The CUDA-graph replay of forward + L2 + backward gives bit-identical loss and gradients to
+    the eager step, follows new inputs, and re-packs updated weights when asked to."""
+    from local_net import LocalNetworkUNetNorm, GraphedTrainingStep
+    from feeder import DeviceFeeder
+    import _native
+    import rovr_oracle as O
+    _native.require_device()
+    dev = torch.device("cuda:0")
+    sd = O.localnet_state_dict(0)
+    net = LocalNetworkUNetNorm()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev)
+    x, c, t = [v.to(dev) for v in O.synthetic_localnet_batch(2, 64, 64, seed=5)]
+    x2, c2, t2 = O.synthetic_localnet_batch(2, 64, 64, seed=6)
+
+    def eager(a, b, cc):
+        net.zero_grad(set_to_none=True)
+        _, loss = net.forward_with_mse(a, b, cc)
+        loss.backward()
+        return loss.detach().clone(), {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None}
+
+    l1, g1 = eager(x, c, t)
+    l2, g2 = eager(x2.to(dev), c2.to(dev), t2.to(dev))
+    step = GraphedTrainingStep(net, x, c, t, repack_weights=True)
+    assert step.launches_per_step > 40
+    la = step().clone()
+    assert torch.equal(la, l1)
+    for n, p in net.named_parameters():
+        if n in g1:
+            assert torch.equal(p.grad, g1[n]), n
+    # new inputs arrive through the pinned-host feeder
+    (xd, cd, td), = list(DeviceFeeder([(x2.pin_memory(), c2.pin_memory(), t2.pin_memory())], dev))
+    lb = step(xd, cd, td).clone()
+    assert torch.equal(lb, l2)
+    for n, p in net.named_parameters():
+        if n in g2:
+            assert torch.equal(p.grad, g2[n]), n
+    # an optimizer-style in-place update of the fp32 masters is picked up by the replay (repack in graph)
+    with torch.no_grad():
+        net.conv5.weight.mul_(1.01)
+    lc = step().clone()
+    ld, _ = eager(x2.to(dev), c2.to(dev), t2.to(dev))
+    assert torch.equal(lc, ld) and not torch.equal(lc, lb)
