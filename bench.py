@@ -297,7 +297,7 @@ def run_cuda(args, rank, local_rank, world):
 
     # ---- per-kernel-class roofline from the events recorded inside the timed region ----
     peaks = measured_peaks()
-    classes = {"igemm": ["rovr_conv3x3_fprop", "rovr_conv3x3_dgrad", "rovr_convT2x2_fprop", "rovr_convT2x2_dgrad"],
+    classes = {"igemm": ["rovr_conv3x3_fprop", "rovr_conv3x3_fprop_pool2", "rovr_conv3x3_dgrad", "rovr_convT2x2_fprop", "rovr_convT2x2_dgrad"],
                "wgrad": ["rovr_conv3x3_wgrad", "rovr_convT2x2_wgrad"],
                "tail": ["rovr_tail_fwd", "rovr_tail_bwd"],
                "pool": ["rovr_maxpool_fwd", "rovr_maxpool_bwd"],

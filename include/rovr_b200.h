@@ -63,6 +63,11 @@ int rovr_repack_linear(const float* w, void* wk, int N, int K, int n_pad, int k_
  * rovr/policy_net_1.py:19-47,61-81; rovr/policy_net_2.py:42-54. Cin, Cout multiples of 16. */
 int rovr_conv3x3_fprop(const void* x, int x_ld, const void* wk, const float* bias, void* y, int y_ld,
                        int B, int H, int W, int Cin, int Cout, int relu, void* stream);
+/* same, and additionally pooled = nn.MaxPool2d(2, 2)(y) from the same epilogue (the encoder's
+ * conv -> ReLU -> pool of rovr/local_net.py:52-55 in one kernel); needs W >= 8, H >= 16, even H, W. */
+int rovr_conv3x3_fprop_pool2(const void* x, int x_ld, const void* wk, const float* bias, void* y, int y_ld,
+                             void* pooled, int pooled_ld, int B, int H, int W, int Cin, int Cout, int relu,
+                             void* stream);
 /* dx = conv3x3^T(dy); if mask != NULL, dx *= (mask > 0) (ReLU of the producer of x).
  * If colsum != NULL it receives sum over pixels of dx[pixel][c] for c < colsum_cols <= Cin (fp32) —
  * the bias gradient of the layer that produced those channels of x — computed in the epilogue;

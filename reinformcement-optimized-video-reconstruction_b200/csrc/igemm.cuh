@@ -85,6 +85,8 @@ struct IgemmParams {
   int cw;                 // epilogue column-block width: 16 / 32 / 64 channels
   int relu;
   int has_mask;
+  int pool2;              // 1 (halo mode, plain epilogue): also emit the 2x2 max-pooled tile (4 x 8 pixels) through
+                          //    the fourth tensor map — nn.MaxPool2d(2, 2) of the encoder fused into the conv
   int b_batched;          // 1: the B operand is a rank-5 map (K, N, d2, d3, d4) whose trailing coordinates are
                           //    the tile's M-space origin org[1..3] (batched GEMM: one B matrix per head / batch)
   int halo;               // 1: Conv2d 3x3 with the input patch loaded once per k-chunk (see below)
@@ -166,7 +168,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* aring = smem + front_bytes;                                           // halo tiles
   aring += (1024u - (smem_u32(aring) & 1023u)) & 1023u;                          // swizzle alignment
   uint8_t* stg_base = aring + (halo ? p.a_slots * halo_slot : 0);                // 2 staging tiles
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + 2 * stg_bytes);
+  const uint32_t pstg_bytes = p.pool2 ? 32u * epi_rowb : 0u;                     // pooled tile: 32 rows
+  uint8_t* pstg_base = stg_base + 2 * stg_bytes;                                 // 2 pooled staging tiles
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(pstg_base + 2 * pstg_bytes);
   uint64_t* empty_bar = full_bar + IG_MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + IG_MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -187,6 +191,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
+    if (p.pool2) tma_prefetch_desc(&tmMask);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -389,6 +394,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int nblk = p.n_tile / p.cw;
     const int chunks = p.cw >> 4;
     uint8_t* stg = stg_base + grp * stg_bytes;
+    uint8_t* pstg = pstg_base + grp * pstg_bytes;
+    // pooled-tile row of this lane's 2x2 window: the tile is 8 (x) by 16 (y) pixels, row m = x + 8 y,
+    // so the window partners are lanes l ^ 1 (x) and l ^ 8 (y) of the same warp
+    const int pm = ((lane & 7) >> 1) + 4 * (quarter * 2 + (lane >> 4));
     const int acc = grp;
     uint32_t aph = 0;
     const int cpr = epi_rowb >> 4;        // 16-byte chunks per output row of a block: 8 / 4 / 2
@@ -551,6 +560,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     }
                     *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2, epi_rowb)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2 + 1, epi_rowb)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    if (kPlainEpi && p.pool2) {
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) {
+                        __nv_bfloat162 a, b;
+                        uint32_t o = __shfl_xor_sync(0xffffffffu, pk[j], 1);
+                        memcpy(&a, &pk[j], 4);
+                        memcpy(&b, &o, 4);
+                        a = __hmax2(a, b);
+                        memcpy(&pk[j], &a, 4);
+                        o = __shfl_xor_sync(0xffffffffu, pk[j], 8);
+                        memcpy(&b, &o, 4);
+                        a = __hmax2(a, b);
+                        memcpy(&pk[j], &a, 4);
+                      }
+                      if ((lane & 9) == 0) {
+                        *reinterpret_cast<uint4*>(pstg + swz_off(pm, ch * 2, epi_rowb)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(pstg + swz_off(pm, ch * 2 + 1, epi_rowb)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                      }
+                    }
                     if (want_cs) {
                       // column sums of the STORED values over the warp's 32 rows: reduce-scatter
                       float w[16];
@@ -607,6 +635,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               c[0] = nglb;
             }
             tma_store_5d(&tmOut, stg, c[0], c[1], c[2], c[3], c[4]);
+            if (kPlainEpi && p.pool2) tma_store_5d(&tmMask, pstg, c[0], c[1] >> 1, c[2] >> 1, c[3], c[4]);
             bulk_commit();
           }
         }
@@ -629,9 +658,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 // Fixed (non-pipeline) shared memory of a configuration (host side).
-inline size_t igemm_fixed_smem(int cw, int has_mask, int n_total, int a_slots = 0, int sw = 128) {
-  (void)has_mask;  // the ReLU mask no longer lives in shared memory
-  const size_t stg = 128 * static_cast<size_t>(cw) * 2;
+inline size_t igemm_fixed_smem(int cw, int pool2, int n_total, int a_slots = 0, int sw = 128) {
+  const size_t stg = 128 * static_cast<size_t>(cw) * 2 + (pool2 ? 32 * static_cast<size_t>(cw) * 2 : 0);
   return 2048 + static_cast<size_t>(a_slots) * ig_halo_slot(sw) + 2 * stg +
          (2 * IG_MAX_STAGES + 2 * IG_MAX_ASLOTS + 7) * 8 + 16 +
          static_cast<size_t>(n_total) * 4 + 64;

@@ -94,15 +94,20 @@ class _LocalNetFunction(torch.autograd.Function):
         a["cat6"] = torch.empty((B, H // 2, W // 2, 256), dtype=bf, device=dev)
         a["cat5"] = torch.empty((B, H // 4, W // 4, 512), dtype=bf, device=dev)
         x1, x2, x3 = a["cat7"][..., 64:], a["cat6"][..., 128:], a["cat5"][..., 256:]
-        ops.conv3x3_fprop(a["in16"], wk("conv1"), P["conv1.bias"], x1)
+        def conv_pool(src, name, dst, pooled):
+            # conv + ReLU + MaxPool2d(2,2) in one kernel when the halo tiling applies (W >= 8, H >= 16)
+            if src.shape[1] >= 16 and src.shape[2] >= 8:
+                ops.conv3x3_fprop(src, wk(name), P[name + ".bias"], dst, pooled=pooled)
+            else:
+                ops.conv3x3_fprop(src, wk(name), P[name + ".bias"], dst)
+                ops.maxpool_fwd(dst, pooled, 2)
+
         a["p1"] = torch.empty((B, H // 2, W // 2, 64), dtype=bf, device=dev)
-        ops.maxpool_fwd(x1, a["p1"], 2)
-        ops.conv3x3_fprop(a["p1"], wk("conv2"), P["conv2.bias"], x2)
+        conv_pool(a["in16"], "conv1", x1, a["p1"])
         a["p2"] = torch.empty((B, H // 4, W // 4, 128), dtype=bf, device=dev)
-        ops.maxpool_fwd(x2, a["p2"], 2)
-        ops.conv3x3_fprop(a["p2"], wk("conv3"), P["conv3.bias"], x3)
+        conv_pool(a["p1"], "conv2", x2, a["p2"])
         a["p3"] = torch.empty((B, H // 8, W // 8, 256), dtype=bf, device=dev)
-        ops.maxpool_fwd(x3, a["p3"], 2)
+        conv_pool(a["p2"], "conv3", x3, a["p3"])
         a["x4"] = torch.empty((B, H // 8, W // 8, 512), dtype=bf, device=dev)
         ops.conv3x3_fprop(a["p3"], wk("conv4"), P["conv4.bias"], a["x4"])
 

@@ -141,11 +141,19 @@ def repack_convT2x2(w, for_dgrad=False):
 # ---------------------------------------------------------------------------------------------
 # Conv2d 3x3
 # ---------------------------------------------------------------------------------------------
-def conv3x3_fprop(x, wk, bias, y, relu=True):
+def conv3x3_fprop(x, wk, bias, y, relu=True, pooled=None):
+    """y = [relu](conv3x3(x) + bias); pooled (optional, [B, H/2, W/2, Cout]) = max_pool2d(y, 2) from the
+    same kernel."""
     B, H, W, Cin, x_ld = _act(x, "x")
     By, Hy, Wy, Cout, y_ld = _act(y, "y")
     assert (B, H, W) == (By, Hy, Wy) and wk.shape == (Cout, 9 * Cin), (x.shape, y.shape, wk.shape)
     _f32(bias, "bias")
+    if pooled is not None:
+        Bp, Hp, Wp, Cp, p_ld = _act(pooled, "pooled")
+        assert (Bp, Hp, Wp, Cp) == (B, H // 2, W // 2, Cout)
+        _launch("rovr_conv3x3_fprop_pool2", _ptr(x), x_ld, _ptr(wk), _ptr(bias), _ptr(y), y_ld, _ptr(pooled), p_ld,
+                B, H, W, Cin, Cout, int(relu), _stream())
+        return y
     _launch("rovr_conv3x3_fprop", _ptr(x), x_ld, _ptr(wk), _ptr(bias), _ptr(y), y_ld, B, H, W, Cin,
            Cout, int(relu), _stream())
     return y

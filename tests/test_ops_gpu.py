@@ -88,6 +88,29 @@ def test_conv3x3_fprop(B, H, W, Cin, Cout):
     assert (ybuf[..., :8] == 7.0).all() and (ybuf[..., 8 + Cout:] == 7.0).all(), "wrote outside its slice"
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (1, 32, 24, 16, 64), (3, 20, 12, 64, 128),
+                                            (1, 16, 8, 128, 256), (2, 64, 64, 64, 16)])
+def test_conv3x3_fprop_fused_pool(B, H, W, Cin, Cout):
+    """conv + ReLU + MaxPool2d(2, 2) from one kernel (encoder of rovr/local_net.py:52-55)."""
+    import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 77 + H + Cin + Cout)
+    x = _rand_act((B, H, W, Cin), g, dev)
+    w = (torch.randn((Cout, Cin, 3, 3), generator=g) * (1.0 / (3 * Cin ** 0.5))).to(dev)
+    b = torch.randn((Cout,), generator=g).to(dev) * 0.1
+    wk = ops.repack_conv3x3(w)
+    ybuf = torch.full((B, H, W, Cout + 16), 7.0, dtype=BF, device=dev)
+    y = ybuf[..., 8:8 + Cout]
+    pooled = torch.full((B, H // 2, W // 2, Cout), -3.0, dtype=BF, device=dev)
+    ops.conv3x3_fprop(x, wk, b, y, relu=True, pooled=pooled)
+    y2 = torch.empty((B, H, W, Cout), dtype=BF, device=dev)
+    ops.conv3x3_fprop(x, wk, b, y2, relu=True)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y2), "fused pooling changed the convolution output"
+    assert torch.equal(_nchw(pooled), F.max_pool2d(_nchw(y2), 2)), "pooled tile differs from max_pool2d of the stored output"
+    assert (ybuf[..., :8] == 7.0).all() and (ybuf[..., 8 + Cout:] == 7.0).all()
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout", CONV_SHAPES)
 def test_conv3x3_dgrad(B, H, W, Cin, Cout):
     import ops
