@@ -239,12 +239,13 @@ def run_cuda(args, rank, local_rank, world):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    # Single GPU: the step (a fixed sequence of ~65 launches) is captured once into a CUDA graph and
-    # replayed; with N > 1 the bucketed NCCL all-reduce overlaps backward from Python hooks, so the
-    # step runs eagerly. The per-kernel CUDA events behind `roofline` / `kernel_classes` always
-    # come from an eager pass over the same K steps (events cannot be read inside a graph replay).
+    # The compute of a step (a fixed sequence of ~65 launches) is captured once into a CUDA graph and
+    # replayed; when N > 1 the two flat gradient buckets are all-reduced with NCCL right after each
+    # replay (inside the timed region). The per-kernel CUDA events behind `roofline` /
+    # `kernel_classes` come from an eager pass over the same K steps (events cannot be read inside a
+    # graph replay).
     graphed = None
-    if world == 1 and not args.no_graph:
+    if not args.no_graph:
         from local_net import GraphedTrainingStep
         graphed = GraphedTrainingStep(net, x, c, t)
         for _ in range(3):
@@ -355,8 +356,9 @@ def run_cuda(args, rank, local_rank, world):
             "config": {"workload": "LocalNet U-Net fwd+L2+bwd (configs[1]): B=24 frames/GPU, 256x256, "
                                    "synthetic masked clips, random-init weights",
                        "global_batch": B_PER_GPU * world, "parallelism": f"dp{world}",
-                       "launch": ("one CUDA graph per step (GraphedTrainingStep)" if graphed is not None
-                                  else "eager launches"),
+                       "launch": (("one CUDA graph per step (GraphedTrainingStep)" +
+                                   (" + NCCL all-reduce of 2 gradient buckets after each replay" if world > 1 else ""))
+                                  if graphed is not None else "eager launches, bucketed all-reduce overlapped with backward"),
                        "eager_ms_per_step_with_per_kernel_events": ms_eager / args.steps,
                        "l2": "each step streams ~2.5 GB of activations/gradients (>> 126 MB L2); no explicit flush",
                        "precision": "bf16 operands + bf16 activation storage, fp32 accumulate, fp32 master weights/grads"},

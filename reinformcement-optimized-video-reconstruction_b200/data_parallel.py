@@ -42,6 +42,7 @@ class GradientBuckets:
         self.launched = 0
         module._grad_bucket_hook = self.ready
         module._grad_bucket_wait = self.wait
+        module._grad_bucket_reduce = self.reduce_now
 
     def ready(self, index, flat):
         if self.world == 1:
@@ -58,6 +59,18 @@ class GradientBuckets:
             # gloo (CPU tests of the host logic): SUM then scale
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self.pending.append((work, flat))
+
+    def reduce_now(self, flats):
+        """Average the given flat gradient buckets on the current stream (used after a CUDA-graph
+        replay of the compute, where the per-bucket hooks do not fire)."""
+        if self.world == 1:
+            return
+        for flat in flats:
+            if self.on_gpu:
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+                flat.div_(self.world)
 
     def wait(self):
         if self.world == 1:

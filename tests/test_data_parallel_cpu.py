@@ -48,6 +48,12 @@ def _worker(rank, world, port, q):
     ok_enc = torch.allclose(enc, torch.arange(enc.numel(), dtype=torch.float32) * mean_scale)
     # views alias the flat buffers: per-parameter gradients see the averaged values
     ok_view = torch.allclose(dviews["conv8.bias"], torch.full((3,), mean_scale))
+    # the post-replay path of GraphedTrainingStep: both buckets averaged in one call
+    dec.fill_(float(rank + 1))
+    enc.fill_(2.0 * (rank + 1))
+    net._grad_bucket_reduce((dec, enc))
+    ok_dec = ok_dec and torch.allclose(dec, torch.full_like(dec, mean_scale))
+    ok_enc = ok_enc and torch.allclose(enc, torch.full_like(enc, 2.0 * mean_scale))
     lo, hi = shard_range(50, rank, world)
     q.put((rank, same_after_broadcast, ok_dec, ok_enc, ok_view, dec.numel(), enc.numel(), gb.launched, lo, hi))
     dist.destroy_process_group()
