@@ -268,6 +268,7 @@ def run_cuda(args, rank, local_rank, world):
     frames = B_PER_GPU * world * args.steps
     value = frames / (ms_total * 1e-3)
 
+    e2e_graph = None
     if args.profile_run:
         ms_e2e, e2e_value = float("nan"), None
     else:
@@ -289,7 +290,18 @@ def run_cuda(args, rank, local_rank, world):
         e2e_loop(2)
         ms_e2e = timed(lambda: e2e_loop(args.steps), 1)
         e2e_value = frames / (ms_e2e * 1e-3)
-        ms_e2e = ms_e2e  # total over args.steps steps
+        # the same end-to-end loop through this repository's graphed training-step entry point
+        e2e_graph = None
+        if graphed is not None:
+            def e2e_graph_loop(steps):
+                last = None
+                for xd, cd, td in DeviceFeeder(((xh, ch, th) for _ in range(steps)), dev):
+                    last = float(graphed(xd, cd, td))
+                return last
+            e2e_graph_loop(2)
+            ms_g = timed(lambda: e2e_graph_loop(args.steps), 1)
+            e2e_graph = {"value": frames / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g / args.steps,
+                         "api": "for batch in DeviceFeeder(pinned_host_batches): float(GraphedTrainingStep(net, ...)(*batch))"}
 
     if rank != 0:
         if world > 1:
@@ -366,6 +378,7 @@ def run_cuda(args, rank, local_rank, world):
                     "h2d_bytes_per_step": (xh.numel() + ch.numel() + th.numel()) * 4, "d2h_bytes_per_step": 4,
                     "api": "for frame, context, target in DeviceFeeder(pinned_host_batches): y = LocalNetworkUNetNorm()"
                            "(frame, context); F.mse_loss(y, target).backward(); float(loss)"},
+            "e2e_graphed_step": e2e_graph,
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
             "clocks": clocks, "roofline": roofline, "kernel_classes": kc,
             "model_tflops": total_flops_per_frame * value / world / 1e12,
