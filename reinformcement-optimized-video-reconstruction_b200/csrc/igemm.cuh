@@ -314,39 +314,53 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait_warp(wfull_bar, 0u, 0xb00u);
       tc_fence_after();
     }
-    auto tile_loop = [&](auto ks_tag) {
+    // The issuing warp's own instruction stream is what bounds thin layers (ncu: with N <= 64 or
+    // 16-channel K chunks an MMA retires faster than ~70 SASS instructions of generic per-tap control
+    // flow), so the tap loop is specialised at compile time: KS = K steps per tap, and for the halo
+    // mode TPS = taps per weight stage (9 / 3 / 1) or 0 = weights resident in shared memory. Inside,
+    // every tap is straight-line code: two adds and one asm block.
+    auto tile_loop = [&](auto ks_tag, auto tps_tag) {
       constexpr int KS = decltype(ks_tag)::value;
+      constexpr int TPS = decltype(tps_tag)::value;
+      uint32_t tap_a[9];  // halo-tile row offset of tap t = (dy, dx): (dy * 10 + dx) rows, in 16-byte units
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tap_a[t] = static_cast<uint32_t>((t / 3) * (IG_HALO_TW + 2) + (t % 3)) * row16;
+      const uint32_t w16 = smem_u32(smem) >> 4;
+      const uint32_t stage16 = stage_bytes >> 4;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait_warp(&tempty_bar[acc], aph ^ 1u, 0x200u + acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
         uint32_t accum = 0;
         if (halo) {
-          const uint32_t w16 = smem_u32(smem) >> 4;
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait_warp(&afull_bar[sa], pha, 0xa00u + sa);
             tc_fence_after();
             const uint32_t a_slot16 = smem_u32(aring + sa * halo_slot) >> 4;
-            uint32_t bd = w16 + static_cast<uint32_t>(kc) * b16;  // resident: tile (t, kc) = t*kchunks + kc
-            const uint32_t bstep = p.resident_b ? static_cast<uint32_t>(kchunks) * b16 : b16;
+            if constexpr (TPS == 0) {
+              // resident weights: tile (t, kc) sits at (t * kchunks + kc) * b16
+              const uint32_t bd0 = w16 + static_cast<uint32_t>(kc) * b16;
+              const uint32_t bstep = static_cast<uint32_t>(kchunks) * b16;
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              if (!p.resident_b && ((p.stage_begin_mask >> t) & 1u)) {
+              for (int t = 0; t < 9; ++t)
+                umma_tap<KS>(d_tmem, a_slot16 + tap_a[t], a_hi_halo, bd0 + static_cast<uint32_t>(t) * bstep, b_hi, idesc,
+                             t == 0 ? accum : 1u);
+            } else {
+#pragma unroll
+              for (int t0 = 0; t0 < 9; t0 += TPS) {
                 mbar_wait_warp(&full_bar[s], ph, 0x300u + s);
                 tc_fence_after();
-                bd = smem_u32(smem + static_cast<size_t>(s) * stage_bytes) >> 4;
-              }
-              // tap t = (dy, dx) views the halo tile (dy*10 + dx) rows further on
-              umma_tap<KS>(d_tmem, a_slot16 + static_cast<uint32_t>((t / 3) * (IG_HALO_TW + 2) + (t % 3)) * row16,
-                           a_hi_halo, bd, b_hi, idesc, accum);
-              accum = 1u;
-              bd += bstep;
-              if (!p.resident_b && ((p.stage_end_mask >> t) & 1u)) {
+                const uint32_t bd0 = w16 + static_cast<uint32_t>(s) * stage16;
+#pragma unroll
+                for (int u = 0; u < TPS; ++u)
+                  umma_tap<KS>(d_tmem, a_slot16 + tap_a[t0 + u], a_hi_halo, bd0 + static_cast<uint32_t>(u) * b16, b_hi,
+                               idesc, (t0 + u) == 0 ? accum : 1u);
                 umma_commit_elect(&empty_bar[s]);
                 __syncwarp();
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
               }
             }
+            accum = 1u;
             umma_commit_elect(&aempty_bar[sa]);  // halo tile consumed by all nine taps
             __syncwarp();
             if (++sa == p.a_slots) { sa = 0; pha ^= 1u; }
@@ -357,7 +371,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const int nsub = (k_iters - it0) < p.tps ? (k_iters - it0) : p.tps;
             mbar_wait_warp(&full_bar[s], ph, 0x300u + s);
             tc_fence_after();
-            const uint32_t st16 = smem_u32(smem + static_cast<size_t>(s) * stage_bytes) >> 4;
+            const uint32_t st16 = w16 + static_cast<uint32_t>(s) * stage16;
             for (int u = 0; u < nsub; ++u) {
               const uint32_t ad = st16 + static_cast<uint32_t>(u) * sub16;
               umma_tap<KS>(d_tmem, ad, a_hi_dense, ad + a16, b_hi, idesc, accum);
@@ -373,9 +387,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (++acc == 2) { acc = 0; aph ^= 1u; }
       }
     };
-    if (ksteps == 4) tile_loop(std::integral_constant<int, 4>{});
-    else if (ksteps == 2) tile_loop(std::integral_constant<int, 2>{});
-    else tile_loop(std::integral_constant<int, 1>{});
+    auto with_ks = [&](auto tps_tag) {
+      if (ksteps == 4) tile_loop(std::integral_constant<int, 4>{}, tps_tag);
+      else if (ksteps == 2) tile_loop(std::integral_constant<int, 2>{}, tps_tag);
+      else tile_loop(std::integral_constant<int, 1>{}, tps_tag);
+    };
+    if (!halo || p.resident_b) with_ks(std::integral_constant<int, 0>{});
+    else if (p.tps == 9) with_ks(std::integral_constant<int, 9>{});
+    else if (p.tps == 3) with_ks(std::integral_constant<int, 3>{});
+    else with_ks(std::integral_constant<int, 1>{});
   } else {
     // ================================ epilogue ====================================
     // Two groups of four warps. Group g drains accumulator stage g — every other tile of this
