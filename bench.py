@@ -89,7 +89,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -237,6 +237,11 @@ def run_cuda(args, rank, local_rank, world):
             ms = float(tms.item())
         return ms
 
+    # nvidia-smi needs a few hundred ms to start reporting: launch the clock sampler before the
+    # warm-up so that it is certainly sampling during the timed regions (warm-up runs the same load)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     # The compute of a step (a fixed sequence of ~65 launches) is captured once into a CUDA graph and
@@ -252,9 +257,6 @@ def run_cuda(args, rank, local_rank, world):
             graphed()
         for _ in range(2):      # torch.cuda.graph() empties the allocator cache: refill it before timing eager steps
             step_resident()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     prof = []
     n0 = _native.lib.rovr_launch_count()
     ms_eager = timed(step_resident, args.steps, profile=prof)

@@ -14,6 +14,8 @@
 // patches; per patch it issues taps x 4 MMAs of N = c-chunk columns. Partials are reduced in a
 // fixed order by wgrad_reduce_kernel.
 #pragma once
+#include <type_traits>
+
 #include "ptx.cuh"
 #include "wgrad.cuh"
 
@@ -151,26 +153,44 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t a_step = static_cast<uint32_t>(16 * sw_a) >> 4;             // 16 rows
     const uint32_t b_step = static_cast<uint32_t>(2 * WH_HALO * sw_b) >> 4;    // 2 image rows
     const uint32_t row16 = static_cast<uint32_t>(sw_b) >> 4;
-    int s = 0;
-    uint32_t ph = 0;
-    uint32_t accum = 0;
-    for (int kt = kt0; kt < kt1; ++kt) {
-      mbar_wait(&full_bar[s], ph, 0x600u + s);
-      __syncwarp();
-      tc_fence_after();
-      const uint32_t a16 = smem_u32(smem + static_cast<size_t>(s) * stage_bytes) >> 4;
-      const uint32_t b16 = a16 + (a_bytes >> 4);
-      for (int tl = 0; tl < t_count; ++tl) {
+    // The tap loop is unrolled at compile time (TC taps per CTA) with the per-tap operand offsets
+    // precomputed: with 16-channel operands an MMA retires faster than a generic loop iteration
+    // issues, and this single warp's instruction stream is what bounds the kernel.
+    auto run = [&](auto tc_tag) {
+      constexpr int TC = decltype(tc_tag)::value;
+      uint32_t tap_b[TC];
+#pragma unroll
+      for (int tl = 0; tl < TC; ++tl) {
         const int t = t_first + tl;
         const int dy = p.tap_sign * (t / 3 - 1) + 1, dx = p.tap_sign * (t % 3 - 1) + 1;  // halo-relative
-        umma_mn_x4(tmem_base + static_cast<uint32_t>(tl * ncol), a_lbo | a16, a_hi, a_step,
-                   b_lbo | (b16 + static_cast<uint32_t>(dy * WH_HALO + dx) * row16), b_hi, b_step, idesc,
-                   accum);
+        tap_b[tl] = b_lbo | (static_cast<uint32_t>(dy * WH_HALO + dx) * row16);
       }
-      accum = 1u;
-      umma_commit_elect(&empty_bar[s]);
-      __syncwarp();
-      if (++s == p.stages) { s = 0; ph ^= 1u; }
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t accum = 0;
+      const uint32_t stage16 = stage_bytes >> 4;
+      const uint32_t base16 = smem_u32(smem) >> 4;
+      for (int kt = kt0; kt < kt1; ++kt) {
+        mbar_wait(&full_bar[s], ph, 0x600u + s);
+        __syncwarp();
+        tc_fence_after();
+        const uint32_t a16 = base16 + static_cast<uint32_t>(s) * stage16;
+        const uint32_t b16 = a16 + (a_bytes >> 4);
+#pragma unroll
+        for (int tl = 0; tl < TC; ++tl)
+          umma_mn_x4(tmem_base + static_cast<uint32_t>(tl * ncol), a_lbo | a16, a_hi, a_step, tap_b[tl] + b16, b_hi,
+                     b_step, idesc, accum);
+        accum = 1u;
+        umma_commit_elect(&empty_bar[s]);
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    };
+    switch (t_count) {
+      case 9: run(std::integral_constant<int, 9>{}); break;
+      case 5: run(std::integral_constant<int, 5>{}); break;
+      case 4: run(std::integral_constant<int, 4>{}); break;
+      default: run(std::integral_constant<int, 3>{}); break;
     }
     umma_commit_elect(done_bar);
     __syncwarp();
