@@ -68,13 +68,15 @@ int rovr_conv3x3_fprop(const void* x, int x_ld, const void* wk, const float* bia
 int rovr_conv3x3_fprop_pool2(const void* x, int x_ld, const void* wk, const float* bias, void* y, int y_ld,
                              void* pooled, int pooled_ld, int B, int H, int W, int Cin, int Cout, int relu,
                              void* stream);
-/* dx = conv3x3^T(dy); if mask != NULL, dx *= (mask > 0) (ReLU of the producer of x).
+/* dx = conv3x3^T(dy); if mask != NULL, dx[..., c] *= (mask[..., c] > 0) for c < mask_cols (ReLU of the
+ * producer of x; mask_cols <= 0 means all Cin channels — the skip half of a U-Net concat gradient is
+ * masked by the pool backward that consumes it, so only the up-conv half needs it here).
  * If colsum != NULL it receives sum over pixels of dx[pixel][c] for c < colsum_cols <= Cin (fp32) —
  * the bias gradient of the layer that produced those channels of x — computed in the epilogue;
  * ws >= rovr_dgrad_colsum_workspace(B,H,W,Cin). */
 size_t rovr_dgrad_colsum_workspace(int B, int H, int W, int C);
 int rovr_conv3x3_dgrad(const void* dy, int dy_ld, const void* wk_d, void* dx, int dx_ld,
-                       const void* mask, int mask_ld, int B, int H, int W, int Cin, int Cout,
+                       const void* mask, int mask_ld, int mask_cols, int B, int H, int W, int Cin, int Cout,
                        float* colsum, int colsum_cols, void* ws, size_t ws_bytes, void* stream);
 size_t rovr_conv3x3_wgrad_workspace(int B, int H, int W, int Cin, int Cout);
 /* dw[Cout][cin_keep][3][3] (fp32) = sum_pixels dy (x) x_shifted; Cin is the padded channel count

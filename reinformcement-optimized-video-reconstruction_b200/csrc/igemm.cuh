@@ -98,6 +98,9 @@ struct IgemmParams {
   int shuf_cout;          // pixel-shuffle: channels per quadrant
   const float* bias;      // may be null
   const __nv_bfloat16* mask;  // non-null: out *= (mask > 0); same pixel space as the output
+  int mask_cols;          // the mask applies to output columns < mask_cols only (the skip half of a concat
+                          // gradient is masked later by the pool backward that consumes it)
+  int cs_cols;            // column sums are wanted for columns < cs_cols only
   long long mstride[4];   // mask element stride per tiled dim
   float* out_f32;         // non-null: direct fp32 epilogue (plain mode) instead of the TMA store
   float* colsum_partial;  // non-null: per-(M tile, lane quarter) column sums of the bf16 output,
@@ -519,7 +522,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint4 mreg[8];
       if (tile < total_tiles) {
         tile_setup(tile, org, valid, moff);
-        if (want_mask) mask_fetch(mreg, valid, moff, (tile % p.n_tiles_n) * p.n_tile);
+        if (want_mask && (tile % p.n_tiles_n) * p.n_tile < p.mask_cols)
+          mask_fetch(mreg, valid, moff, (tile % p.n_tiles_n) * p.n_tile);
       }
       while (tile < total_tiles) {
         const int nt = tile % p.n_tiles_n;
@@ -539,7 +543,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (cb + 1 == nblk && ntile_next < total_tiles) tile_setup(ntile_next, org_n, valid_n, moff_n);
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                  static_cast<uint32_t>(acc * p.n_tile + nloc);
-          float* cs_dst = want_cs ? p.colsum_partial + (static_cast<long long>(tile_m) * 4 + quarter) * p.n_total + nglb
+          const bool blk_mask = want_mask && nglb < p.mask_cols;   // warp-uniform
+          const bool blk_cs = want_cs && nglb < p.cs_cols;
+          float* cs_dst = blk_cs ? p.colsum_partial + (static_cast<long long>(tile_m) * 4 + quarter) * p.n_total + nglb
                                   : nullptr;
           // G = 16-column chunks fetched from TMEM per wait: all four when registers allow (plain
           // forward epilogue), two when the ReLU mask / column sums keep more state live
@@ -568,7 +574,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                       if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
                       pk[j] = pack_bf16x2(f0, f1);
                     }
-                    if (want_mask) {
+                    if (blk_mask) {
                       const uint32_t mw[8] = {mreg[2 * ch].x, mreg[2 * ch].y, mreg[2 * ch].z, mreg[2 * ch].w,
                                               mreg[2 * ch + 1].x, mreg[2 * ch + 1].y, mreg[2 * ch + 1].z, mreg[2 * ch + 1].w};
 #pragma unroll
@@ -599,7 +605,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         *reinterpret_cast<uint4*>(pstg + swz_off(pm, ch * 2 + 1, epi_rowb)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                       }
                     }
-                    if (want_cs) {
+                    if (blk_cs) {
                       // column sums of the STORED values over the warp's 32 rows: reduce-scatter
                       float w[16];
 #pragma unroll
@@ -633,8 +639,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           // this block has just finished with: the loads fly during the store hand-off below and the
           // next block's TMEM fetch
           if (want_mask) {
-            if (cb + 1 < nblk) mask_fetch(mreg, valid, moff, nglb + p.cw);
-            else if (ntile_next < total_tiles) mask_fetch(mreg, valid_n, moff_n, (ntile_next % p.n_tiles_n) * p.n_tile);
+            if (cb + 1 < nblk) {
+              if (nglb + p.cw < p.mask_cols) mask_fetch(mreg, valid, moff, nglb + p.cw);
+            } else if (ntile_next < total_tiles) {
+              const int n_next = (ntile_next % p.n_tiles_n) * p.n_tile;
+              if (n_next < p.mask_cols) mask_fetch(mreg, valid_n, moff_n, n_next);
+            }
           }
           if (cb == nblk - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
             tc_fence_before();

@@ -166,7 +166,8 @@ class _LocalNetFunction(torch.autograd.Function):
         # ---- conv7 (its bias gradient came out of the tail kernel) ----
         ops.conv3x3_wgrad(g7, a["cat7"], G["conv7.weight"])
         gcat7 = el(a["cat7"])
-        ops.conv3x3_dgrad(g7, wd("conv7"), gcat7, mask=a["cat7"], colsum=G["upconv3.bias"])
+        # the ReLU mask is only needed on the up-conv half: the skip half (x1) is masked by pool1's backward
+        ops.conv3x3_dgrad(g7, wd("conv7"), gcat7, mask=a["cat7"], mask_cols=64, colsum=G["upconv3.bias"])
         # ---- upconv3 ----
         gu3 = gcat7[..., :64]
         ops.convT2x2_wgrad(gu3, a["y6"], G["upconv3.weight"])
@@ -175,7 +176,7 @@ class _LocalNetFunction(torch.autograd.Function):
         # ---- conv6 ----
         ops.conv3x3_wgrad(g6, a["cat6"], G["conv6.weight"])
         gcat6 = el(a["cat6"])
-        ops.conv3x3_dgrad(g6, wd("conv6"), gcat6, mask=a["cat6"], colsum=G["upconv2.bias"])
+        ops.conv3x3_dgrad(g6, wd("conv6"), gcat6, mask=a["cat6"], mask_cols=128, colsum=G["upconv2.bias"])
         # ---- upconv2 ----
         gu2 = gcat6[..., :128]
         ops.convT2x2_wgrad(gu2, a["y5"], G["upconv2.weight"])
@@ -184,7 +185,7 @@ class _LocalNetFunction(torch.autograd.Function):
         # ---- conv5 ----
         ops.conv3x3_wgrad(g5, a["cat5"], G["conv5.weight"])
         gcat5 = el(a["cat5"])
-        ops.conv3x3_dgrad(g5, wd("conv5"), gcat5, mask=a["cat5"], colsum=G["upconv1.bias"])
+        ops.conv3x3_dgrad(g5, wd("conv5"), gcat5, mask=a["cat5"], mask_cols=256, colsum=G["upconv1.bias"])
         # ---- upconv1 ----
         gu1 = gcat5[..., :256]
         ops.convT2x2_wgrad(gu1, a["x4"], G["upconv1.weight"])

@@ -168,8 +168,9 @@ def _colsum_ws(colsum, B, H, W, C, device):
     return _ptr(colsum), colsum.numel(), _ptr(ws), ws.numel()
 
 
-def conv3x3_dgrad(dy, wk_d, dx, mask=None, colsum=None):
-    """dx = conv^T(dy) [* (mask > 0)]; colsum (fp32 [Cin]) optionally receives sum_pixels dx."""
+def conv3x3_dgrad(dy, wk_d, dx, mask=None, colsum=None, mask_cols=0):
+    """dx = conv^T(dy) [* (mask > 0) on the first mask_cols channels (0 = all)]; colsum (fp32, up to Cin
+    entries) optionally receives sum_pixels dx of its leading channels."""
     B, H, W, Cout, dy_ld = _act(dy, "dy")
     Bx, Hx, Wx, Cin, dx_ld = _act(dx, "dx")
     assert (B, H, W) == (Bx, Hx, Wx) and wk_d.shape == (Cin, 9 * Cout), (dy.shape, dx.shape, wk_d.shape)
@@ -178,7 +179,7 @@ def conv3x3_dgrad(dy, wk_d, dx, mask=None, colsum=None):
         Bm, Hm, Wm, Cm, mask_ld = _act(mask, "mask")
         assert (Bm, Hm, Wm, Cm) == (B, H, W, Cin)
     cs, ncs, ws, wsn = _colsum_ws(colsum, B, H, W, Cin, dy.device)
-    _launch("rovr_conv3x3_dgrad", _ptr(dy), dy_ld, _ptr(wk_d), _ptr(dx), dx_ld, _ptr(mask), mask_ld,
+    _launch("rovr_conv3x3_dgrad", _ptr(dy), dy_ld, _ptr(wk_d), _ptr(dx), dx_ld, _ptr(mask), mask_ld, mask_cols,
            B, H, W, Cin, Cout, cs, ncs, ws, wsn, _stream())
     return dx
 

@@ -132,6 +132,15 @@ def test_conv3x3_dgrad(B, H, W, Cin, Cout):
     ops.conv3x3_dgrad(dy, wd, dx, mask=xmask, colsum=half)
     torch.cuda.synchronize()
     _report("conv3x3_dgrad.colsum[:half]", half, dx.float().sum(dim=(0, 1, 2))[: Cin // 2], 1e-3)
+    if Cin % 128 == 0:
+        # mask only the first half of the channels (U-Net concat gradient: the skip half is masked later)
+        dxh = torch.empty_like(dx)
+        ops.conv3x3_dgrad(dy, wd, dxh, mask=xmask, mask_cols=Cin // 2, colsum=half)
+        torch.cuda.synchronize()
+        m = _nchw(xmask) > 0
+        m[:, Cin // 2:] = True
+        _report("conv3x3_dgrad.mask_cols", _nchw(dxh), F.conv_transpose2d(_nchw(dy), w.to(BF).float(), padding=1) * m, 1e-2)
+        _report("conv3x3_dgrad.mask_cols.colsum", half, dxh.float().sum(dim=(0, 1, 2))[: Cin // 2], 1e-3)
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", CONV_SHAPES)
