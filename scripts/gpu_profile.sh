@@ -2,7 +2,7 @@
 # ncu evidence for the current build: launch list of one bench run + full-set capture of every
 # igemm launch of one step. Output in gpurun_out/ (copy summaries into profiles/).
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --profile-run"
+CMD="python bench.py --steps 2 --warmup 3 --profile-run --no-graph"
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 echo "launch list rc=$?"
