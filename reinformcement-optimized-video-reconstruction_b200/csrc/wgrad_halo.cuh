@@ -153,6 +153,9 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t a_step = static_cast<uint32_t>(16 * sw_a) >> 4;             // 16 rows
     const uint32_t b_step = static_cast<uint32_t>(2 * WH_HALO * sw_b) >> 4;    // 2 image rows
     const uint32_t row16 = static_cast<uint32_t>(sw_b) >> 4;
+    const bool merge3 = p.c_blocks_per_group == 1 && p.tap_sign == 1 && (t_first % 3) == 0 && 3 * ncol <= 256;
+    const uint32_t idesc3 = umma_idesc_bf16(128, 3 * ncol, 1, 1);
+    const uint32_t b_lbo_row = row16 << 16;   // LBO = one halo pixel row
     // The tap loop is unrolled at compile time (TC taps per CTA) with the per-tap operand offsets
     // precomputed: with 16-channel operands an MMA retires faster than a generic loop iteration
     // issues, and this single warp's instruction stream is what bounds the kernel.
@@ -176,10 +179,20 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
         const uint32_t a16 = base16 + static_cast<uint32_t>(s) * stage16;
         const uint32_t b16 = a16 + (a_bytes >> 4);
+        if (TC % 3 == 0 && merge3) {
+          // the three dx taps of one kernel row are the same halo view shifted by one pixel row each:
+          // with the leading-dimension offset set to ONE ROW they become three N blocks of a single
+          // MMA (N = 3 * ncol) — a third of the MMA instructions for the thin (16 / 32-channel) operands
 #pragma unroll
-        for (int tl = 0; tl < TC; ++tl)
-          umma_mn_x4(tmem_base + static_cast<uint32_t>(tl * ncol), a_lbo | a16, a_hi, a_step, tap_b[tl] + b16, b_hi,
-                     b_step, idesc, accum);
+          for (int r = 0; r < TC / 3; ++r)
+            umma_mn_x4(tmem_base + static_cast<uint32_t>(3 * r * ncol), a_lbo | a16, a_hi, a_step,
+                       (tap_b[3 * r] & 0xFFFFu) + b_lbo_row + b16, b_hi, b_step, idesc3, accum);
+        } else {
+#pragma unroll
+          for (int tl = 0; tl < TC; ++tl)
+            umma_mn_x4(tmem_base + static_cast<uint32_t>(tl * ncol), a_lbo | a16, a_hi, a_step, tap_b[tl] + b16, b_hi,
+                       b_step, idesc, accum);
+        }
         accum = 1u;
         umma_commit_elect(&empty_bar[s]);
         __syncwarp();
