@@ -94,6 +94,8 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int kt1 = static_cast<int>((static_cast<long long>(p.k_tiles) * (slice + 1)) / p.n_slices);
   const int t_first = p.taps_first[tg], t_count = p.taps_count[tg];
   const int ncol = p.c_blocks_per_group * p.blk_b;  // columns per tap
+  // whole kernel rows of a single-block operand: the three dx taps of a row run as one MMA (see below)
+  const bool merge3 = p.c_blocks_per_group == 1 && (t_first % 3) == 0 && (t_count % 3) == 0 && 3 * ncol <= 256;
 
   // A blocks that are never loaded (m_total < 128) must read as zero
   {
@@ -153,7 +155,6 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t a_step = static_cast<uint32_t>(16 * sw_a) >> 4;             // 16 rows
     const uint32_t b_step = static_cast<uint32_t>(2 * WH_HALO * sw_b) >> 4;    // 2 image rows
     const uint32_t row16 = static_cast<uint32_t>(sw_b) >> 4;
-    const bool merge3 = p.c_blocks_per_group == 1 && p.tap_sign == 1 && (t_first % 3) == 0 && 3 * ncol <= 256;
     const uint32_t idesc3 = umma_idesc_bf16(128, 3 * ncol, 1, 1);
     const uint32_t b_lbo_row = row16 << 16;   // LBO = one halo pixel row
     // The tap loop is unrolled at compile time (TC taps per CTA) with the per-tap operand offsets
@@ -184,9 +185,12 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // with the leading-dimension offset set to ONE ROW they become three N blocks of a single
           // MMA (N = 3 * ncol) — a third of the MMA instructions for the thin (16 / 32-channel) operands
 #pragma unroll
+          // (operand swap reads the halo at p - (dy, dx): the tap with dx = 0 is then the LAST of its
+          // row, and the N blocks come out in reversed tap order — the epilogue undoes that)
           for (int r = 0; r < TC / 3; ++r)
             umma_mn_x4(tmem_base + static_cast<uint32_t>(3 * r * ncol), a_lbo | a16, a_hi, a_step,
-                       (tap_b[3 * r] & 0xFFFFu) + b_lbo_row + b16, b_hi, b_step, idesc3, accum);
+                       (tap_b[p.tap_sign == 1 ? 3 * r : 3 * r + 2] & 0xFFFFu) + b_lbo_row + b16, b_hi, b_step, idesc3,
+                       accum);
         } else {
 #pragma unroll
           for (int tl = 0; tl < TC; ++tl)
@@ -228,8 +232,9 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int j = 0; j < 16; ++j) v[j] = 0u;
       }
       const int col = c * 16;
-      const int tl = col / ncol;
+      int tl = col / ncol;
       const int cc = cg * ncol + (col - tl * ncol);
+      if (merge3 && p.tap_sign != 1) tl = 3 * (tl / 3) + (2 - tl % 3);
       const int t = t_first + tl;
       if (m < p.m_total && cc < p.c_total) {
         float4* dst = reinterpret_cast<float4*>(
