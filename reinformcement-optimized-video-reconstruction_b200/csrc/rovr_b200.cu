@@ -150,9 +150,15 @@ static int make_map5(CUtensorMap* m, const void* base, const long long dims[5],
     ROVR_REQUIRE((gs[i] & 15u) == 0 && gs[i] > 0, "tensor stride %d (%llu B) not a multiple of 16",
                  i, static_cast<unsigned long long>(gs[i]));
   ROVR_REQUIRE(box[0] * 2 == sw_bytes, "inner box (%d elems) must equal the swizzle span", box[0]);
+  // A map over a <= 64-channel SLICE of a wider pixel (e.g. the up-conv half of a concat gradient)
+  // only ever touches 128 of every 256+ bytes: promoting its misses to 256 B would drag the unused
+  // half through DRAM (ncu: upconv3 dgrad read 502 MB for 301 MB of operands). Everything else is
+  // read in full, where 256 B promotion prefetches the neighbouring chunk / pixel.
+  const bool narrow_slice = dims[0] * 2 <= 128 && strides_elems[0] > dims[0];
   CUresult r = g_dev.encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gd, gs,
                             bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(sw_bytes),
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            narrow_slice ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(-5,
                 "cuTensorMapEncodeTiled(5d) failed rc=%d dims=[%lld,%lld,%lld,%lld,%lld] "
