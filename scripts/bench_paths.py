@@ -33,10 +33,17 @@ def timeit(fn, iters=20, warm=3):
     return e0.elapsed_time(e1) / iters, (_native.lib.rovr_launch_count() - n0) / iters
 
 
-def report(name, ms, launches, units, unit, gflop_per_unit):
+def report(name, ms, launches, units, unit, gflop_per_unit, fn=None, inputs=None, modules=()):
     rate = units / (ms * 1e-3)
-    print(json.dumps({"path": name, "ms": round(ms, 3), "launches": launches, "rate": round(rate, 1), "unit": unit,
-                      "tflops": round(rate * gflop_per_unit / 1e3, 2)}), flush=True)
+    line = {"path": name, "ms": round(ms, 3), "launches": launches, "rate": round(rate, 1), "unit": unit,
+            "tflops": round(rate * gflop_per_unit / 1e3, 2)}
+    if fn is not None:      # the same step captured into one CUDA graph (graphs.GraphedFunction)
+        from graphs import GraphedFunction
+        g = GraphedFunction(fn, inputs, modules=modules)
+        gms, _ = timeit(lambda: g(*inputs))
+        line.update({"graph_ms": round(gms, 3), "graph_rate": round(units / (gms * 1e-3), 1),
+                     "graph_tflops": round(units / (gms * 1e-3) * gflop_per_unit / 1e3, 2)})
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -54,7 +61,11 @@ def main():
         pn1.zero_grad(set_to_none=True)
         pn1.logprob(img, ctx, act).sum().backward()
     ms, l = timeit(f_pn1)
-    report("PN1 logprob fwd+bwd b=25 80x80", ms, l, 25, "samples/s", 2.960)
+
+    def g_pn1(i, c, a):
+        pn1.logprob(i, c, a).sum().backward()
+    pn1.zero_grad(set_to_none=True)
+    report("PN1 logprob fwd+bwd b=25 80x80", ms, l, 25, "samples/s", 2.960, g_pn1, (img, ctx, act), [pn1])
 
     pn2 = PolicyNetwork2UNet().to(dev).train()
     enc, feat = torch.rand(20, 1, 160, 160, device=dev), torch.randn(20, 1, 1024, device=dev)
@@ -64,7 +75,11 @@ def main():
         pn2.zero_grad(set_to_none=True)
         (pn2(enc, feat, tgt, extra=True) ** 2).sum().backward()
     ms, l = timeit(f_pn2)
-    report("PN2 IL logits fwd+bwd b=20 160x160", ms, l, 20, "samples/s", 0.503)
+
+    def g_pn2(e, f, t):
+        (pn2(e, f, t, extra=True) ** 2).sum().backward()
+    pn2.zero_grad(set_to_none=True)
+    report("PN2 IL logits fwd+bwd b=20 160x160", ms, l, 20, "samples/s", 0.503, g_pn2, (enc, feat, tgt), [pn2])
     for k in (8, 64):
         b = 20 * k
         encb, featb = torch.rand(b, 1, 160, 160, device=dev), torch.randn(b, 1, 1024, device=dev)
@@ -86,7 +101,11 @@ def main():
         rn.zero_grad(set_to_none=True)
         (rn(frames) ** 2).sum().backward()
     ms, l = timeit(f_rn, iters=10)
-    report("ResNet-50 extractor fwd (+linear bwd) 25 frames 224x224", ms, l, 25, "frames/s", 8.174)
+
+    def g_rn(fr):
+        (rn(fr) ** 2).sum().backward()
+    rn.zero_grad(set_to_none=True)
+    report("ResNet-50 extractor fwd (+linear bwd) 25 frames 224x224", ms, l, 25, "frames/s", 8.174, g_rn, (frames,), [rn])
 
     E, S, B = 3072, 256, 8
     blk = EncoderBlock(E, 8, 0.0).to(dev).eval()
@@ -96,7 +115,12 @@ def main():
         blk.zero_grad(set_to_none=True)
         (blk(x) ** 2).sum().backward()
     ms, l = timeit(f_enc, iters=10)
-    report("EncoderBlock fwd+bwd E=3072 S=256 B=8 heads=8", ms, l, B, "sequences/s", 3 * (20.13 + 2.42))
+
+    def g_enc(xx):
+        (blk(xx) ** 2).sum().backward()
+    blk.zero_grad(set_to_none=True)
+    x.grad = None
+    report("EncoderBlock fwd+bwd E=3072 S=256 B=8 heads=8", ms, l, B, "sequences/s", 3 * (20.13 + 2.42), g_enc, (x,), [blk])
 
 
 if __name__ == "__main__":

@@ -538,3 +538,43 @@ def test_action_lstm_matches_reference(golden_dir):
         _close(f"lstm.grad.{n}", p.grad, leaf[n].grad, 1e-3)
     m.reset_hidden_states()
     assert float(m.hx.abs().sum()) == 0.0
+
+
+def test_graphed_function_matches_eager():
+    """graphs.GraphedFunction: the PN2 imitation-learning step replayed from a CUDA graph gives the
+    eager logits and gradients bit for bit, for the captured inputs and for new ones."""
+    import policy_net_2 as M
+    from graphs import GraphedFunction
+    dev = _dev()
+    sd = O.pn2_state_dict(0, False)
+    net = M.PolicyNetwork2UNet(is_critic=False)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).train()
+    enc, feat, target, _ = _pn2_inputs(20, 21)
+    enc2, feat2, target2, _ = _pn2_inputs(20, 22)
+
+    def eager(e, f, t):
+        net.zero_grad(set_to_none=True)
+        out = net(e.to(dev), f.to(dev), t.to(dev), extra=True)
+        (out ** 2).sum().backward()
+        return out.detach().clone(), {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+
+    o1, g1 = eager(enc, feat, target)
+    o2, g2 = eager(enc2, feat2, target2)
+    net.zero_grad(set_to_none=True)
+    box = {}
+
+    def fn(e, f, t):
+        box["out"] = net(e, f, t, extra=True)
+        (box["out"] ** 2).sum().backward()
+        return box["out"]
+
+    step = GraphedFunction(fn, (enc.to(dev), feat.to(dev), target.to(dev)), modules=[net])
+    assert step.launches > 40
+    for (e, f, t), (o_ref, g_ref) in (((enc, feat, target), (o1, g1)), ((enc2, feat2, target2), (o2, g2))):
+        out = step(e.to(dev), f.to(dev), t.to(dev))
+        torch.cuda.synchronize()
+        assert torch.equal(out.detach(), o_ref)
+        for n, p in net.named_parameters():
+            if n in g_ref:
+                assert torch.equal(p.grad, g_ref[n]), n
