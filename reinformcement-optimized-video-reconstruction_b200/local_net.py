@@ -299,15 +299,15 @@ class GraphedTrainingStep:
         loss = step(frame, context, target)                         # copies into the static inputs, replays
         # net.<param>.grad now hold this step's gradients (static tensors, overwritten by every replay)
 
-    The bf16 operand copies of the weights are re-packed inside the graph when
-    `repack_weights=True` (training: the optimizer changes the fp32 masters every step); with
-    False they are packed once before capture (inference-style benchmarking with fixed weights).
+    The bf16 operand copies of the weights are re-packed inside the graph (`repack_weights=True`, the
+    default: a training loop's optimizer changes the fp32 masters every step, 19 small kernels);
+    with False they are packed once before capture — only valid while the weights never change.
     With data_parallel.GradientBuckets installed, the graph holds the compute only and the two
     flat gradient buckets are all-reduced right after each replay (15 MB over NVLink, ~0.1 ms; the
     backward/all-reduce overlap of the eager path is traded for the removal of ~65 launch gaps).
     """
 
-    def __init__(self, net, x, context, target, repack_weights=False, warmup=2):
+    def __init__(self, net, x, context, target, repack_weights=True, warmup=2):
         self.net = net
         self._hooks = (net._grad_bucket_hook, net._grad_bucket_wait, getattr(net, "_grad_bucket_reduce", None))
         net._grad_bucket_hook = net._grad_bucket_wait = None     # capture compute only
