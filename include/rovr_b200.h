@@ -68,6 +68,14 @@ int rovr_conv3x3_fprop(const void* x, int x_ld, const void* wk, const float* bia
 int rovr_conv3x3_fprop_pool2(const void* x, int x_ld, const void* wk, const float* bias, void* y, int y_ld,
                              void* pooled, int pooled_ld, int B, int H, int W, int Cin, int Cout, int relu,
                              void* stream);
+/* conv7 + ReLU with the LocalNet tail fused into its epilogue: out = sigmoid(conv8_1x1(y)) (NCHW fp32
+ * [B][3][H][W]) and, if target != NULL, *loss = mean((out - target)^2) — rovr/local_net.py:68,71 and
+ * nn.MSELoss of rovr/train_local_net_unet.py:90,107 without a second pass over y. Cout must be 64.
+ * ws >= rovr_conv3x3_fprop_tail_workspace(B, H, W) when a loss is requested. */
+size_t rovr_conv3x3_fprop_tail_workspace(int B, int H, int W);
+int rovr_conv3x3_fprop_tail(const void* x, int x_ld, const void* wk, const float* bias, void* y, int y_ld,
+                            const float* w8, const float* b8, float* out, const float* target, float* loss,
+                            void* ws, size_t ws_bytes, int B, int H, int W, int Cin, int Cout, void* stream);
 /* dx = conv3x3^T(dy); if mask != NULL, dx[..., c] *= (mask[..., c] > 0) for c < mask_cols (ReLU of the
  * producer of x; mask_cols <= 0 means all Cin channels — the skip half of a U-Net concat gradient is
  * masked by the pool backward that consumes it, so only the up-conv half needs it here).

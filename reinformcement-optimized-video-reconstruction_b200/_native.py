@@ -41,6 +41,8 @@ SIGNATURES = {
     "rovr_gemm_wgrad": (_i, [_p, _i, _p, _i, _p, _ll, _i, _i, _i, _i, _p, _sz, _p]),
     "rovr_conv3x3_fprop": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "rovr_conv3x3_fprop_pool2": (_i, [_p, _i, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_conv3x3_fprop_tail_workspace": (_sz, [_i, _i, _i]),
+    "rovr_conv3x3_fprop_tail": (_i, [_p, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _i, _i, _p]),
     "rovr_dgrad_colsum_workspace": (_sz, [_i, _i, _i, _i]),
     "rovr_conv3x3_dgrad": (_i, [_p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _sz, _p]),
     "rovr_conv3x3_wgrad_workspace": (_sz, [_i, _i, _i, _i, _i]),

@@ -87,6 +87,15 @@ struct IgemmParams {
   int has_mask;
   int pool2;              // 1 (halo mode, plain epilogue): also emit the 2x2 max-pooled tile (4 x 8 pixels) through
                           //    the fourth tensor map — nn.MaxPool2d(2, 2) of the encoder fused into the conv
+  // Fused LocalNet tail (conv7 forward only: n_tile == cw == 64): out[b][k][pixel] = sigmoid(b8[k] +
+  // sum_c w8[k][c] * y[pixel][c]) for k < 3, computed by the thread that owns the pixel row from the
+  // bf16-rounded values it stores, plus (optional) per-(tile, warp) partial sums of (out - target)^2.
+  const float* tail_w;    // [3][64] fp32 (Conv2d 1x1 weight), null = no tail
+  const float* tail_b;    // [3]
+  float* tail_out;        // NCHW fp32 [B][3][H][W]
+  const float* tail_target;   // may be null
+  float* tail_loss_partial;   // [m_tiles * 4], may be null
+  long long tail_plane;   // H * W
   int b_batched;          // 1: the B operand is a rank-5 map (K, N, d2, d3, d4) whose trailing coordinates are
                           //    the tile's M-space origin org[1..3] (batched GEMM: one B matrix per head / batch)
   int halo;               // 1: Conv2d 3x3 with the input patch loaded once per k-chunk (see below)
@@ -183,6 +192,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* wfull_bar = aempty_bar + IG_MAX_ASLOTS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
   float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
+  float4* stail = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(sbias + p.n_total) + 15) & ~uintptr_t(15));
 
   const int m_tiles = p.ntile[0] * p.ntile[1] * p.ntile[2] * p.ntile[3];
   const int total_tiles = m_tiles * p.n_tiles_n;
@@ -214,6 +224,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == IG_WARP_MMA) tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
   for (int i = threadIdx.x; i < p.n_total; i += IG_THREADS)
     sbias[i] = p.bias ? p.bias[i % p.bias_mod] : 0.f;
+  if (p.tail_w != nullptr && threadIdx.x < 64)   // w8 transposed to [c][k] so that one 16-byte read serves a column
+    stail[threadIdx.x] = make_float4(p.tail_w[threadIdx.x], p.tail_w[64 + threadIdx.x], p.tail_w[128 + threadIdx.x], 0.f);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -492,6 +504,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool want_cs = !kPlainEpi && p.colsum_partial != nullptr;
       const bool want_mask = !kPlainEpi && p.mask != nullptr;
       const bool has_bias = p.bias != nullptr;
+      const bool want_tail = kPlainEpi && p.tail_w != nullptr;
+      float tail_bias[3] = {0.f, 0.f, 0.f};
+      if (want_tail) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tail_bias[k] = __ldg(p.tail_b + k);
+      }
       // tile geometry: origin, validity of this thread's row, its mask row offset
       auto tile_setup = [&](int tile, int* org, bool& valid, long long& moff) {
         int mt = tile / p.n_tiles_n;
@@ -532,6 +550,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         int org_n[4] = {0, 0, 0, 0};
         bool valid_n = false;
         long long moff_n = 0;
+        // fused tail: this pixel's three target values, requested before the accumulator wait so that
+        // their DRAM latency hides behind it and the conversion
+        float ttgt[3] = {0.f, 0.f, 0.f};
+        if (want_tail && p.tail_target != nullptr && valid) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) ttgt[k] = __ldg(p.tail_target + moff + k * p.tail_plane);
+        }
         mbar_wait(&tfull_bar[acc], aph, 0x400u + acc);
         tc_fence_after();
         for (int cb = 0; cb < nblk; ++cb) {
@@ -549,6 +574,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                   : nullptr;
           // G = 16-column chunks fetched from TMEM per wait: all four when registers allow (plain
           // forward epilogue), two when the ReLU mask / column sums keep more state live
+          float tz[3] = {0.f, 0.f, 0.f};   // fused tail: conv8 pre-activations of this thread's pixel
           auto convert = [&](auto g_tag) {
             constexpr int G = decltype(g_tag)::value;
 #pragma unroll
@@ -586,6 +612,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     }
                     *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2, epi_rowb)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2 + 1, epi_rowb)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    if (kPlainEpi && want_tail) {
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) {
+                        const float4 w0 = stail[ch * 16 + 2 * j], w1 = stail[ch * 16 + 2 * j + 1];
+                        const float v0 = bf16_lo(pk[j]), v1 = bf16_hi(pk[j]);
+                        tz[0] = fmaf(v0, w0.x, tz[0]); tz[1] = fmaf(v0, w0.y, tz[1]); tz[2] = fmaf(v0, w0.z, tz[2]);
+                        tz[0] = fmaf(v1, w1.x, tz[0]); tz[1] = fmaf(v1, w1.y, tz[1]); tz[2] = fmaf(v1, w1.z, tz[2]);
+                      }
+                    }
                     if (kPlainEpi && p.pool2) {
 #pragma unroll
                       for (int j = 0; j < 8; ++j) {
@@ -635,6 +670,28 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           };
           convert(std::integral_constant<int, 4>{});
+          if (want_tail) {
+            // moff = b * 3 * plane + y * W + x (mstride set by the host); three planes per image
+            float se = 0.f;
+            if (valid) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                const float z = tz[k] + tail_bias[k];
+                const float yv = 1.f / (1.f + expf(-z));
+                const long long o = moff + k * p.tail_plane;
+                p.tail_out[o] = yv;
+                if (p.tail_target != nullptr) {
+                  const float d = yv - ttgt[k];
+                  se = fmaf(d, d, se);
+                }
+              }
+            }
+            if (p.tail_loss_partial != nullptr) {
+#pragma unroll
+              for (int o2 = 16; o2 > 0; o2 >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o2);
+              if (lane == 0) p.tail_loss_partial[static_cast<long long>(tile_m) * 4 + quarter] = se;
+            }
+          }
           // mask of the NEXT column block (possibly of the next tile), straight into the registers
           // this block has just finished with: the loads fly during the store hand-off below and the
           // next block's TMEM fetch
@@ -692,7 +749,7 @@ inline size_t igemm_fixed_smem(int cw, int pool2, int n_total, int a_slots = 0, 
   const size_t stg = 128 * static_cast<size_t>(cw) * 2 + (pool2 ? 32 * static_cast<size_t>(cw) * 2 : 0);
   return 2048 + static_cast<size_t>(a_slots) * ig_halo_slot(sw) + 2 * stg +
          (2 * IG_MAX_STAGES + 2 * IG_MAX_ASLOTS + 7) * 8 + 16 +
-         static_cast<size_t>(n_total) * 4 + 64;
+         static_cast<size_t>(n_total) * 4 + 64 + 64 * 16 + 16;
 }
 inline size_t igemm_stage_bytes(int bk, int n_tile, int tps) {
   return (128 + static_cast<size_t>(n_tile)) * bk * 2 * tps;

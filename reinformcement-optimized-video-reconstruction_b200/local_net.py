@@ -119,9 +119,10 @@ class _LocalNetFunction(torch.autograd.Function):
         ops.conv3x3_fprop(a["cat6"], wk("conv6"), P["conv6.bias"], a["y6"])
         ops.convT2x2_fprop(a["y6"], wk("upconv3", "up"), P["upconv3.bias"], a["cat7"][..., :64])
         a["y7"] = torch.empty((B, H, W, 64), dtype=bf, device=dev)
-        ops.conv3x3_fprop(a["cat7"], wk("conv7"), P["conv7.bias"], a["y7"])
-
-        out, loss = ops.tail_fwd(a["y7"], P["conv8.weight"], P["conv8.bias"], target)
+        # conv7 + ReLU + conv8 (1x1) + sigmoid (+ L2 loss) in one kernel: the conv7 epilogue thread owns
+        # a whole pixel of y7, so the 64 -> 3 projection needs no second pass over it
+        out, loss = ops.conv3x3_fprop_tail(a["cat7"], wk("conv7"), P["conv7.bias"], a["y7"], P["conv8.weight"],
+                                           P["conv8.bias"], target)
         a["out"] = out
         ctx.net = net
         ctx.acts = a

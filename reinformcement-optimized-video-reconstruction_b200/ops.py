@@ -159,6 +159,30 @@ def conv3x3_fprop(x, wk, bias, y, relu=True, pooled=None):
     return y
 
 
+def conv3x3_fprop_tail(x, wk, bias, y, w8, b8, target=None):
+    """y = relu(conv3x3(x) + bias) (Cout = 64) and, from the same epilogue, out = sigmoid(conv8_1x1(y))
+    (NCHW fp32) [+ mean((out - target)^2)]. Returns (out, loss | None)."""
+    B, H, W, Cin, x_ld = _act(x, "x")
+    By, Hy, Wy, Cout, y_ld = _act(y, "y")
+    assert (B, H, W) == (By, Hy, Wy) and Cout == 64 and wk.shape == (Cout, 9 * Cin)
+    _f32(bias, "bias")
+    w8 = w8.reshape(3, 64)
+    _f32(w8, "w8")
+    _f32(b8, "b8")
+    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=x.device)
+    loss = None
+    ws, wsn = _vp(0), 0
+    if target is not None:
+        _f32(target, "target")
+        assert target.shape == out.shape
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        wbuf = workspace(N.lib.rovr_conv3x3_fprop_tail_workspace(B, H, W), x.device)
+        ws, wsn = _ptr(wbuf), wbuf.numel()
+    _launch("rovr_conv3x3_fprop_tail", _ptr(x), x_ld, _ptr(wk), _ptr(bias), _ptr(y), y_ld, _ptr(w8), _ptr(b8),
+            _ptr(out), _ptr(target), _ptr(loss), ws, wsn, B, H, W, Cin, Cout, _stream())
+    return out, loss
+
+
 def _colsum_ws(colsum, B, H, W, C, device):
     if colsum is None:
         return _vp(0), 0, _vp(0), 0

@@ -111,6 +111,36 @@ def test_conv3x3_fprop_fused_pool(B, H, W, Cin, Cout):
     assert (ybuf[..., :8] == 7.0).all() and (ybuf[..., 8 + Cout:] == 7.0).all()
 
 
+@pytest.mark.parametrize("B,H,W,Cin", [(2, 16, 16, 128), (1, 32, 24, 64), (3, 20, 12, 128), (5, 8, 8, 128), (1, 64, 64, 128)])
+def test_conv3x3_fprop_fused_tail(B, H, W, Cin):
+    """conv7 + ReLU + conv8 (1x1, 64 -> 3) + sigmoid + L2 loss from one kernel equals the conv kernel
+    followed by the stand-alone tail kernel (same bf16-rounded y)."""
+    import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 13 + H + Cin)
+    x = _rand_act((B, H, W, Cin), g, dev)
+    w = (torch.randn((64, Cin, 3, 3), generator=g) * (1.0 / (3 * Cin ** 0.5))).to(dev)
+    b = torch.randn((64,), generator=g).to(dev) * 0.1
+    w8 = (torch.randn((3, 64, 1, 1), generator=g) * 0.2).to(dev)
+    b8 = torch.randn((3,), generator=g).to(dev) * 0.1
+    tgt = torch.rand((B, 3, H, W), generator=g).to(dev)
+    wk = ops.repack_conv3x3(w)
+    y1 = torch.empty((B, H, W, 64), dtype=BF, device=dev)
+    out1, loss1 = ops.conv3x3_fprop_tail(x, wk, b, y1, w8, b8, tgt)
+    y2 = torch.empty((B, H, W, 64), dtype=BF, device=dev)
+    ops.conv3x3_fprop(x, wk, b, y2, relu=True)
+    out2, loss2 = ops.tail_fwd(y2, w8, b8, tgt)
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2)
+    ref = torch.sigmoid(F.conv2d(_nchw(y2), w8, b8))
+    _report("fused_tail.out", out1, ref, 1e-5)
+    _report("fused_tail.out vs tail kernel", out1, out2, 1e-5)
+    assert abs(loss1.item() - F.mse_loss(ref, tgt).item()) < 1e-5 * max(1.0, loss2.item())
+    out3, loss3 = ops.conv3x3_fprop_tail(x, wk, b, y1, w8, b8, None)
+    torch.cuda.synchronize()
+    assert loss3 is None and torch.equal(out3, out1)
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout", CONV_SHAPES)
 def test_conv3x3_dgrad(B, H, W, Cin, Cout):
     import ops
