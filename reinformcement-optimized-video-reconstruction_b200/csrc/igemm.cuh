@@ -150,7 +150,9 @@ __device__ __forceinline__ uint32_t swz_off(int m, int j, int rowb) {
 
 // kPlainEpi: the epilogue has neither a ReLU mask nor fused column sums (every forward launch):
 // their register state disappears and all four 16-column TMEM chunks of a block are fetched at once.
-template <bool kPlainEpi>
+// kTail: the fused LocalNet tail (conv7 forward only) — its own instance so that the plain one
+// keeps its 130-register epilogue.
+template <bool kPlainEpi, bool kTail = false>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmMask,
@@ -224,7 +226,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == IG_WARP_MMA) tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
   for (int i = threadIdx.x; i < p.n_total; i += IG_THREADS)
     sbias[i] = p.bias ? p.bias[i % p.bias_mod] : 0.f;
-  if (p.tail_w != nullptr && threadIdx.x < 64)   // w8 transposed to [c][k] so that one 16-byte read serves a column
+  if (kTail && threadIdx.x < 64)   // w8 transposed to [c][k] so that one 16-byte read serves a column
     stail[threadIdx.x] = make_float4(p.tail_w[threadIdx.x], p.tail_w[64 + threadIdx.x], p.tail_w[128 + threadIdx.x], 0.f);
   tc_fence_before();
   __syncthreads();
@@ -504,7 +506,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool want_cs = !kPlainEpi && p.colsum_partial != nullptr;
       const bool want_mask = !kPlainEpi && p.mask != nullptr;
       const bool has_bias = p.bias != nullptr;
-      const bool want_tail = kPlainEpi && p.tail_w != nullptr;
+      constexpr bool want_tail = kPlainEpi && kTail;
       float tail_bias[3] = {0.f, 0.f, 0.f};
       if (want_tail) {
 #pragma unroll
@@ -597,8 +599,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         f0 += sbias[nglb + ch * 16 + 2 * j];
                         f1 += sbias[nglb + ch * 16 + 2 * j + 1];
                       }
-                      if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
-                      pk[j] = pack_bf16x2(f0, f1);
+                      pk[j] = p.relu ? pack_bf16x2_relu(f0, f1) : pack_bf16x2(f0, f1);
                     }
                     if (blk_mask) {
                       const uint32_t mw[8] = {mreg[2 * ch].x, mreg[2 * ch].y, mreg[2 * ch].z, mreg[2 * ch].w,
@@ -612,7 +613,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     }
                     *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2, epi_rowb)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2 + 1, epi_rowb)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                    if (kPlainEpi && want_tail) {
+                    if constexpr (want_tail) {
 #pragma unroll
                       for (int j = 0; j < 8; ++j) {
                         const float4 w0 = stail[ch * 16 + 2 * j], w1 = stail[ch * 16 + 2 * j + 1];
