@@ -165,6 +165,16 @@ int rovr_bn_train_bwd(const void* dy, int dy_ld, const void* y, int y_ld, const 
                       const float* mean, const float* rstd, float* dgamma, float* dbeta, int relu,
                       void* ws, size_t ws_bytes, void* stream);
 
+/* eval mode (module.eval()): running statistics, buffers untouched. rstd (fp32 [C]) is produced for the
+ * backward pass, whose statistics are constants: dx = gamma * rstd * dy * (y > 0). */
+int rovr_bn_eval_fwd(const void* x, int x_ld, void* y, int y_ld, long long npix, int C, int c_valid,
+                     const float* gamma, const float* beta, float eps, const float* running_mean,
+                     const float* running_var, float* rstd, int relu, void* stream);
+int rovr_bn_eval_bwd(const void* dy, int dy_ld, const void* y, int y_ld, const void* x, int x_ld, void* dx,
+                     int dx_ld, long long npix, int C, int c_valid, const float* gamma,
+                     const float* running_mean, const float* rstd, float* dgamma, float* dbeta, int relu,
+                     void* ws, size_t ws_bytes, void* stream);
+
 /* ---- LayerNorm over the last dim of fp32 rows [rows][E] ---------------------------------------
  * nn.LayerNorm: rovr/common_layers.py:59,63,71-72,75-76,86,90. y_f32 and / or y_bf16 may be NULL. */
 int rovr_layernorm_fwd(const float* x, long long rows, int E, float eps, const float* gamma,

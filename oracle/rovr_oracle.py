@@ -203,9 +203,27 @@ def localnet_step(sd, x, context, target):
 # ------------------------------------------------------------------------------------------------
 # Policy network 1
 # ------------------------------------------------------------------------------------------------
+_BN_EVAL = False   # set by `bn_eval_mode()`: evaluate BatchNorm with the running statistics (module.eval())
+
+
+class bn_eval_mode:
+    """Context manager: the policy-network oracles use eval-mode BatchNorm inside it."""
+
+    def __enter__(self):
+        global _BN_EVAL
+        self.prev, _BN_EVAL = _BN_EVAL, True
+
+    def __exit__(self, *exc):
+        global _BN_EVAL
+        _BN_EVAL = self.prev
+
+
 def _bn_train(sd, name, t, eps=1e-5):
     """Train-mode BatchNorm2d (batch statistics, biased variance for normalisation). Running-stat
-    updates are returned by pn*_running_stats, not applied here."""
+    updates are returned by pn*_running_stats, not applied here. Inside `bn_eval_mode()`: eval mode."""
+    if _BN_EVAL:
+        return F.batch_norm(t, sd[name + ".running_mean"], sd[name + ".running_var"], sd[name + ".weight"],
+                            sd[name + ".bias"], False, 0.0, eps)
     return F.batch_norm(t, None, None, sd[name + ".weight"], sd[name + ".bias"], True, 0.0, eps)
 
 

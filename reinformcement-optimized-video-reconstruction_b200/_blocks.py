@@ -63,21 +63,30 @@ class TrunkOps:
         if self.training:
             rm, rv, nbt = self.B[bn + ".running_mean"], self.B[bn + ".running_var"], self.B[bn + ".num_batches_tracked"]
             return ops.bn_train_fwd(raw, y, gamma, beta, c_valid, self.eps, self.momentum, rm, rv, nbt, relu=True)
-        raise NotImplementedError(
-            "eval-mode BatchNorm (running statistics) is not part of the ROVR hot path: the reference "
-            "never calls .eval() on the policy networks (rovr/rovr.py:68-78)")
+        # module.eval(): running statistics, buffers untouched (the reference's drivers never do this
+        # with the policy networks, but a validation loop would)
+        rm, rv = self.B[bn + ".running_mean"], self.B[bn + ".running_var"]
+        rstd = ops.bn_eval_fwd(raw, y, gamma, beta, c_valid, self.eps, rm, rv, relu=True)
+        return rm, rstd
 
-    def _zero_bias_grad(self, name):
+    def _bias_grad(self, name, draw, c_valid):
         """A bias that feeds train-mode BatchNorm has an exactly-zero gradient (the batch mean is
         subtracted right after it); autograd in the reference produces fp32 rounding noise around
-        zero there. Column sums of the bf16 gradient would only add rounding noise of their own."""
+        zero there, and column sums of the bf16 gradient would only add rounding noise of their own.
+        In eval mode the statistics are constants and the gradient is the column sum of draw."""
         p = self.P[name]
-        self.G[name] = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+        if self.training:
+            self.G[name] = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+            return
+        full = torch.empty(draw.shape[-1], dtype=torch.float32, device=p.device)
+        ops.colsum(draw, full)
+        g = self._grad(name)
+        ops.copy2d_f32(full[:c_valid].reshape(1, -1), g.reshape(1, -1))
 
     def _bn_bwd(self, bn, gy, y, raw, mean, rstd, c_valid):
         draw = torch.empty_like(raw)
         ops.bn_train_bwd(gy, y, raw, draw, self.P[bn + ".weight"], mean, rstd, c_valid,
-                         self._grad(bn + ".weight"), self._grad(bn + ".bias"), relu=True)
+                         self._grad(bn + ".weight"), self._grad(bn + ".bias"), relu=True, eval_mode=not self.training)
         return draw
 
     # -- Conv2d 3x3 + BN + ReLU --------------------------------------------------------------------
@@ -97,7 +106,7 @@ class TrunkOps:
         w = self.P[conv + ".weight"]
         draw = self._bn_bwd(bn, gy, y, raw, mean, rstd, w.shape[0])
         ops.conv3x3_wgrad(draw, x, self._grad(conv + ".weight"))
-        self._zero_bias_grad(conv + ".bias")
+        self._bias_grad(conv + ".bias", draw, w.shape[0])
         if gx is not None:
             wd = self.packed.get((conv, "d"), w, lambda t: ops.repack_conv3x3(t, True))
             ops.conv3x3_dgrad(draw, wd, gx)
@@ -117,7 +126,7 @@ class TrunkOps:
         w = self.P[up + ".weight"]
         draw = self._bn_bwd(bn, gy, y, raw, mean, rstd, w.shape[1])
         ops.convT2x2_wgrad(draw, x, self._grad(up + ".weight"))
-        self._zero_bias_grad(up + ".bias")
+        self._bias_grad(up + ".bias", draw, w.shape[1])
         if gx is not None:
             wd = self.packed.get((up, "d"), w, lambda t: ops.repack_convT2x2(t, True))
             ops.convT2x2_dgrad(draw, wd, gx)
@@ -143,7 +152,7 @@ class TrunkOps:
         draw = self._bn_bwd(bn, gy, y, raw, mean, rstd, cout)
         d2, x2 = draw.reshape(-1, cpad), x.reshape(-1, cin_pad)
         ops.gemm_wgrad(d2, x2, self._grad(conv + ".weight"))
-        self._zero_bias_grad(conv + ".bias")
+        self._bias_grad(conv + ".bias", draw, cout)
         if gx is not None:
             wd = self.packed.get((conv, "d"), w, lambda t: ops.repack_linear(t, True))
             ops.gemm_bf16(d2, wd, None, out=gx.reshape(-1, cin_pad))

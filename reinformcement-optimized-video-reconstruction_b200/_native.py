@@ -61,6 +61,8 @@ SIGNATURES = {
     "rovr_bn_workspace": (_sz, [_i]),
     "rovr_bn_train_fwd": (_i, [_p, _i, _p, _i, _ll, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
     "rovr_bn_train_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _i, _ll, _i, _i, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
+    "rovr_bn_eval_fwd": (_i, [_p, _i, _p, _i, _ll, _i, _i, _p, _p, _f, _p, _p, _p, _i, _p]),
+    "rovr_bn_eval_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _i, _ll, _i, _i, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
     "rovr_layernorm_fwd": (_i, [_p, _ll, _i, _f, _p, _p, _p, _p, _p, _p, _p]),
     "rovr_layernorm_workspace": (_sz, [_i]),
     "rovr_layernorm_bwd": (_i, [_p, _p, _ll, _i, _p, _p, _p, _p, _i, _p, _p, _p, _sz, _p]),

@@ -77,6 +77,13 @@ __global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int 
   }
 }
 
+// eval mode: rstd[c] = 1 / sqrt(running_var[c] + eps) (mean is running_mean itself)
+__global__ void bn_eval_rstd_kernel(const float* __restrict__ running_var, float eps, float* __restrict__ rstd,
+                                    int c_valid, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) rstd[c] = c < c_valid ? rsqrtf(running_var[c] + eps) : 0.f;
+}
+
 // y = [relu](gamma * (x - mean) * rstd + beta); channels >= c_valid (zero padding) are written as 0.
 __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld,
                                 __nv_bfloat16* __restrict__ y, int y_ld, long long npix, int C,
@@ -184,7 +191,7 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy
                                     __nv_bfloat16* __restrict__ dx, int dx_ld, long long npix, int C,
                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ gamma, const float* __restrict__ sums,
-                                    int c_valid, int relu) {
+                                    int c_valid, int relu, int eval_mode) {
   const int c8 = C >> 3;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= npix * c8) return;
@@ -210,7 +217,9 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy
       if (c < c_valid) {
         const float gg = (yv[e] > 0.f) ? g[e] : 0.f;
         const float xh = (xv[e] - mean[c]) * rstd[c];
-        r = gamma[c] * rstd[c] * (gg - sums[c] * inv_n - xh * sums[C + c] * inv_n);
+        // eval mode: mean / rstd are constants (running statistics), so only the direct term remains
+        r = eval_mode ? gamma[c] * rstd[c] * gg
+                      : gamma[c] * rstd[c] * (gg - sums[c] * inv_n - xh * sums[C + c] * inv_n);
       }
       g[e] = r;
     }

@@ -425,13 +425,25 @@ def bn_train_fwd(x, y, gamma, beta, c_valid, eps, momentum, running_mean, runnin
     return mean, rstd
 
 
-def bn_train_bwd(dy, y, x, dx, gamma, mean, rstd, c_valid, dgamma, dbeta, relu=True):
+def bn_eval_fwd(x, y, gamma, beta, c_valid, eps, running_mean, running_var, relu=True):
+    """Eval-mode BatchNorm (+ReLU) with the running statistics; returns rstd (fp32 [C]) for backward."""
+    B, H, W, C, x_ld = _act(x, "x")
+    _, _, _, Cy, y_ld = _act(y, "y")
+    assert Cy == C
+    rstd = torch.empty(C, dtype=torch.float32, device=x.device)
+    _launch("rovr_bn_eval_fwd", _ptr(x), x_ld, _ptr(y), y_ld, B * H * W, C, c_valid, _ptr(gamma), _ptr(beta),
+            ctypes.c_float(eps), _ptr(running_mean), _ptr(running_var), _ptr(rstd), int(relu), _stream())
+    return rstd
+
+
+def bn_train_bwd(dy, y, x, dx, gamma, mean, rstd, c_valid, dgamma, dbeta, relu=True, eval_mode=False):
     B, H, W, C, dy_ld = _act(dy, "dy")
     _, _, _, _, y_ld = _act(y, "y")
     _, _, _, _, x_ld = _act(x, "x")
     _, _, _, _, dx_ld = _act(dx, "dx")
     ws = workspace(N.lib.rovr_bn_workspace(C), x.device)
-    _launch("rovr_bn_train_bwd", _ptr(dy), dy_ld, _ptr(y), y_ld, _ptr(x), x_ld, _ptr(dx), dx_ld, B * H * W, C,
+    _launch("rovr_bn_eval_bwd" if eval_mode else "rovr_bn_train_bwd", _ptr(dy), dy_ld, _ptr(y), y_ld, _ptr(x), x_ld,
+            _ptr(dx), dx_ld, B * H * W, C,
             c_valid, _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dgamma), _ptr(dbeta), int(relu), _ptr(ws),
             ws.numel(), _stream())
     return dx

@@ -578,3 +578,36 @@ def test_graphed_function_matches_eager():
         for n, p in net.named_parameters():
             if n in g_ref:
                 assert torch.equal(p.grad, g_ref[n]), n
+
+
+def test_pn2_eval_mode_batchnorm():
+    """module.eval(): BatchNorm uses (and does not touch) the running statistics; forward and gradients
+    follow the oracle evaluated the same way (nn.BatchNorm2d eval semantics)."""
+    import policy_net_2 as M
+    dev = _dev()
+    sd = O.pn2_state_dict(0, False)
+    g = torch.Generator().manual_seed(5)
+    for k in list(sd.keys()):
+        if k.endswith("running_mean"):
+            sd[k] = 0.3 * torch.randn(sd[k].shape, generator=g)
+        if k.endswith("running_var"):
+            sd[k] = 0.5 + torch.rand(sd[k].shape, generator=g)
+    enc, feat, target, _ = _pn2_inputs(20, 23)
+    net = M.PolicyNetwork2UNet(is_critic=False)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    logits = net(enc.to(dev), feat.to(dev), target.to(dev), extra=True)
+    (logits ** 2).sum().backward()
+    for n, bfr in net.named_buffers():
+        assert torch.equal(bfr.cpu(), sd[n]), f"eval mode must not update {n}"
+    with O.bn_eval_mode():
+        leaf = _leaf(sd)
+        ref = O.pn2_forward(leaf, enc, feat, target, False, extra=True)
+        (ref ** 2).sum().backward()
+        emu = _leaf(sd)
+        (O.pn2_forward(emu, enc, feat, target, False, extra=True, bf16=True) ** 2).sum().backward()
+    _close("pn2.eval.il_logits", logits, ref, 2e-2)
+    grads = {k: v.grad for k, v in emu.items() if v.requires_grad}
+    _check_param_grads("pn2.eval vs bf16-storage oracle", net, grads, _pn2_tol)
+    # in eval mode the convolution biases DO receive a gradient (the statistics are constants)
+    assert net.video_conv[0].bias.grad.abs().max().item() > 0
