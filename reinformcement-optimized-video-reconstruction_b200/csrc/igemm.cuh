@@ -150,9 +150,10 @@ __device__ __forceinline__ uint32_t swz_off(int m, int j, int rowb) {
 
 // kPlainEpi: the epilogue has neither a ReLU mask nor fused column sums (every forward launch):
 // their register state disappears and all four 16-column TMEM chunks of a block are fetched at once.
-// kTail: the fused LocalNet tail (conv7 forward only) — its own instance so that the plain one
-// keeps its 130-register epilogue.
-template <bool kPlainEpi, bool kTail = false>
+// kTail: the fused LocalNet tail (conv7 forward only); kPool: the fused 2x2 max-pool (encoder convs).
+// Each is its own instance so that the plain one keeps its 130-register epilogue — growing it to 141
+// (pool) or 167 (tail) registers measurably slows every thin layer.
+template <bool kPlainEpi, bool kTail = false, bool kPool = false>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmMask,
@@ -206,7 +207,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
-    if (p.pool2) tma_prefetch_desc(&tmMask);
+    if (kPool) tma_prefetch_desc(&tmMask);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -622,7 +623,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         tz[0] = fmaf(v1, w1.x, tz[0]); tz[1] = fmaf(v1, w1.y, tz[1]); tz[2] = fmaf(v1, w1.z, tz[2]);
                       }
                     }
-                    if (kPlainEpi && p.pool2) {
+                    if constexpr (kPlainEpi && kPool) {
 #pragma unroll
                       for (int j = 0; j < 8; ++j) {
                         __nv_bfloat162 a, b;
@@ -670,7 +671,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
             }
           };
-          convert(std::integral_constant<int, 4>{});
+          convert(std::integral_constant<int, kPlainEpi ? 4 : 2>{});
           if (want_tail) {
             // moff = b * 3 * plane + y * W + x (mstride set by the host); three planes per image
             float se = 0.f;
@@ -723,7 +724,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               c[0] = nglb;
             }
             tma_store_5d(&tmOut, stg, c[0], c[1], c[2], c[3], c[4]);
-            if (kPlainEpi && p.pool2) tma_store_5d(&tmMask, pstg, c[0], c[1] >> 1, c[2] >> 1, c[3], c[4]);
+            if constexpr (kPlainEpi && kPool) tma_store_5d(&tmMask, pstg, c[0], c[1] >> 1, c[2] >> 1, c[3], c[4]);
             bulk_commit();
           }
         }
