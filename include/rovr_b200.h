@@ -294,6 +294,8 @@ int rovr_softmax_bwd(const float* dp, const void* p, void* ds, long long rows, i
 int rovr_gelu_fwd(const void* h, void* a, long long n, void* stream);
 int rovr_gelu_bwd(const void* da, const void* h, void* dh, long long n, void* stream);
 int rovr_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
+/* out = a + b, dense fp32 (residual joins, rovr/common_layers.py:101-102,113-115); n multiple of 4 */
+int rovr_add_f32(const float* a, const float* b, float* out, long long n, void* stream);
 /* positional encodings (rovr/common_layers.py:7-52): out[b][p][j] = x + w1[j]*(p % n1) + b1[j]
  * [+ w2[j]*(p / n1) + b2[j]] with w, b the weight / bias of Linear(1, D); grad: which = 0 -> (w1, b1),
  * 1 -> (w2, b2) */
@@ -305,6 +307,12 @@ int rovr_posenc_grad(const float* g, int B, int P, int D, int n1, int which, flo
 size_t rovr_colsum_workspace(int C);
 int rovr_colsum(const void* g, int ld, long long npix, int C, float* out, void* ws, size_t ws_bytes,
                 void* stream);
+
+/* the same for a wide bf16 row-major matrix [M][C] with row stride ld, any even C (bias gradients of
+ * nn.Linear / in-projection layers, rovr/common_layers.py:58,70,84-85) */
+size_t rovr_colsum_rows_workspace(int C);
+int rovr_colsum_rows(const void* g, long long ld, long long M, int C, float* out, void* ws, size_t ws_bytes,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -98,9 +98,18 @@ class _Packed:
         return self.cache.get((key, "d"), w, lambda t: ops.repack_linear(t, True))
 
 
+def _wgrad(gy_bf, x_bf, gw):
+    """dW = gy^T x: a regular GEMM over transposed operands when there are many tokens (full MMA tiles,
+    no split-K partial traffic), the split-K wgrad engine otherwise."""
+    if gy_bf.shape[0] >= 512 and gw.is_contiguous():
+        ops.linear_wgrad(gy_bf, x_bf, gw)
+    else:
+        ops.gemm_wgrad(gy_bf, x_bf, gw)
+
+
 def _linear_grads(gy_bf, x_bf, w, want_bias=True):
     gw = torch.empty_like(w)
-    ops.gemm_wgrad(gy_bf, x_bf, gw)
+    _wgrad(gy_bf, x_bf, gw)
     gb = None
     if want_bias:
         gb = torch.empty(w.shape[0], dtype=torch.float32, device=w.device)
@@ -170,8 +179,8 @@ class _AttentionFn(torch.autograd.Function):
         gb_in = torch.empty(3 * E, dtype=torch.float32, device=dev)
         genc = glne_w = glne_b = None
         if cross:
-            ops.gemm_wgrad(dq_buf, x2, gw_in[:E])
-            ops.gemm_wgrad(dkv_buf, e2, gw_in[E:])
+            _wgrad(dq_buf, x2, gw_in[:E])
+            _wgrad(dkv_buf, e2, gw_in[E:])
             ops.colsum_rows(dq_buf, gb_in[:E])
             ops.colsum_rows(dkv_buf, gb_in[E:])
             dxn = ops.gemm_bf16(dq_buf, pk.bwd("in_q", w_in[:E]), out_dtype=torch.float32)      # [E, E]
@@ -180,7 +189,7 @@ class _AttentionFn(torch.autograd.Function):
             glne_w, glne_b = torch.empty_like(lne_w), torch.empty_like(lne_w)
             ops.layernorm_bwd(den, enc.contiguous(), lne_w, emean, erstd, genc, dgamma=glne_w, dbeta=glne_b)
         else:
-            ops.gemm_wgrad(dq_buf, x2, gw_in)
+            _wgrad(dq_buf, x2, gw_in)
             ops.colsum_rows(dq_buf, gb_in)
             dxn = ops.gemm_bf16(dq_buf, pk.bwd("in", w_in), out_dtype=torch.float32)           # [E, 3E]
         ops.copy2d_f32(g.view(b * S, E), dxn, accumulate=True)             # residual branch
@@ -229,11 +238,7 @@ class _AddFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, a, b):
-        out = torch.empty_like(a, memory_format=torch.contiguous_format)
-        E = a.shape[-1]
-        ops.copy2d_f32(a.contiguous().view(-1, E), out.view(-1, E))
-        ops.copy2d_f32(b.contiguous().view(-1, E), out.view(-1, E), accumulate=True)
-        return out
+        return ops.add_f32(a.contiguous(), b.contiguous())
 
     @staticmethod
     def backward(ctx, g):

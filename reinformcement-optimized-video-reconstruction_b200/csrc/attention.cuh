@@ -8,23 +8,33 @@
 namespace rovr {
 
 // out[i2][i1][c][r] = in[i2][i1][r][c] for r < R, c < C; out columns r in [R, r_pad) are zero.
-// 32x32 tiles through shared memory; grid = (ceil(r_pad/32), ceil(C/32), n1*n2).
+// 64x64 tiles through shared memory, bf16 PAIRS on both sides (a warp reads / writes 128 contiguous
+// bytes per row); grid = (ceil(r_pad/64), ceil(C/64), n1*n2), block = (32, 8). C and the strides are
+// even (all callers: multiples of 8).
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long in_ld, long long in_s1,
                                       long long in_s2, __nv_bfloat16* __restrict__ out, long long out_ld,
                                       long long out_s1, long long out_s2, int R, int C, int r_pad, int n1) {
-  __shared__ __nv_bfloat16 tile[32][33];
+  __shared__ uint32_t tile[64][33];   // [row r][pair of columns]
   const int i1 = blockIdx.z % n1, i2 = blockIdx.z / n1;
   const __nv_bfloat16* src = in + i2 * in_s2 + i1 * in_s1;
   __nv_bfloat16* dst = out + i2 * out_s2 + i1 * out_s1;
-  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-    const int r = r0 + j, c = c0 + threadIdx.x;
-    tile[j][threadIdx.x] = (r < R && c < C) ? src[r * in_ld + c] : __float2bfloat16_rn(0.f);
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  for (int j = threadIdx.y; j < 64; j += 8) {
+    const int r = r0 + j, c = c0 + 2 * threadIdx.x;
+    uint32_t v = 0u;
+    if (r < R && c < C) v = __ldg(reinterpret_cast<const uint32_t*>(src + r * in_ld + c));
+    tile[j][threadIdx.x] = v;
   }
   __syncthreads();
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-    const int c = c0 + j, r = r0 + threadIdx.x;
-    if (c < C && r < r_pad) dst[c * out_ld + r] = tile[threadIdx.x][j];
+  // output row = input column c0 + j; this thread writes the pair of input rows (r0 + 2 tx, r0 + 2 tx + 1)
+  for (int j = threadIdx.y; j < 64; j += 8) {
+    const int c = c0 + j, r = r0 + 2 * threadIdx.x;
+    if (c < C && r < r_pad) {
+      const uint32_t a = tile[2 * threadIdx.x][j >> 1], bb = tile[2 * threadIdx.x + 1][j >> 1];
+      const uint32_t lo = (j & 1) ? (a >> 16) : (a & 0xFFFFu);
+      const uint32_t hi = (j & 1) ? (bb >> 16) : (bb & 0xFFFFu);
+      *reinterpret_cast<uint32_t*>(dst + c * out_ld + r) = lo | (hi << 16);
+    }
   }
 }
 
@@ -79,6 +89,15 @@ __global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv
   const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
   const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
   dh[i] = __float2bfloat16_rn(__bfloat162float(da[i]) * (cdf + x * pdf));
+}
+
+// out = a + b on fp32 vectors (residual joins of the encoder / decoder blocks), 16 bytes per thread
+__global__ void add_f32_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out,
+                               long long n4) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 x = __ldg(a + i), y = __ldg(b + i);
+  out[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {

@@ -440,6 +440,36 @@ __global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ g, int l
   }
 }
 
+// Column sums of a wide bf16 row-major matrix [M][C] (bias gradients of the attention / feed-forward
+// projections, C up to 9216): block = 64 columns (32 lanes x one bf16 pair) x 8 row groups over a
+// chunk of rows; partial [chunks][C] is combined by reduce_rows_kernel.
+__global__ void __launch_bounds__(256)
+colsum_wide_kernel(const __nv_bfloat16* __restrict__ g, long long ld, long long M, int C, int rows_per_chunk,
+                   float* __restrict__ partial) {
+  __shared__ float sred[8][64];
+  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + 2 * lane;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_chunk;
+  const long long r1 = min(M, r0 + rows_per_chunk);
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    for (long long r = r0 + rg; r < r1; r += 8) {
+      const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(g + r * ld + c));
+      s0 += bf16_lo(u);
+      s1 += bf16_hi(u);
+    }
+  }
+  sred[rg][2 * lane] = s0;
+  sred[rg][2 * lane + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += sred[k][threadIdx.x];
+    partial[static_cast<long long>(blockIdx.y) * C + blockIdx.x * 64 + threadIdx.x] = s;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Weight repack: dst[i0][i1][i2] (bf16, dense) = src[i0*s0 + i1*s1 + i2*s2] (fp32) for i2 < v2,
 // i0 < v0, else 0.

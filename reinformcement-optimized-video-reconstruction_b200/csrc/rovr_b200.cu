@@ -399,6 +399,24 @@ extern "C" int rovr_maxpool_bwd(const void* x, int x_ld, const void* gp, int gp_
 // ------------------------------------------------------------------------------------------------
 // bias gradient
 // ------------------------------------------------------------------------------------------------
+// wide matrices (any even C): rows split into up to 64 chunks
+static const int kColsumWideChunks = 64;
+extern "C" size_t rovr_colsum_rows_workspace(int C) { return static_cast<size_t>(kColsumWideChunks) * C * sizeof(float); }
+extern "C" int rovr_colsum_rows(const void* g, long long ld, long long M, int C, float* out, void* ws,
+                                size_t ws_bytes, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  ROVR_REQUIRE(C % 2 == 0 && ld % 2 == 0 && M > 0, "colsum_rows: C and ld must be even");
+  ROVR_REQUIRE(ws_bytes >= rovr_colsum_rows_workspace(C), "colsum_rows: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rpc = static_cast<int>((M + kColsumWideChunks - 1) / kColsumWideChunks);
+  const int chunks = static_cast<int>((M + rpc - 1) / rpc);
+  colsum_wide_kernel<<<dim3((C + 63) / 64, chunks), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), ld, M, C, rpc,
+                                                                 static_cast<float*>(ws));
+  if (int rc = launch_check("colsum_wide")) return rc;
+  reduce_rows_kernel<<<(C + 31) / 32, RR_THREADS, 0, st>>>(static_cast<float*>(ws), chunks, C, C, out, 0);
+  return launch_check("reduce_rows(colsum_rows)");
+}
+
 static const int kColsumBlocks = 592;  // 4 per SM
 extern "C" size_t rovr_colsum_workspace(int C) { return static_cast<size_t>(kColsumBlocks) * C * sizeof(float); }
 extern "C" int rovr_colsum(const void* g, int ld, long long npix, int C, float* out, void* ws,

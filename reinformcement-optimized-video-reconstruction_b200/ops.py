@@ -812,15 +812,41 @@ def cast_bf16(x):
     return out
 
 
+def add_f32(a, b):
+    """a + b for two dense fp32 tensors of the same shape (one pass)."""
+    _f32(a, "a")
+    _f32(b, "b")
+    assert a.shape == b.shape and a.numel() % 4 == 0
+    out = torch.empty_like(a)
+    _launch("rovr_add_f32", _ptr(a), _ptr(b), _ptr(out), a.numel(), _stream())
+    return out
+
+
 def colsum_rows(g, out):
-    """out[c] = sum_m g[m, c] for a bf16 [M, C] matrix of any even width (512-column slabs)."""
+    """out[c] = sum_m g[m, c] for a bf16 [M, C] matrix of any even width (one kernel + one reduction)."""
     _bf(g, "g")
     M, C = g.shape
     assert out.numel() == C and g.stride(1) == 1
-    for c0 in range(0, C, 512):
-        c1 = min(C, c0 + 512)
-        colsum(g[:, c0:c1].unflatten(0, (1, 1, M)), out[c0:c1])
+    _f32(out, "out")
+    ws = workspace(N.lib.rovr_colsum_rows_workspace(C), g.device)
+    _launch("rovr_colsum_rows", _ptr(g), g.stride(0), M, C, _ptr(out), _ptr(ws), ws.numel(), _stream())
     return out
+
+
+def linear_wgrad(dy, x, dw):
+    """dw[N, K] (fp32) = dy[M, N]^T @ x[M, K] for large M: both operands are transposed once (zero-padded
+    to a multiple of 16 rows) and the product runs as a regular tcgen05 GEMM with full 128 x 256 tiles
+    and an fp32 epilogue straight into dw — no split-K partials. For small M use gemm_wgrad."""
+    _bf(dy, "dy")
+    _bf(x, "x")
+    M, Nn = dy.shape
+    K = x.shape[1]
+    assert x.shape[0] == M and dw.shape == (Nn, K) and dw.dtype == torch.float32 and dw.is_contiguous()
+    m_pad = pad16(M)
+    dyT = transpose_heads(dy.unflatten(0, (1, 1, M)), m_pad)[0, 0]      # [N, m_pad]
+    xT = transpose_heads(x.unflatten(0, (1, 1, M)), m_pad)[0, 0]        # [K, m_pad]
+    gemm_bf16(dyT, xT, None, out=dw)
+    return dw
 
 
 def posenc_add(x, w1, b1, n1, w2=None, b2=None):
