@@ -115,7 +115,24 @@ struct IgemmParams {
   float* colsum_partial;  // non-null: per-(M tile, lane quarter) column sums of the bf16 output,
                           // [m_tiles * 4][n_total] fp32 — the bias gradient of the layer that
                           // consumes this gradient tensor, reduced afterwards in a fixed order
+  // division by the run-time tile counts without the ~25-instruction integer-division sequence (ncu: the
+  // per-tile index arithmetic was a quarter of the epilogue's instruction stream on thin layers):
+  // x / d == (umulhi(x, fd_mul) + x) >> fd_shr for x < 2^31. Index 0..3 = ntile[j], 4 = n_tiles_n,
+  // 5 = shuf_cout (filled by igemm_dispatch).
+  uint32_t fd_mul[6], fd_shr[6];
+  int stg_bufs;           // staging tiles per epilogue group: 2 when shared memory allows (the TMA store of a
+                          // column block drains while the next block is converted), else 1
 };
+
+inline void ig_fastdiv_make(uint32_t d, uint32_t* mul, uint32_t* shr) {
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  *mul = static_cast<uint32_t>(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  *shr = l;
+}
+__device__ __forceinline__ int ig_fastdiv(int x, uint32_t mul, uint32_t shr) {
+  return static_cast<int>((__umulhi(static_cast<uint32_t>(x), mul) + static_cast<uint32_t>(x)) >> shr);
+}
 
 // ---- TMA store / bulk-group helpers ------------------------------------------------------------
 __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int c1,
@@ -182,10 +199,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                           : static_cast<size_t>(p.stages) * stage_bytes;
   uint8_t* aring = smem + front_bytes;                                           // halo tiles
   aring += (1024u - (smem_u32(aring) & 1023u)) & 1023u;                          // swizzle alignment
-  uint8_t* stg_base = aring + (halo ? p.a_slots * halo_slot : 0);                // 2 staging tiles
+  uint8_t* stg_base = aring + (halo ? p.a_slots * halo_slot : 0);                // 2 or 4 staging tiles
   const uint32_t pstg_bytes = p.pool2 ? 32u * epi_rowb : 0u;                     // pooled tile: 32 rows
-  uint8_t* pstg_base = stg_base + 2 * stg_bytes;                                 // 2 pooled staging tiles
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(pstg_base + 2 * pstg_bytes);
+  uint8_t* pstg_base = stg_base + 2 * p.stg_bufs * stg_bytes;                    // 2 pooled staging tiles
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(pstg_base + 2 * p.stg_bufs * pstg_bytes);
   uint64_t* empty_bar = full_bar + IG_MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + IG_MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -194,7 +211,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* aempty_bar = afull_bar + IG_MAX_ASLOTS;
   uint64_t* wfull_bar = aempty_bar + IG_MAX_ASLOTS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
-  float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
+  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
   float4* stail = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(sbias + p.n_total) + 15) & ~uintptr_t(15));
 
   const int m_tiles = p.ntile[0] * p.ntile[1] * p.ntile[2] * p.ntile[3];
@@ -248,13 +265,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int s = 0, sa = 0;
       uint32_t ph = 0, pha = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles_n;
-        int mt = tile / p.n_tiles_n;
+        int mt = ig_fastdiv(tile, p.fd_mul[4], p.fd_shr[4]);
+        const int nt = tile - mt * p.n_tiles_n;
         int org[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          org[j] = (mt % p.ntile[j]) * p.boxM[j];
-          mt /= p.ntile[j];
+          const int q = ig_fastdiv(mt, p.fd_mul[j], p.fd_shr[j]);
+          org[j] = (mt - q * p.ntile[j]) * p.boxM[j];
+          mt = q;
         }
         if (halo) {
           // per k-chunk: one halo tile of the input, then (unless resident) the nine weight tiles
@@ -431,8 +449,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const bool elected = (quarter == 0 && lane == 0);
     const int nblk = p.n_tile / p.cw;
     const int chunks = p.cw >> 4;
-    uint8_t* stg = stg_base + grp * stg_bytes;
-    uint8_t* pstg = pstg_base + grp * pstg_bytes;
+    uint8_t* const stg0 = stg_base + grp * p.stg_bufs * stg_bytes;
+    uint8_t* const pstg0 = pstg_base + grp * p.stg_bufs * pstg_bytes;
     // pooled-tile row of this lane's 2x2 window: the tile is 8 (x) by 16 (y) pixels, row m = x + 8 y,
     // so the window partners are lanes l ^ 1 (x) and l ^ 8 (y) of the same warp
     const int pm = ((lane & 7) >> 1) + 4 * (quarter * 2 + (lane >> 4));
@@ -515,13 +533,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       // tile geometry: origin, validity of this thread's row, its mask row offset
       auto tile_setup = [&](int tile, int* org, bool& valid, long long& moff) {
-        int mt = tile / p.n_tiles_n;
+        int mt = ig_fastdiv(tile, p.fd_mul[4], p.fd_shr[4]);
         valid = m < rows;
         moff = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          org[j] = (mt % p.ntile[j]) * p.boxM[j];
-          mt /= p.ntile[j];
+          const int q = ig_fastdiv(mt, p.fd_mul[j], p.fd_shr[j]);
+          org[j] = (mt - q * p.ntile[j]) * p.boxM[j];
+          mt = q;
           const int pj = org[j] + lrow[j];
           valid = valid && (pj < p.dimM[j]);
           moff += static_cast<long long>(pj) * p.mstride[j];
@@ -541,14 +560,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       bool valid = false;
       long long moff = 0;
       uint4 mreg[8];
+      auto tile_nt = [&](int t) { return t - ig_fastdiv(t, p.fd_mul[4], p.fd_shr[4]) * p.n_tiles_n; };
       if (tile < total_tiles) {
         tile_setup(tile, org, valid, moff);
-        if (want_mask && (tile % p.n_tiles_n) * p.n_tile < p.mask_cols)
-          mask_fetch(mreg, valid, moff, (tile % p.n_tiles_n) * p.n_tile);
+        if (want_mask && tile_nt(tile) * p.n_tile < p.mask_cols)
+          mask_fetch(mreg, valid, moff, tile_nt(tile) * p.n_tile);
       }
+      int sbuf = 0;   // staging tile of this group used by the current column block
       while (tile < total_tiles) {
-        const int nt = tile % p.n_tiles_n;
-        const int tile_m = tile / p.n_tiles_n;
+        const int tile_m = ig_fastdiv(tile, p.fd_mul[4], p.fd_shr[4]);
+        const int nt = tile - tile_m * p.n_tiles_n;
         const int ntile_next = tile + tstep;
         int org_n[4] = {0, 0, 0, 0};
         bool valid_n = false;
@@ -565,8 +586,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int cb = 0; cb < nblk; ++cb) {
           const int nloc = cb * p.cw;
           const int nglb = nt * p.n_tile + nloc;
-          // staging buffer free again? (the previous TMA store of this group has read it)
-          if (elected) bulk_wait_read<0>();
+          // staging tile free again? (with two tiles per group: the store issued two blocks ago has read it)
+          uint8_t* const stg = stg0 + sbuf * stg_bytes;
+          uint8_t* const pstg = pstg0 + sbuf * pstg_bytes;
+          if (elected) {
+            if (p.stg_bufs == 2) bulk_wait_read<1>();
+            else bulk_wait_read<0>();
+          }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
           if (cb + 1 == nblk && ntile_next < total_tiles) tile_setup(ntile_next, org_n, valid_n, moff_n);
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
@@ -593,12 +619,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   const int ch = G * h + c2;
                   if (ch < chunks) {
                     uint32_t pk[8];
+                    float bv[16];
+                    if (has_bias) {   // nglb and sbias are 16-byte aligned: four 128-bit shared loads
+                      const float4* b4 = reinterpret_cast<const float4*>(sbias + nglb + ch * 16);
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) {
+                        const float4 t = b4[j];
+                        bv[4 * j] = t.x; bv[4 * j + 1] = t.y; bv[4 * j + 2] = t.z; bv[4 * j + 3] = t.w;
+                      }
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                       float f0 = __uint_as_float(v[c2][2 * j]), f1 = __uint_as_float(v[c2][2 * j + 1]);
                       if (has_bias) {
-                        f0 += sbias[nglb + ch * 16 + 2 * j];
-                        f1 += sbias[nglb + ch * 16 + 2 * j + 1];
+                        f0 += bv[2 * j];
+                        f1 += bv[2 * j + 1];
                       }
                       pk[j] = p.relu ? pack_bf16x2_relu(f0, f1) : pack_bf16x2(f0, f1);
                     }
@@ -701,7 +736,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (cb + 1 < nblk) {
               if (nglb + p.cw < p.mask_cols) mask_fetch(mreg, valid, moff, nglb + p.cw);
             } else if (ntile_next < total_tiles) {
-              const int n_next = (ntile_next % p.n_tiles_n) * p.n_tile;
+              const int n_next = tile_nt(ntile_next) * p.n_tile;
               if (n_next < p.mask_cols) mask_fetch(mreg, valid_n, moff_n, n_next);
             }
           }
@@ -716,7 +751,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             int c[5];
             c[1] = org[0]; c[2] = org[1]; c[3] = org[2]; c[4] = org[3];
             if (p.epi_mode == IG_EPI_PIXSHUF) {
-              const int q = nglb / p.shuf_cout;
+              const int q = ig_fastdiv(nglb, p.fd_mul[5], p.fd_shr[5]);
               c[0] = nglb - q * p.shuf_cout;
               c[1] += q & 1;
               c[3] += q >> 1;
@@ -727,6 +762,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if constexpr (kPlainEpi && kPool) tma_store_5d(&tmMask, pstg, c[0], c[1] >> 1, c[2] >> 1, c[3], c[4]);
             bulk_commit();
           }
+          sbuf = (p.stg_bufs == 2) ? (sbuf ^ 1) : 0;
         }
         aph ^= 1u;
         tile = ntile_next;
@@ -747,9 +783,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 // Fixed (non-pipeline) shared memory of a configuration (host side).
-inline size_t igemm_fixed_smem(int cw, int pool2, int n_total, int a_slots = 0, int sw = 128) {
-  const size_t stg = 128 * static_cast<size_t>(cw) * 2 + (pool2 ? 32 * static_cast<size_t>(cw) * 2 : 0);
-  return 2048 + static_cast<size_t>(a_slots) * ig_halo_slot(sw) + 2 * stg +
+inline size_t igemm_fixed_smem(int cw, int pool2, int n_total, int a_slots = 0, int sw = 128, int stg_bufs = 1) {
+  const size_t stg = (128 * static_cast<size_t>(cw) * 2 + (pool2 ? 32 * static_cast<size_t>(cw) * 2 : 0)) * stg_bufs;
+  return 2048 + 16 + static_cast<size_t>(a_slots) * ig_halo_slot(sw) + 2 * stg +
          (2 * IG_MAX_STAGES + 2 * IG_MAX_ASLOTS + 7) * 8 + 16 +
          static_cast<size_t>(n_total) * 4 + 64 + 64 * 16 + 16;
 }

@@ -107,21 +107,23 @@ def main():
     rn.zero_grad(set_to_none=True)
     report("ResNet-50 extractor fwd (+linear bwd) 25 frames 224x224", ms, l, 25, "frames/s", 8.174, g_rn, (frames,), [rn])
 
-    E, S, B = 3072, 256, 8
-    blk = EncoderBlock(E, 8, 0.0).to(dev).eval()
-    x = torch.randn(B, S, E, device=dev, requires_grad=True)
+    E, S = 3072, 256
+    for B in (8, 24):
+        blk = EncoderBlock(E, 8, 0.0).to(dev).eval()
+        x = torch.randn(B, S, E, device=dev, requires_grad=True)
 
-    def f_enc():
+        def f_enc():
+            blk.zero_grad(set_to_none=True)
+            (blk(x) ** 2).sum().backward()
+        ms, l = timeit(f_enc, iters=10)
+
+        def g_enc(xx):
+            (blk(xx) ** 2).sum().backward()
         blk.zero_grad(set_to_none=True)
-        (blk(x) ** 2).sum().backward()
-    ms, l = timeit(f_enc, iters=10)
-
-    def g_enc(xx):
-        (blk(xx) ** 2).sum().backward()
-    blk.zero_grad(set_to_none=True)
-    x.grad = None
-    report("EncoderBlock fwd+bwd E=3072 S=256 B=8 heads=8", ms, l, B, "sequences/s", 3 * (20.13 + 2.42), g_enc, (x,), [blk])
-
+        x.grad = None
+        report(f"EncoderBlock fwd+bwd E=3072 S=256 B={B} heads=8", ms, l, B, "sequences/s", 3 * (20.13 + 2.42),
+               g_enc, (x,), [blk])
+        del blk, x
 
 if __name__ == "__main__":
     main()
