@@ -677,29 +677,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         *reinterpret_cast<uint4*>(pstg + swz_off(pm, ch * 2 + 1, epi_rowb)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                       }
                     }
-                    if (blk_cs) {
-                      // column sums of the STORED values over the warp's 32 rows: reduce-scatter
-                      float w[16];
-#pragma unroll
-                      for (int j = 0; j < 8; ++j) {
-                        w[2 * j] = valid ? bf16_lo(pk[j]) : 0.f;
-                        w[2 * j + 1] = valid ? bf16_hi(pk[j]) : 0.f;
-                      }
-#pragma unroll
-                      for (int st = 0; st < 4; ++st) {
-                        const int off = 16 >> st, n = 8 >> st;
-                        const bool up = (lane & off) != 0;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                          if (j < n) {
-                            const float send = up ? w[j] : w[j + n];
-                            const float keep = up ? w[j + n] : w[j];
-                            w[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                          }
-                        }
-                      }
-                      w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
-                      if ((lane & 1) == 0) cs_dst[ch * 16 + (lane >> 1)] = w[0];
+                    if (blk_cs && !blk_mask && !valid) {   // rows outside the image must not reach the column sums
+                      *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2, epi_rowb)) = make_uint4(0, 0, 0, 0);
+                      *reinterpret_cast<uint4*>(stg + swz_off(m, ch * 2 + 1, epi_rowb)) = make_uint4(0, 0, 0, 0);
                     }
                   }
                 }
@@ -761,6 +741,31 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tma_store_5d(&tmOut, stg, c[0], c[1], c[2], c[3], c[4]);
             if constexpr (kPlainEpi && kPool) tma_store_5d(&tmMask, pstg, c[0], c[1] >> 1, c[2] >> 1, c[3], c[4]);
             bulk_commit();
+          }
+          if (blk_cs) {
+            // Fused bias gradient: column sums of the STORED bf16 values over this warp's 32 rows, read
+            // back from the staging tile — one channel pair per lane, one row per instruction (a row is
+            // 32 distinct words, so the reads are conflict-free under any swizzle), rows added in a
+            // fixed order. Narrow blocks (32 / 16 channels) fold 2 / 4 rows into one instruction and
+            // combine the row subsets with shuffles. The tile is only overwritten after the group's
+            // next barrier, which every thread reaches after these reads.
+            const int npair = p.cw >> 1;                 // 32 / 16 / 8
+            const int pair = lane & (npair - 1), rs = lane / npair, rstep = 32 / npair;
+            float s0 = 0.f, s1 = 0.f, u0 = 0.f, u1 = 0.f;
+            const uint32_t wofs = static_cast<uint32_t>(pair & 3) * 4u;
+#pragma unroll 8
+            for (int r = 0; r < 32; r += 2 * rstep) {
+              const uint32_t wa = *reinterpret_cast<const uint32_t*>(stg + swz_off(quarter * 32 + r + rs, pair >> 2, epi_rowb) + wofs);
+              const uint32_t wb = *reinterpret_cast<const uint32_t*>(stg + swz_off(quarter * 32 + r + rstep + rs, pair >> 2, epi_rowb) + wofs);
+              s0 += bf16_lo(wa); s1 += bf16_hi(wa);
+              u0 += bf16_lo(wb); u1 += bf16_hi(wb);
+            }
+            s0 += u0; s1 += u1;
+            for (int off = npair; off < 32; off <<= 1) {
+              s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+            }
+            if (rs == 0) *reinterpret_cast<float2*>(cs_dst + 2 * pair) = make_float2(s0, s1);
           }
           sbuf = (p.stg_bufs == 2) ? (sbuf ^ 1) : 0;
         }
