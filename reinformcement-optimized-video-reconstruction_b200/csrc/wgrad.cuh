@@ -229,6 +229,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 // final[m*fs_m + t*fs_t + c*fs_c] = sum_slices P[slice][m][t][c], for m < m_keep, c < c_keep.
+// One thread per element: right when there are few slices and many elements (the wide layers).
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad,
                                     int n_slices, int m_total, int taps, int c_total, int m_keep,
                                     int c_keep, long long fs_m, long long fs_t, long long fs_c,
@@ -254,6 +255,56 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   const float s = (s0 + s1) + (s2 + s3);
   float* dst = grad + m * fs_m + t * fs_t + c * fs_c;
   *dst = accumulate ? (*dst + s) : s;
+}
+// Many slices, few elements (thin layers: up to 148 slices of a few thousand weights):
+// Block = 32 consecutive elements (x) by NY slice lanes (y): lane y adds slices y, y + NY, ... (up to
+// four loads in flight), the NY partial sums meet in shared memory and are added in the order
+// y = 0 .. NY-1 — a fixed order, so the gradient is bitwise reproducible. With one thread per element
+// (the first version) a thin layer's 148 slices were 37 dependent round trips to L2 on 36 CTAs.
+constexpr int WGR_MAX_NY = 32;
+__global__ void wgrad_reduce_tall_kernel(const float* __restrict__ partial, float* __restrict__ grad,
+                                    int n_slices, int m_total, int taps, int c_total, int m_keep,
+                                    int c_keep, long long fs_m, long long fs_t, long long fs_c,
+                                    int accumulate) {
+  __shared__ float part[WGR_MAX_NY][33];
+  const long long n = static_cast<long long>(m_total) * taps * c_total;
+  const long long i = static_cast<long long>(blockIdx.x) * 32 + threadIdx.x;
+  const int ny = blockDim.y, y = threadIdx.y;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (i < n) {
+    int k = y;
+    for (; k + 3 * ny < n_slices; k += 4 * ny) {
+      s0 += __ldg(partial + static_cast<long long>(k) * n + i);
+      s1 += __ldg(partial + static_cast<long long>(k + ny) * n + i);
+      s2 += __ldg(partial + static_cast<long long>(k + 2 * ny) * n + i);
+      s3 += __ldg(partial + static_cast<long long>(k + 3 * ny) * n + i);
+    }
+    for (; k < n_slices; k += ny) s0 += __ldg(partial + static_cast<long long>(k) * n + i);
+  }
+  part[y][threadIdx.x] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (y != 0 || i >= n) return;
+  float s = 0.f;
+  for (int j = 0; j < ny; ++j) s += part[j][threadIdx.x];
+  const int c = static_cast<int>(i % c_total);
+  const int t = static_cast<int>((i / c_total) % taps);
+  const int m = static_cast<int>(i / (static_cast<long long>(c_total) * taps));
+  if (c >= c_keep || m >= m_keep) return;
+  float* dst = grad + m * fs_m + t * fs_t + c * fs_c;
+  *dst = accumulate ? (*dst + s) : s;
+}
+inline void launch_wgrad_reduce(const float* partial, float* grad, int n_slices, int m_total, int taps, int c_total,
+                                int m_keep, int c_keep, long long fs_m, long long fs_t, long long fs_c, int accumulate,
+                                cudaStream_t st) {
+  const long long n = static_cast<long long>(m_total) * taps * c_total;
+  // measured: the slice-parallel kernel only wins when the element count is too small to fill the GPU
+  if (n_slices >= 24 && n <= 32768) {
+    wgrad_reduce_tall_kernel<<<static_cast<unsigned>((n + 31) / 32), dim3(32, WGR_MAX_NY), 0, st>>>(
+        partial, grad, n_slices, m_total, taps, c_total, m_keep, c_keep, fs_m, fs_t, fs_c, accumulate);
+  } else {
+    wgrad_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+        partial, grad, n_slices, m_total, taps, c_total, m_keep, c_keep, fs_m, fs_t, fs_c, accumulate);
+  }
 }
 
 inline size_t wgrad_stage_bytes(int kp, int blk_b, int nblk) {
