@@ -279,17 +279,17 @@ def run_cuda(args, rank, local_rank, world):
         # end to end through the reference-facing nn.Module call, inputs in pinned HOST memory:
         # every step copies its own inputs host -> device (DeviceFeeder: the copy of step i+1 is
         # issued on a side stream before step i is computed) and reads the loss back to the host.
-        from feeder import DeviceFeeder
+        from feeder import DeviceFeeder, ScalarReadback
 
         def e2e_loop(steps):
-            last = None
+            rb = ScalarReadback(dev, lag=1)
             for xd, cd, td in DeviceFeeder(((xh, ch, th) for _ in range(steps)), dev):
                 net.zero_grad(set_to_none=True)
                 y = net(xd, cd)                                  # the reference-facing call
                 loss = torch.nn.functional.mse_loss(y, td)       # rovr/train_local_net_unet.py:107
                 loss.backward()
-                last = float(loss.detach())                      # D2H read of the step's result
-            return last
+                rb.exchange(loss)            # D2H read of every step's loss, one step behind the enqueue point
+            return rb.drain()
 
         e2e_loop(2)
         ms_e2e = timed(lambda: e2e_loop(args.steps), 1)
@@ -298,14 +298,15 @@ def run_cuda(args, rank, local_rank, world):
         e2e_graph = None
         if graphed is not None:
             def e2e_graph_loop(steps):
-                last = None
+                rb = ScalarReadback(dev, lag=1)
                 for xd, cd, td in DeviceFeeder(((xh, ch, th) for _ in range(steps)), dev):
-                    last = float(graphed(xd, cd, td))
-                return last
+                    rb.exchange(graphed(xd, cd, td))
+                return rb.drain()
             e2e_graph_loop(2)
             ms_g = timed(lambda: e2e_graph_loop(args.steps), 1)
             e2e_graph = {"value": frames / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g / args.steps,
-                         "api": "for batch in DeviceFeeder(pinned_host_batches): float(GraphedTrainingStep(net, ...)(*batch))"}
+                         "api": "rb = ScalarReadback(lag=1); for batch in DeviceFeeder(pinned_host_batches): "
+                                "rb.exchange(GraphedTrainingStep(net, ...)(*batch))"}
 
     if rank != 0:
         if world > 1:
@@ -381,7 +382,8 @@ def run_cuda(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": (xh.numel() + ch.numel() + th.numel()) * 4, "d2h_bytes_per_step": 4,
                     "api": "for frame, context, target in DeviceFeeder(pinned_host_batches): y = LocalNetworkUNetNorm()"
-                           "(frame, context); F.mse_loss(y, target).backward(); float(loss)"},
+                           "(frame, context); loss = F.mse_loss(y, target); loss.backward(); ScalarReadback.exchange(loss)  "
+                           "# every step's loss is read on the host, one step behind the enqueue point"},
             "e2e_graphed_step": e2e_graph,
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
             "clocks": clocks, "roofline": roofline, "kernel_classes": kc,

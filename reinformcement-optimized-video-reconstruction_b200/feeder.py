@@ -54,3 +54,49 @@ class DeviceFeeder:
         torch.cuda.current_stream(self.device).wait_event(ev)
         self._preload()          # the next copy overlaps the compute the caller is about to enqueue
         return dev
+
+
+class ScalarReadback:
+    """Device -> host reads of one scalar per step (the loss), `lag` steps behind the enqueue point.
+
+    `float(loss)` right after `backward()` (rovr/train_local_net_unet.py:117 does `loss.item()`)
+    blocks the host until the step has finished, so the next step's launches only start once the GPU
+    is already idle. `push(loss)` instead enqueues a 4-byte copy into pinned memory behind the step
+    and `pop()` returns the OLDEST outstanding value — the host reads step i's loss while step i+1 is
+    already queued. Every step's value is still read, in order.
+    """
+
+    def __init__(self, device, lag=1):
+        self.host = torch.empty(lag + 1, dtype=torch.float32).pin_memory()
+        self.events = [torch.cuda.Event() for _ in range(lag + 1)]
+        self.device = device
+        self.head = 0      # next slot to write
+        self.tail = 0      # oldest unread slot
+        self.lag = lag
+
+    def __len__(self):
+        return self.head - self.tail
+
+    def push(self, scalar):
+        assert len(self) <= self.lag, "pop() before pushing more than lag + 1 values"
+        k = self.head % (self.lag + 1)
+        self.host[k:k + 1].copy_(scalar.detach().reshape(1), non_blocking=True)
+        self.events[k].record(torch.cuda.current_stream(self.device))
+        self.head += 1
+
+    def pop(self):
+        k = self.tail % (self.lag + 1)
+        self.events[k].synchronize()
+        self.tail += 1
+        return float(self.host[k])
+
+    def exchange(self, scalar):
+        """push(scalar); returns the value that is now `lag` steps old, or None while the pipe fills."""
+        self.push(scalar)
+        return self.pop() if len(self) > self.lag else None
+
+    def drain(self):
+        out = None
+        while len(self):
+            out = self.pop()
+        return out
