@@ -293,6 +293,10 @@ int rovr_softmax_bwd(const float* dp, const void* p, void* ds, long long rows, i
 /* exact GELU on bf16 (F.gelu, rovr/common_layers.py:91) and its gradient */
 int rovr_gelu_fwd(const void* h, void* a, long long n, void* stream);
 int rovr_gelu_bwd(const void* da, const void* h, void* dh, long long n, void* stream);
+/* Tuning knob (no reference counterpart): CTA-pair (cta_group::2, 256-row MMA) launches of the igemm engine.
+ * 0 = never, 1 = where measured to pay (default; env ROVR_PAIR overrides at load), 2 = whenever the shape
+ * allows (even number of 128-pixel tiles, N tile a multiple of 32). Returns the previous mode. */
+int rovr_set_pair_mode(int mode);
 int rovr_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
 /* out = a + b, dense fp32 (residual joins, rovr/common_layers.py:101-102,113-115); n multiple of 4 */
 int rovr_add_f32(const float* a, const float* b, float* out, long long n, void* stream);

@@ -120,6 +120,8 @@ struct IgemmParams {
   // x / d == (umulhi(x, fd_mul) + x) >> fd_shr for x < 2^31. Index 0..3 = ntile[j], 4 = n_tiles_n,
   // 5 = shuf_cout (filled by igemm_dispatch).
   uint32_t fd_mul[6], fd_shr[6];
+  int pair;               // 1: CTA-pair launch (cluster of 2, cta_group::2 MMAs of 256 rows; each CTA stages its own
+                          //    128-row A tile and half of the B tile) — halves the weight traffic L2 -> SM
   int stg_bufs;           // staging tiles per epilogue group: 2 when shared memory allows (the TMA store of a
                           // column block drains while the next block is converted), else 1
 };
@@ -170,7 +172,8 @@ __device__ __forceinline__ uint32_t swz_off(int m, int j, int rowb) {
 // kTail: the fused LocalNet tail (conv7 forward only); kPool: the fused 2x2 max-pool (encoder convs).
 // Each is its own instance so that the plain one keeps its 130-register epilogue — growing it to 141
 // (pool) or 167 (tail) registers measurably slows every thin layer.
-template <bool kPlainEpi, bool kTail = false, bool kPool = false>
+// kPair: CTA-pair variant (see IgemmParams::pair); launched as clusters of two CTAs.
+template <bool kPlainEpi, bool kTail = false, bool kPool = false, bool kPair = false>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmMask,
@@ -182,11 +185,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;   // rank in the CTA pair; 0 = leader (issues the MMAs)
   const int sw = p.bk * 2;  // bytes per operand row == swizzle span
   const int rows = p.boxM[0] * p.boxM[1] * p.boxM[2] * p.boxM[3];
   const bool halo = p.halo != 0;
   const uint32_t a_bytes = halo ? 0u : 128u * sw;  // always reserve the full 128-row tile
-  const uint32_t b_bytes = static_cast<uint32_t>(p.n_tile) * sw;
+  const int nb_rows = kPair ? (p.n_tile >> 1) : p.n_tile;   // B rows staged by this CTA
+  const uint32_t b_bytes = static_cast<uint32_t>(nb_rows) * sw;
   const uint32_t sub_bytes = a_bytes + b_bytes;
   const uint32_t stage_bytes = sub_bytes * p.tps;
   const uint32_t sub_tx = (halo ? 0u : static_cast<uint32_t>(rows) * sw) + b_bytes;
@@ -231,7 +236,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], kPair ? 8 : 4);   // the leader's barrier also collects the peer's four warps
       mbar_init(&mfull_bar[a], 1);
     }
     for (int a = 0; a < IG_MAX_ASLOTS; ++a) {
@@ -241,30 +246,62 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     mbar_init(wfull_bar, 1);
     mbar_fence_init();
   }
-  if (warp == IG_WARP_MMA) tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+  if (warp == IG_WARP_MMA) {
+    if constexpr (kPair) tmem_alloc_pair(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    else tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+  }
   for (int i = threadIdx.x; i < p.n_total; i += IG_THREADS)
     sbias[i] = p.bias ? p.bias[i % p.bias_mod] : 0.f;
   if (kTail && threadIdx.x < 64)   // w8 transposed to [c][k] so that one 16-byte read serves a column
     stail[threadIdx.x] = make_float4(p.tail_w[threadIdx.x], p.tail_w[64 + threadIdx.x], p.tail_w[128 + threadIdx.x], 0.f);
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / complete_tx
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Work items: a CTA walks tiles blockIdx.x, +gridDim.x, ...; a CTA pair walks PAIRS of M tiles
+  // (2 pm + rank, nt) with the same stride in pair units.
+  const int it0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int it_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int total_its = kPair ? (total_tiles >> 1) : total_tiles;
+  auto tile_of = [&](int it) {
+    if constexpr (!kPair) {
+      return it;
+    } else {
+      const int pm = ig_fastdiv(it, p.fd_mul[4], p.fd_shr[4]);
+      return ((pm << 1) + static_cast<int>(crank)) * p.n_tiles_n + (it - pm * p.n_tiles_n);
+    }
+  };
+  // loads: in a pair the bytes of both CTAs are counted on the LEADER's barrier
+  auto expect_tx = [&](uint64_t* bar, uint32_t bytes) {
+    if constexpr (!kPair) mbar_expect_tx(bar, bytes);
+    else if (crank == 0) mbar_expect_tx(bar, 2u * bytes);
+  };
+  auto load_b2 = [&](uint64_t* bar, void* dst, int c0, int c1) {
+    if constexpr (kPair) tma_load_2d_pair(&tmB, leader_addr(bar), dst, c0, c1);
+    else tma_load_2d(&tmB, bar, dst, c0, c1);
+  };
+  auto load_a5 = [&](uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+    if constexpr (kPair) tma_load_5d_pair(&tmA, leader_addr(bar), dst, c0, c1, c2, c3, c4);
+    else tma_load_5d(&tmA, bar, dst, c0, c1, c2, c3, c4);
+  };
+  const int b_row0 = static_cast<int>(crank) * nb_rows;   // this CTA's half of a B tile
 
   if (warp == IG_WARP_TMA) {
     // ================================ TMA producer ================================
     {
       if (p.resident_b) {  // all weight tiles, once: tile index = t * kchunks + kc
         if (elect_one_sync()) {
-          mbar_expect_tx(wfull_bar, static_cast<uint32_t>(k_iters) * b_bytes);
+          expect_tx(wfull_bar, static_cast<uint32_t>(k_iters) * b_bytes);
           for (int it = 0; it < k_iters; ++it)
-            tma_load_2d(&tmB, wfull_bar, smem + static_cast<size_t>(it) * b_bytes, it * p.bk, 0);
+            load_b2(wfull_bar, smem + static_cast<size_t>(it) * b_bytes, it * p.bk, b_row0);
         }
         __syncwarp();
       }
       int s = 0, sa = 0;
       uint32_t ph = 0, pha = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int it = it0; it < total_its; it += it_step) {
+        const int tile = tile_of(it);
         int mt = ig_fastdiv(tile, p.fd_mul[4], p.fd_shr[4]);
         const int nt = tile - mt * p.n_tiles_n;
         int org[4];
@@ -279,9 +316,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait_warp(&aempty_bar[sa], pha ^ 1u, 0x900u + sa);
             if (elect_one_sync()) {
-              mbar_expect_tx(&afull_bar[sa], halo_bytes);
-              tma_load_5d(&tmA, &afull_bar[sa], aring + sa * halo_slot, kc * p.bk, org[0] - 1,
-                          org[1] - 1, org[2], org[3]);
+              expect_tx(&afull_bar[sa], halo_bytes);
+              load_a5(&afull_bar[sa], aring + sa * halo_slot, kc * p.bk, org[0] - 1, org[1] - 1, org[2], org[3]);
             }
             __syncwarp();
             if (++sa == p.a_slots) { sa = 0; pha ^= 1u; }
@@ -290,10 +326,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               mbar_wait_warp(&empty_bar[s], ph ^ 1u, 0x100u + s);
               uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
               if (elect_one_sync()) {
-                mbar_expect_tx(&full_bar[s], b_bytes * nsub);
+                expect_tx(&full_bar[s], b_bytes * nsub);
                 for (int u = 0; u < nsub; ++u)
-                  tma_load_2d(&tmB, &full_bar[s], st + static_cast<size_t>(u) * b_bytes,
-                              (t0 + u) * p.cin + kc * p.bk, nt * p.n_tile);
+                  load_b2(&full_bar[s], st + static_cast<size_t>(u) * b_bytes, (t0 + u) * p.cin + kc * p.bk,
+                          nt * p.n_tile + b_row0);
               }
               __syncwarp();
               if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -306,21 +342,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int nsub = (k_iters - it0) < p.tps ? (k_iters - it0) : p.tps;
           mbar_wait_warp(&empty_bar[s], ph ^ 1u, 0x100u + s);
           uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
-          if (elect_one_sync()) mbar_expect_tx(&full_bar[s], sub_tx * nsub);
+          if (elect_one_sync()) expect_tx(&full_bar[s], sub_tx * nsub);
           for (int u = 0; u < nsub; ++u) {
             const int it = it0 + u;
             const int t = it / kchunks;
             const int kc = it - t * kchunks;
             uint8_t* a_dst = st + static_cast<size_t>(u) * sub_bytes;
             if (elect_one_sync()) {
-              tma_load_5d(&tmA, &full_bar[s], a_dst, kc * p.bk, org[0] + p.tap_off[t][0],
-                          org[1] + p.tap_off[t][1], org[2] + p.tap_off[t][2],
-                          org[3] + p.tap_off[t][3]);
-              if (p.b_batched)
+              load_a5(&full_bar[s], a_dst, kc * p.bk, org[0] + p.tap_off[t][0], org[1] + p.tap_off[t][1],
+                      org[2] + p.tap_off[t][2], org[3] + p.tap_off[t][3]);
+              if (p.b_batched)   // (never combined with a pair launch)
                 tma_load_5d(&tmB, &full_bar[s], a_dst + a_bytes, t * p.cin + kc * p.bk, nt * p.n_tile, org[1],
                             org[2], org[3]);
               else
-                tma_load_2d(&tmB, &full_bar[s], a_dst + a_bytes, t * p.cin + kc * p.bk, nt * p.n_tile);
+                load_b2(&full_bar[s], a_dst + a_bytes, t * p.cin + kc * p.bk, nt * p.n_tile + b_row0);
             }
           }
           __syncwarp();
@@ -328,12 +363,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == IG_WARP_MMA) {
-    // ================================ MMA issuer ==================================
+  } else if (warp == IG_WARP_MMA && (!kPair || crank == 0)) {
+    // ================================ MMA issuer (the leader's, in a pair) ==================================
     // The whole warp walks the pipeline with warp-uniform control flow; waits are done by one
     // lane + __syncwarp, and every (tap, k-chunk) sub-tile is issued by one asm block
     // (umma_tap<KS>) whose elected lane fires KS tcgen05.mma with 32-byte descriptor steps.
-    const uint32_t idesc = umma_idesc_bf16(128, p.n_tile, 0, 0);
+    const uint32_t idesc = umma_idesc_bf16(kPair ? 256 : 128, p.n_tile, 0, 0);
+    auto commit = [&](uint64_t* bar) {
+      if constexpr (kPair) umma_commit_elect_pair(bar);
+      else umma_commit_elect(bar);
+    };
     const uint64_t dkm = umma_smem_desc(0u, 0u, 8u * sw, sw);  // K-major, dense rows
     const uint32_t b_hi = static_cast<uint32_t>(dkm >> 32);
     const uint32_t a_hi_dense = b_hi;
@@ -363,7 +402,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int t = 0; t < 9; ++t) tap_a[t] = static_cast<uint32_t>((t / 3) * (IG_HALO_TW + 2) + (t % 3)) * row16;
       const uint32_t w16 = smem_u32(smem) >> 4;
       const uint32_t stage16 = stage_bytes >> 4;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      auto tap = [&](uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t bh, uint32_t id, uint32_t ac) {
+        if constexpr (kPair) umma_tap_pair<KS>(d, a_lo, a_hi, b_lo, bh, id, ac);
+        else umma_tap<KS>(d, a_lo, a_hi, b_lo, bh, id, ac);
+      };
+      for (int it = it0; it < total_its; it += it_step) {
         mbar_wait_warp(&tempty_bar[acc], aph ^ 1u, 0x200u + acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
@@ -379,7 +422,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               const uint32_t bstep = static_cast<uint32_t>(kchunks) * b16;
 #pragma unroll
               for (int t = 0; t < 9; ++t)
-                umma_tap<KS>(d_tmem, a_slot16 + tap_a[t], a_hi_halo, bd0 + static_cast<uint32_t>(t) * bstep, b_hi, idesc,
+                tap(d_tmem, a_slot16 + tap_a[t], a_hi_halo, bd0 + static_cast<uint32_t>(t) * bstep, b_hi, idesc,
                              t == 0 ? accum : 1u);
             } else {
 #pragma unroll
@@ -389,15 +432,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 const uint32_t bd0 = w16 + static_cast<uint32_t>(s) * stage16;
 #pragma unroll
                 for (int u = 0; u < TPS; ++u)
-                  umma_tap<KS>(d_tmem, a_slot16 + tap_a[t0 + u], a_hi_halo, bd0 + static_cast<uint32_t>(u) * b16, b_hi,
+                  tap(d_tmem, a_slot16 + tap_a[t0 + u], a_hi_halo, bd0 + static_cast<uint32_t>(u) * b16, b_hi,
                                idesc, (t0 + u) == 0 ? accum : 1u);
-                umma_commit_elect(&empty_bar[s]);
+                commit(&empty_bar[s]);
                 __syncwarp();
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
               }
             }
             accum = 1u;
-            umma_commit_elect(&aempty_bar[sa]);  // halo tile consumed by all nine taps
+            commit(&aempty_bar[sa]);  // halo tile consumed by all nine taps
             __syncwarp();
             if (++sa == p.a_slots) { sa = 0; pha ^= 1u; }
           }
@@ -410,15 +453,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const uint32_t st16 = w16 + static_cast<uint32_t>(s) * stage16;
             for (int u = 0; u < nsub; ++u) {
               const uint32_t ad = st16 + static_cast<uint32_t>(u) * sub16;
-              umma_tap<KS>(d_tmem, ad, a_hi_dense, ad + a16, b_hi, idesc, accum);
+              tap(d_tmem, ad, a_hi_dense, ad + a16, b_hi, idesc, accum);
               accum = 1u;
             }
-            umma_commit_elect(&empty_bar[s]);  // frees the slot once these MMAs retire
+            commit(&empty_bar[s]);  // frees the slot once these MMAs retire
             __syncwarp();
             if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
         }
-        umma_commit_elect(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         __syncwarp();
         if (++acc == 2) { acc = 0; aph ^= 1u; }
       }
@@ -432,7 +475,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     else if (p.tps == 9) with_ks(std::integral_constant<int, 9>{});
     else if (p.tps == 3) with_ks(std::integral_constant<int, 3>{});
     else with_ks(std::integral_constant<int, 1>{});
-  } else {
+  } else if (warp < 8) {
     // ================================ epilogue ====================================
     // Two groups of four warps. Group g drains accumulator stage g — every other tile of this
     // CTA — so two tiles are in their epilogue at once (thin-K layers are epilogue-bound).
@@ -554,23 +597,26 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (i < cpr && valid) mreg[i] = __ldg(src + i);
         }
       };
-      const int tstep = 2 * static_cast<int>(gridDim.x);
-      int tile = static_cast<int>(blockIdx.x) + grp * static_cast<int>(gridDim.x);
+      const int istep = 2 * it_step;
+      int it = it0 + grp * it_step;
+      int tile = it < total_its ? tile_of(it) : 0;
       int org[4] = {0, 0, 0, 0};
       bool valid = false;
       long long moff = 0;
       uint4 mreg[8];
       auto tile_nt = [&](int t) { return t - ig_fastdiv(t, p.fd_mul[4], p.fd_shr[4]) * p.n_tiles_n; };
-      if (tile < total_tiles) {
+      if (it < total_its) {
         tile_setup(tile, org, valid, moff);
         if (want_mask && tile_nt(tile) * p.n_tile < p.mask_cols)
           mask_fetch(mreg, valid, moff, tile_nt(tile) * p.n_tile);
       }
       int sbuf = 0;   // staging tile of this group used by the current column block
-      while (tile < total_tiles) {
+      while (it < total_its) {
         const int tile_m = ig_fastdiv(tile, p.fd_mul[4], p.fd_shr[4]);
         const int nt = tile - tile_m * p.n_tiles_n;
-        const int ntile_next = tile + tstep;
+        const int it_next = it + istep;
+        const bool has_next = it_next < total_its;
+        const int ntile_next = has_next ? tile_of(it_next) : 0;
         int org_n[4] = {0, 0, 0, 0};
         bool valid_n = false;
         long long moff_n = 0;
@@ -594,7 +640,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             else bulk_wait_read<0>();
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-          if (cb + 1 == nblk && ntile_next < total_tiles) tile_setup(ntile_next, org_n, valid_n, moff_n);
+          if (cb + 1 == nblk && has_next) tile_setup(ntile_next, org_n, valid_n, moff_n);
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                  static_cast<uint32_t>(acc * p.n_tile + nloc);
           const bool blk_mask = want_mask && nglb < p.mask_cols;   // warp-uniform
@@ -715,7 +761,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (want_mask) {
             if (cb + 1 < nblk) {
               if (nglb + p.cw < p.mask_cols) mask_fetch(mreg, valid, moff, nglb + p.cw);
-            } else if (ntile_next < total_tiles) {
+            } else if (has_next) {
               const int n_next = tile_nt(ntile_next) * p.n_tile;
               if (n_next < p.mask_cols) mask_fetch(mreg, valid_n, moff_n, n_next);
             }
@@ -723,7 +769,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (cb == nblk - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+              if constexpr (kPair) mbar_arrive_cluster(leader_addr(&tempty_bar[acc]));   // the leader's MMA warp waits
+              else mbar_arrive(&tempty_bar[acc]);
+            }
           }
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
@@ -771,6 +820,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         aph ^= 1u;
         tile = ntile_next;
+        it = it_next;
 #pragma unroll
         for (int j = 0; j < 4; ++j) org[j] = org_n[j];
         valid = valid_n;
@@ -781,9 +831,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // the peer's shared memory and TMEM are in use until the leader is done
   if (warp == IG_WARP_MMA) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    if constexpr (kPair) tmem_dealloc_pair(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    else tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
 }
 

@@ -236,6 +236,57 @@ __device__ __forceinline__ void umma_tap<4>(uint32_t d_tmem, uint32_t a_lo, uint
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+template <int KS>
+__device__ __forceinline__ void umma_tap_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                         uint32_t b_hi, uint32_t idesc, uint32_t accumulate);
+template <>
+__device__ __forceinline__ void umma_tap_pair<1>(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                            uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa;\n\t.reg .b64 a0, b0;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %6, 0;\n\t"
+      "mov.b64 a0, {%1, %2};\n\tmov.b64 b0, {%3, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], a0, b0, %5, pa;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void umma_tap_pair<2>(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                            uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 a0, b0, a1, b1;\n\t.reg .b32 l1, m1;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %6, 0;\n\tsetp.eq.u32 pt, 0, 0;\n\t"
+      "add.u32 l1, %1, 2;\n\tadd.u32 m1, %3, 2;\n\t"
+      "mov.b64 a0, {%1, %2};\n\tmov.b64 b0, {%3, %4};\n\t"
+      "mov.b64 a1, {l1, %2};\n\tmov.b64 b1, {m1, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], a0, b0, %5, pa;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %5, pt;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void umma_tap_pair<4>(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                            uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 a0, b0, a1, b1, a2, b2, a3, b3;\n\t"
+      ".reg .b32 l1, l2, l3, m1, m2, m3;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %6, 0;\n\tsetp.eq.u32 pt, 0, 0;\n\t"
+      "add.u32 l1, %1, 2;\n\tadd.u32 l2, %1, 4;\n\tadd.u32 l3, %1, 6;\n\t"
+      "add.u32 m1, %3, 2;\n\tadd.u32 m2, %3, 4;\n\tadd.u32 m3, %3, 6;\n\t"
+      "mov.b64 a0, {%1, %2};\n\tmov.b64 b0, {%3, %4};\n\t"
+      "mov.b64 a1, {l1, %2};\n\tmov.b64 b1, {m1, %4};\n\t"
+      "mov.b64 a2, {l2, %2};\n\tmov.b64 b2, {m2, %4};\n\t"
+      "mov.b64 a3, {l3, %2};\n\tmov.b64 b3, {m3, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], a0, b0, %5, pa;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %5, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %5, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %5, pt;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"
@@ -263,6 +314,64 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA pairs (cta_group::2): two CTAs of a 2-CTA cluster on one TPC execute ONE 256-row MMA. Each CTA
+// stages its own 128 rows of A and HALF of B (N/2 rows); the leader (cluster rank 0) issues the
+// MMA and owns the "data ready" barriers, commits are multicast to both CTAs.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in the cluster's rank-0 CTA
+__device__ __forceinline__ uint32_t leader_addr(const void* p) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(p)));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// pair loads: data into THIS CTA's shared memory, bytes counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t leader_bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(const CUtensorMap* m, uint32_t leader_bar, void* dst, int c0, int c1,
+                                                 int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot_in_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_elect_pair(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t.reg .b16 msk;\n\t"
+      "mov.b16 msk, 3;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], msk;\n\t}" ::"r"(
+          smem_u32(bar))
+      : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -21,6 +21,16 @@ def _dev():
     return torch.device("cuda:0")
 
 
+@pytest.fixture(params=["pair-auto", "pair-always"], autouse=True)
+def pair_mode(request):
+    """Every operator test runs twice: with the default CTA-pair policy and with cta_group::2 launches
+    forced wherever the shape allows, so the 256-row MMA path sees the small / ragged shapes too."""
+    import _native
+    prev = _native.lib.rovr_set_pair_mode(2 if request.param == "pair-always" else 1)
+    yield
+    _native.lib.rovr_set_pair_mode(prev)
+
+
 def _rand_act(shape, gen, dev, scale=1.0, relu=False):
     t = torch.randn(shape, generator=gen, device="cpu") * scale
     if relu:
