@@ -122,6 +122,7 @@ struct IgemmParams {
   uint32_t fd_mul[6], fd_shr[6];
   int pair;               // 1: CTA-pair launch (cluster of 2, cta_group::2 MMAs of 256 rows; each CTA stages its own
                           //    128-row A tile and half of the B tile) — halves the weight traffic L2 -> SM
+  int acc_stages;         // TMEM accumulator stages: 4 when 4 * n_tile <= 512 columns, else 2
   int stg_bufs;           // staging tiles per epilogue group: 2 when shared memory allows (the TMA store of a
                           // column block drains while the next block is converted), else 1
 };
@@ -210,9 +211,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(pstg_base + 2 * p.stg_bufs * pstg_bytes);
   uint64_t* empty_bar = full_bar + IG_MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + IG_MAX_STAGES;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* mfull_bar = tempty_bar + 2;
-  uint64_t* afull_bar = mfull_bar + 2;
+  uint64_t* tempty_bar = tfull_bar + 4;
+  uint64_t* afull_bar = tempty_bar + 4;
   uint64_t* aempty_bar = afull_bar + IG_MAX_ASLOTS;
   uint64_t* wfull_bar = aempty_bar + IG_MAX_ASLOTS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
@@ -234,10 +234,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < 4; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], kPair ? 8 : 4);   // the leader's barrier also collects the peer's four warps
-      mbar_init(&mfull_bar[a], 1);
     }
     for (int a = 0; a < IG_MAX_ASLOTS; ++a) {
       mbar_init(&afull_bar[a], 1);
@@ -463,7 +462,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         __syncwarp();
-        if (++acc == 2) { acc = 0; aph ^= 1u; }
+        if (++acc == p.acc_stages) { acc = 0; aph ^= 1u; }
       }
     };
     auto with_ks = [&](auto tps_tag) {
@@ -497,8 +496,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // pooled-tile row of this lane's 2x2 window: the tile is 8 (x) by 16 (y) pixels, row m = x + 8 y,
     // so the window partners are lanes l ^ 1 (x) and l ^ 8 (y) of the same warp
     const int pm = ((lane & 7) >> 1) + 4 * (quarter * 2 + (lane >> 4));
-    const int acc = grp;
+    // accumulator stages: tile j of this CTA lives in stage j % acc_stages and is drained by group j % 2, so
+    // group g alternates between stages g and g + 2 when four stages fit (N tile <= 128): the MMA warp can
+    // then run two tiles ahead of each group and a group never waits for "its" next accumulator
+    int acc = grp;
     uint32_t aph = 0;
+    auto next_acc = [&]() {
+      acc += 2;
+      if (acc >= p.acc_stages) { acc = grp; aph ^= 1u; }
+    };
     const int cpr = epi_rowb >> 4;        // 16-byte chunks per output row of a block: 8 / 4 / 2
 
     if (p.out_f32 != nullptr) {
@@ -546,7 +552,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        aph ^= 1u;
+        next_acc();
       }
     } else {
       // ---- bf16 epilogue: TMEM -> registers (thread = output row) -> bias / ReLU -> bf16 ->
@@ -818,7 +824,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           sbuf = (p.stg_bufs == 2) ? (sbuf ^ 1) : 0;
         }
-        aph ^= 1u;
+        next_acc();
         tile = ntile_next;
         it = it_next;
 #pragma unroll
@@ -843,7 +849,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 inline size_t igemm_fixed_smem(int cw, int pool2, int n_total, int a_slots = 0, int sw = 128, int stg_bufs = 1) {
   const size_t stg = (128 * static_cast<size_t>(cw) * 2 + (pool2 ? 32 * static_cast<size_t>(cw) * 2 : 0)) * stg_bufs;
   return 2048 + 16 + static_cast<size_t>(a_slots) * ig_halo_slot(sw) + 2 * stg +
-         (2 * IG_MAX_STAGES + 2 * IG_MAX_ASLOTS + 7) * 8 + 16 +
+         (2 * IG_MAX_STAGES + 2 * IG_MAX_ASLOTS + 9) * 8 + 16 +
          static_cast<size_t>(n_total) * 4 + 64 + 64 * 16 + 16;
 }
 inline size_t igemm_stage_bytes(int bk, int n_tile, int tps) {
