@@ -215,9 +215,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* afull_bar = tempty_bar + 4;
   uint64_t* aempty_bar = afull_bar + IG_MAX_ASLOTS;
   uint64_t* wfull_bar = aempty_bar + IG_MAX_ASLOTS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
-  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
-  float4* stail = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(sbias + p.n_total) + 15) & ~uintptr_t(15));
+  // 33 barriers + one pad = 272 bytes: everything after stays 16-byte aligned by construction (pointer
+  // arithmetic only — an integer round trip would make ptxas emit generic instead of shared loads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 2);
+  float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
+  float4* stail = reinterpret_cast<float4*>(sbias + ((p.n_total + 3) & ~3));
 
   const int m_tiles = p.ntile[0] * p.ntile[1] * p.ntile[2] * p.ntile[3];
   const int total_tiles = m_tiles * p.n_tiles_n;
@@ -849,7 +851,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 inline size_t igemm_fixed_smem(int cw, int pool2, int n_total, int a_slots = 0, int sw = 128, int stg_bufs = 1) {
   const size_t stg = (128 * static_cast<size_t>(cw) * 2 + (pool2 ? 32 * static_cast<size_t>(cw) * 2 : 0)) * stg_bufs;
   return 2048 + 16 + static_cast<size_t>(a_slots) * ig_halo_slot(sw) + 2 * stg +
-         (2 * IG_MAX_STAGES + 2 * IG_MAX_ASLOTS + 9) * 8 + 16 +
+         (2 * IG_MAX_STAGES + 2 * IG_MAX_ASLOTS + 10) * 8 + 16 +
          static_cast<size_t>(n_total) * 4 + 64 + 64 * 16 + 16;
 }
 inline size_t igemm_stage_bytes(int bk, int n_tile, int tps) {
