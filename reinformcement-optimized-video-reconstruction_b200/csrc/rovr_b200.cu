@@ -364,18 +364,8 @@ extern "C" int rovr_maxpool_bwd(const void* x, int x_ld, const void* gp, int gp_
     if (int rc = launch_check("maxpool_bwd_tiled")) return rc;
     if (colsum == nullptr) return 0;
     // [blocks][C] -> [chunks][C] -> [C], both stages in a fixed order
-    const int kChunks = 256;
-    if (blocks <= 4 * kChunks) {
-      reduce_rows_kernel<<<(C + 31) / 32, RR_THREADS, 0, st>>>(partial, blocks, C, C, colsum, 0);
-      return launch_check("reduce_rows(pool colsum)");
-    }
-    float* tmp = partial + static_cast<size_t>(blocks) * C;
-    const int rpc = (blocks + kChunks - 1) / kChunks;
-    const int chunks = (blocks + rpc - 1) / rpc;
-    reduce_rows_kernel<<<dim3((C + 31) / 32, chunks), RR_THREADS, 0, st>>>(partial, blocks, C, C, tmp, 0, rpc, C);
-    if (int rc = launch_check("reduce_rows(pool colsum, stage 1)")) return rc;
-    reduce_rows_kernel<<<(C + 31) / 32, RR_THREADS, 0, st>>>(tmp, chunks, C, C, colsum, 0);
-    return launch_check("reduce_rows(pool colsum, stage 2)");
+    launch_reduce_rows(partial, blocks, C, C, colsum, partial + static_cast<size_t>(blocks) * C, st);
+    return launch_check("reduce_rows(pool colsum)");
   }
   ROVR_REQUIRE(gskip == nullptr, "maxpool_bwd: skip gradient only supported for non-overlapping windows");
   ROVR_REQUIRE(colsum == nullptr, "maxpool_bwd: fused column sums only supported for non-overlapping windows");
