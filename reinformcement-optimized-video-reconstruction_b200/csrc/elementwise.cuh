@@ -20,6 +20,8 @@ struct PackSrc {
 };
 __global__ void pack_nchw_to_nhwc_kernel(PackSrc src, __nv_bfloat16* __restrict__ dst, int B,
                                          int HW, int cpad) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(B) * HW) return;
   const int b = static_cast<int>(i / HW);
@@ -230,6 +232,8 @@ maxpool_bwd_2x2_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const __nv
                        int gp_ld, const __nv_bfloat16* __restrict__ gskip, int gs_ld,
                        __nv_bfloat16* __restrict__ gx, int gx_ld, int B, int H, int W, int C, int relu_mask,
                        float* __restrict__ colsum_partial) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float scs[8][32][9];
   const int c8 = C >> 3;
   const int Ho = H >> 1, Wo = W >> 1;
@@ -350,6 +354,8 @@ __global__ void maxpool_bwd_generic_kernel(const __nv_bfloat16* __restrict__ x, 
 // sum a vector of per-block partials in a fixed order -> out[0] = scale * sum
 __global__ void sum_partials_kernel(const float* __restrict__ partial, int n, float scale,
                                     float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sred[32];
   // eight independent accumulators: the loads of a thread are in flight together (one dependent chain
   // of 48 L2 round trips took 24 us for the 49152 partials of a B=24 step); fixed order throughout
@@ -385,6 +391,8 @@ __global__ void __launch_bounds__(RR_THREADS)
 reduce_rows_kernel(const float* __restrict__ partial, int nrows, int row_stride, int ncols,
                    float* __restrict__ out, int accumulate, int rows_per_chunk = 0,
                    int out_stride = 0) {
+  pdl_trigger();
+  pdl_wait();
   // blockIdx.y selects a chunk of rows (two-stage reduction of very tall partial buffers);
   // with gridDim.y == 1 the whole buffer is reduced straight into `out`.
   __shared__ float sred[RR_GROUPS][33];
@@ -422,15 +430,17 @@ constexpr int RR_MAX_CHUNKS = 128;
 inline void launch_reduce_rows(const float* partial, int nrows, int row_stride, int ncols, float* out, float* tmp,
                                cudaStream_t st) {
   if (nrows <= 2048 || tmp == nullptr) {
-    reduce_rows_kernel<<<(ncols + 31) / 32, RR_THREADS, 0, st>>>(partial, nrows, row_stride, ncols, out, 0);
+    launch_chain(reduce_rows_kernel, dim3((ncols + 31) / 32), dim3(RR_THREADS), 0, st, 1, partial, nrows, row_stride, ncols,
+                 out, 0, 0, 0);
     return;
   }
   int rpc = (nrows + RR_MAX_CHUNKS - 1) / RR_MAX_CHUNKS;
   if (rpc < 256) rpc = 256;
   const int chunks = (nrows + rpc - 1) / rpc;
-  reduce_rows_kernel<<<dim3((ncols + 31) / 32, chunks), RR_THREADS, 0, st>>>(partial, nrows, row_stride, ncols, tmp, 0,
-                                                                         rpc, row_stride);
-  reduce_rows_kernel<<<(ncols + 31) / 32, RR_THREADS, 0, st>>>(tmp, chunks, row_stride, ncols, out, 0);
+  launch_chain(reduce_rows_kernel, dim3((ncols + 31) / 32, chunks), dim3(RR_THREADS), 0, st, 1, partial, nrows, row_stride,
+               ncols, tmp, 0, rpc, row_stride);
+  launch_chain(reduce_rows_kernel, dim3((ncols + 31) / 32), dim3(RR_THREADS), 0, st, 1, tmp, chunks, row_stride, ncols, out,
+               0, 0, 0);
 }
 
 // ---------------------------------------------------------------------------------------------

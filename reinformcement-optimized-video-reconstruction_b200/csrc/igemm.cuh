@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmMask,
              const IgemmParams p) {
+  pdl_trigger();   // the next launch may start filling SMs as this grid's CTAs retire
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is what SWIZZLE_128B tiles need.
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -251,6 +252,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if constexpr (kPair) tmem_alloc_pair(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
     else tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
   }
+  pdl_wait();      // everything above is private to this CTA; from here on global memory is read
   for (int i = threadIdx.x; i < p.n_total; i += IG_THREADS)
     sbias[i] = p.bias ? p.bias[i % p.bias_mod] : 0.f;
   if (kTail && threadIdx.x < 64)   // w8 transposed to [c][k] so that one 16-byte read serves a column

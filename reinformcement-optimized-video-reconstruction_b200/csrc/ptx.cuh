@@ -7,6 +7,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace rovr {
 
@@ -35,6 +37,50 @@ __device__ __forceinline__ bool elect_one_sync() {
 // becomes a kernel that finishes with wrong results plus a non-zero rovr_hang_code(), instead of
 // a GPU that has to be reset.
 __device__ unsigned int g_rovr_hang_code = 0;
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch. A kernel of the LocalNet step calls pdl_trigger() first thing, which lets
+// the NEXT launch on the stream (made with launch_chain() below) place its CTAs on SMs as soon as they
+// free up, and run its prologue (barrier init, TMEM allocation, descriptor prefetch) while this grid is
+// still draining. pdl_wait() returns once every grid launched before has completed and flushed; nothing
+// before it may touch global memory. Both are no-ops in a launch without the attribute.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline int pdl_mode() {   // ROVR_PDL=0: plain stream-ordered launches (A/B experiments)
+  static const int v = [] { const char* e = getenv("ROVR_PDL"); return e ? atoi(e) : 1; }();
+  return v;
+}
+// Launch `kernel` behind the previous launch of the stream with programmatic stream serialisation, optionally
+// as clusters of `cluster_x` CTAs. Argument types are converted to the kernel's parameter types.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (pdl_mode()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = static_cast<unsigned>(cluster_x);
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier

@@ -250,9 +250,8 @@ extern "C" int rovr_pack_nchw_to_nhwc(const float* s0, int c0, const float* s1, 
     }
   ROVR_REQUIRE(tot <= cpad, "pack: %d source channels exceed cpad %d", tot, cpad);
   const long long n = 1ll * B * H * W;
-  pack_nchw_to_nhwc_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0,
-                             static_cast<cudaStream_t>(stream)>>>(
-      src, static_cast<__nv_bfloat16*>(dst), B, H * W, cpad);
+  launch_chain(pack_nchw_to_nhwc_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0,
+               static_cast<cudaStream_t>(stream), 1, src, static_cast<__nv_bfloat16*>(dst), B, H * W, cpad);
   return launch_check("pack_nchw_to_nhwc");
 }
 extern "C" int rovr_unpack_nhwc_to_nchw(const void* src, int ld, float* dst, int B, int H, int W,
@@ -352,10 +351,10 @@ extern "C" int rovr_maxpool_bwd(const void* x, int x_ld, const void* gp, int gp_
     }
     if (kh == 2 && kw == 2 && (C / 8 <= 32) && 256 % (C / 8) == 0) {
       blocks = std::min(blocks, 8 * g_dev.sms);
-      maxpool_bwd_2x2_kernel<<<blocks, 256, 0, st>>>(
-          static_cast<const __nv_bfloat16*>(x), x_ld, static_cast<const __nv_bfloat16*>(gp), gp_ld,
-          static_cast<const __nv_bfloat16*>(gskip), gs_ld, static_cast<__nv_bfloat16*>(gx), gx_ld, B, H, W, C,
-          relu_mask, partial);
+      launch_chain(maxpool_bwd_2x2_kernel, dim3(blocks), dim3(256), 0, st, 1,
+                   static_cast<const __nv_bfloat16*>(x), x_ld, static_cast<const __nv_bfloat16*>(gp), gp_ld,
+                   static_cast<const __nv_bfloat16*>(gskip), gs_ld, static_cast<__nv_bfloat16*>(gx), gx_ld, B, H, W, C,
+                   relu_mask, partial);
     } else
     maxpool_bwd_tiled_kernel<<<blocks, 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(x), x_ld, static_cast<const __nv_bfloat16*>(gp), gp_ld,

@@ -103,6 +103,8 @@ tail_bwd_kernel(const __nv_bfloat16* __restrict__ y7, const float* __restrict__ 
                 const float* __restrict__ target, float mse_scale,
                 const float* __restrict__ gloss, __nv_bfloat16* __restrict__ g7,
                 float* __restrict__ partial, int B, int HW) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sacc[TAILB_COLS];
   for (int i = threadIdx.x; i < TAILB_COLS; i += blockDim.x) sacc[i] = 0.f;
   const float lscale = mse_scale * (gloss ? __ldg(gloss) : 1.f);
@@ -211,6 +213,8 @@ tail_bwd_kernel(const __nv_bfloat16* __restrict__ y7, const float* __restrict__ 
 __global__ void __launch_bounds__(1024)
 tail_reduce_kernel(const float* __restrict__ partial, int nrows, float* __restrict__ dw8,
                    float* __restrict__ db8, float* __restrict__ db7) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sred[32][33];
   const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + cl;

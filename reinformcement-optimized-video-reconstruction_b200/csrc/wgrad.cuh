@@ -53,6 +53,7 @@ struct WgradParams {
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const WgradParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5;
@@ -108,6 +109,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -234,6 +236,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
                                     int n_slices, int m_total, int taps, int c_total, int m_keep,
                                     int c_keep, long long fs_m, long long fs_t, long long fs_c,
                                     int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   const long long n = static_cast<long long>(m_total) * taps * c_total;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -266,6 +270,8 @@ __global__ void wgrad_reduce_tall_kernel(const float* __restrict__ partial, floa
                                     int n_slices, int m_total, int taps, int c_total, int m_keep,
                                     int c_keep, long long fs_m, long long fs_t, long long fs_c,
                                     int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float part[WGR_MAX_NY][33];
   const long long n = static_cast<long long>(m_total) * taps * c_total;
   const long long i = static_cast<long long>(blockIdx.x) * 32 + threadIdx.x;
@@ -299,10 +305,10 @@ inline void launch_wgrad_reduce(const float* partial, float* grad, int n_slices,
   const long long n = static_cast<long long>(m_total) * taps * c_total;
   // measured: the slice-parallel kernel only wins when the element count is too small to fill the GPU
   if (n_slices >= 24 && n <= 32768) {
-    wgrad_reduce_tall_kernel<<<static_cast<unsigned>((n + 31) / 32), dim3(32, WGR_MAX_NY), 0, st>>>(
+    launch_chain(wgrad_reduce_tall_kernel, dim3(static_cast<unsigned>((n + 31) / 32)), dim3(32, WGR_MAX_NY), 0, st, 1,
         partial, grad, n_slices, m_total, taps, c_total, m_keep, c_keep, fs_m, fs_t, fs_c, accumulate);
   } else {
-    wgrad_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+    launch_chain(wgrad_reduce_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, 1,
         partial, grad, n_slices, m_total, taps, c_total, m_keep, c_keep, fs_m, fs_t, fs_c, accumulate);
   }
 }

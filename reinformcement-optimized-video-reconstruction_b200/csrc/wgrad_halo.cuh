@@ -64,6 +64,7 @@ __device__ __forceinline__ void umma_mn_x4(uint32_t d_tmem, uint32_t a_lo, uint3
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const WgradHaloParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5;
@@ -118,6 +119,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
