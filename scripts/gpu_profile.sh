@@ -10,4 +10,7 @@ echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:igemm_kernel -s 57 -c 19 -f -o gpurun_out/prof_igemm $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full rc=$?"
 tail -3 gpurun_out/ncu_full.log
+# the report itself can exceed what gpurun copies back (64 MiB): keep the CSV pages, drop the report
+ncu -i gpurun_out/prof_igemm.ncu-rep --page raw --csv > gpurun_out/prof_igemm_raw.csv 2>/dev/null
+[ "$(stat -c %s gpurun_out/prof_igemm.ncu-rep)" -gt 40000000 ] && rm -f gpurun_out/prof_igemm.ncu-rep
 ls -la gpurun_out
