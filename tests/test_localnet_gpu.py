@@ -267,6 +267,36 @@ def test_graphed_training_step_matches_eager():
     assert torch.equal(lc, ld) and not torch.equal(lc, lb)
 
 
+def test_feeder_and_lagged_loss_readback():
+    """DeviceFeeder (double-buffered pinned-host -> device copies) + ScalarReadback (every step's loss
+    read one step behind the enqueue point): five different batches give, in order, exactly the losses
+    of five blocking eager steps — no batch is overwritten while a step still reads it."""
+    from local_net import LocalNetworkUNetNorm
+    from feeder import DeviceFeeder, ScalarReadback
+    import _native
+    import rovr_oracle as O
+    _native.require_device()
+    dev = torch.device("cuda:0")
+    net = LocalNetworkUNetNorm()
+    net.load_state_dict(O.localnet_state_dict(0), strict=True)
+    net = net.to(dev)
+    host = [tuple(v.pin_memory() for v in O.synthetic_localnet_batch(2, 32, 32, seed=20 + i)) for i in range(5)]
+    want = []
+    for xh, ch, th in host:
+        _, loss = net.forward_with_mse(xh.to(dev), ch.to(dev), th.to(dev))
+        want.append(float(loss))
+    assert len(set(want)) == 5
+    rb = ScalarReadback(dev, lag=1)
+    got = []
+    for xd, cd, td in DeviceFeeder(iter(host), dev):
+        _, loss = net.forward_with_mse(xd, cd, td)
+        v = rb.exchange(loss)
+        if v is not None:
+            got.append(v)
+    got.append(rb.drain())
+    assert got == want, (got, want)
+
+
 @pytest.mark.parametrize("shape", [(1, 8, 8), (3, 24, 40), (5, 16, 72), (2, 8, 136), (1, 200, 8)])
 def test_localnet_ragged_shapes_vs_oracle(shape):
     """Odd batch sizes and H, W that are multiples of 8 but not of the kernel tiles (8 x 16 pixel
