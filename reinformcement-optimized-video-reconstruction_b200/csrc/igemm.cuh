@@ -21,13 +21,15 @@
 //             land in the 128/64/32-byte swizzled K-major layout tcgen05.mma reads directly. A
 //             pipeline stage holds `tps` (tap, k-chunk) sub-tiles so that thin layers (Cin = 16)
 //             still move tens of KB per barrier round trip.
-//   compute : accumulators live in TMEM (2 stages x n_tile fp32 columns): the epilogue of tile i
-//             overlaps the main loop of tile i+1.
+//   compute : accumulators live in TMEM (2 or 4 stages x n_tile fp32 columns): the epilogues of
+//             tiles i and i+1 overlap the main loops of the tiles after them.
 //   stores  : the epilogue converts 64-channel column blocks to bf16 into a swizzled smem staging
 //             tile and a TMA store (cp.async.bulk.tensor...global.shared::cta) writes it out, so
 //             global writes are full 128-byte lines and ragged tiles are clipped by the TMA unit.
-//             The ReLU mask of dgrad (the forward activation at the same coordinates) is
-//             prefetched by TMA into smem the same way.
+//             The ReLU mask of dgrad (the forward activation at the same coordinates) is read
+//             from global memory by the thread that owns the row, one column block ahead.
+//   pairs   : optionally two CTAs of a cluster (one TPC) run ONE 256-row cta_group::2 MMA per
+//             step, each staging its own 128 pixels and half of the weight tile (kPair).
 //
 // Warp roles (320 threads): warps 0..7 = two epilogue groups, warp 8 = TMA producer,
 // warp 9 = TMEM owner + MMA issuer.
@@ -84,7 +86,6 @@ struct IgemmParams {
   int epi_mode;
   int cw;                 // epilogue column-block width: 16 / 32 / 64 channels
   int relu;
-  int has_mask;
   int pool2;              // 1 (halo mode, plain epilogue): also emit the 2x2 max-pooled tile (4 x 8 pixels) through
                           //    the fourth tensor map — nn.MaxPool2d(2, 2) of the encoder fused into the conv
   // Fused LocalNet tail (conv7 forward only: n_tile == cw == 64): out[b][k][pixel] = sigmoid(b8[k] +
@@ -480,15 +481,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     else with_ks(std::integral_constant<int, 1>{});
   } else if (warp < 8) {
     // ================================ epilogue ====================================
-    // Two groups of four warps. Group g drains accumulator stage g — every other tile of this
-    // CTA — so two tiles are in their epilogue at once (thin-K layers are epilogue-bound).
-    //   pass 1: TMEM -> registers (thread = output row) -> bias / ReLU -> bf16 -> swizzled smem;
-    //   pass 2 (dgrad only): each warp re-reads its 32 staged rows with a coalescing-friendly
-    //           mapping (one 16-byte chunk per lane, 32/cpr rows per instruction), applies the ReLU
-    //           mask fetched from global memory with the same mapping (full 128-byte lines,
-    //           prefetched into registers before the accumulator is even ready) and accumulates
-    //           the per-column sums that become the bias gradient;
-    //   then one TMA store per 64-channel block (ragged tiles are clipped by the TMA unit).
+    // Two groups of four warps. Group g drains every other tile of this CTA, so two tiles are in
+    // their epilogue at once (thin-K layers are epilogue-bound). Per 64-channel column block:
+    // TMEM -> registers (thread = output row) -> bias / ReLU / ReLU mask -> bf16 -> swizzled
+    // staging tile -> one TMA store (ragged tiles are clipped by the TMA unit); the fused bias
+    // gradient reads its column sums back from the staging tile.
     const int grp = warp >> 2;
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
@@ -563,9 +560,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // [ReLU mask of dgrad] -> swizzled smem -> TMA store, one 64-channel block at a time.
       // The mask is read straight from global memory by the thread that owns the row (16-byte
       // loads of its own 128-byte channel segment, issued one block ahead so their latency hides
-      // behind the previous block) and applied on the packed bf16 pairs. The fused bias gradient
-      // (column sums of the stored values) is a reduce-scatter across the 32 rows of the warp done
-      // with shuffles, 16 columns at a time. Nothing is re-read from shared memory.
+      // behind the previous block) and applied on the packed bf16 pairs.
       int lrow[4];
       {
         int mm = m;
