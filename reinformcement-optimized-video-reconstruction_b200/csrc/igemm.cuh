@@ -645,7 +645,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             else bulk_wait_read<0>();
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-          if (cb + 1 == nblk && has_next) tile_setup(ntile_next, org_n, valid_n, moff_n);
+          if (cb == 0 && has_next) tile_setup(ntile_next, org_n, valid_n, moff_n);
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                  static_cast<uint32_t>(acc * p.n_tile + nloc);
           const bool blk_mask = want_mask && nglb < p.mask_cols;   // warp-uniform
@@ -760,13 +760,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               if (lane == 0) p.tail_loss_partial[static_cast<long long>(tile_m) * 4 + quarter] = se;
             }
           }
-          // mask of the NEXT column block (possibly of the next tile), straight into the registers
-          // this block has just finished with: the loads fly during the store hand-off below and the
-          // next block's TMEM fetch
+          // mask of the NEXT MASKED column block, straight into the registers this block has just finished
+          // with: the next block of this tile if it is masked, else — as soon as the tile's last masked block
+          // is converted, not at the end of the tile — the first block of the next tile. With only the up-conv
+          // half of a concat gradient masked (conv7 dgrad) the loads get a whole unmasked block more to land.
           if (want_mask) {
-            if (cb + 1 < nblk) {
-              if (nglb + p.cw < p.mask_cols) mask_fetch(mreg, valid, moff, nglb + p.cw);
-            } else if (has_next) {
+            const bool more_here = cb + 1 < nblk && nglb + p.cw < p.mask_cols;
+            const bool last_masked_here = blk_mask ? !more_here : (cb == 0);   // cb == 0: tile without masked blocks
+            if (more_here) {
+              mask_fetch(mreg, valid, moff, nglb + p.cw);
+            } else if (last_masked_here && has_next) {
               const int n_next = tile_nt(ntile_next) * p.n_tile;
               if (n_next < p.mask_cols) mask_fetch(mreg, valid_n, moff_n, n_next);
             }
