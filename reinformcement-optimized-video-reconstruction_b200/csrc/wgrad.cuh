@@ -235,7 +235,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad,
                                     int n_slices, int m_total, int taps, int c_total, int m_keep,
                                     int c_keep, long long fs_m, long long fs_t, long long fs_c,
-                                    int accumulate) {
+                                    int accumulate, int tap_split, int n_slices_hi) {
   pdl_trigger();
   pdl_wait();
   const long long n = static_cast<long long>(m_total) * taps * c_total;
@@ -245,6 +245,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   const int t = static_cast<int>((i / c_total) % taps);
   const int m = static_cast<int>(i / (static_cast<long long>(c_total) * taps));
   if (c >= c_keep || m >= m_keep) return;
+  if (t >= tap_split) n_slices = n_slices_hi;   // tap groups with their own number of pixel slices (6 + 3 taps)
   // four independent partial sums keep four loads in flight (slices are ~100s of KB apart); the
   // combination order is fixed, so the result stays bitwise reproducible
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -338,8 +339,13 @@ wgrad_reduce_tiled_kernel(const float* __restrict__ partial, float* __restrict__
 
 inline void launch_wgrad_reduce(const float* partial, float* grad, int n_slices, int m_total, int taps, int c_total,
                                 int m_keep, int c_keep, long long fs_m, long long fs_t, long long fs_c, int accumulate,
-                                cudaStream_t st) {
+                                cudaStream_t st, int tap_split = 1 << 30, int n_slices_hi = 0) {
   const long long n = static_cast<long long>(m_total) * taps * c_total;
+  if (tap_split < taps) {   // per-tap-group slice counts: only the element-per-thread kernel knows them
+    launch_chain(wgrad_reduce_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, 1, partial, grad,
+                 n_slices, m_total, taps, c_total, m_keep, c_keep, fs_m, fs_t, fs_c, accumulate, tap_split, n_slices_hi);
+    return;
+  }
   if (fs_t == 1 && fs_c == taps && taps > 1 && taps <= WGR_MAX_TAPS && n_slices <= 32) {   // (more slices: measured slower)
     launch_chain(wgrad_reduce_tiled_kernel, dim3((c_total + 31) / 32, m_total), dim3(32 * taps), 0, st, 1, partial, grad,
                  n_slices, m_total, taps, c_total, m_keep, c_keep, fs_m, accumulate);
@@ -351,7 +357,7 @@ inline void launch_wgrad_reduce(const float* partial, float* grad, int n_slices,
         partial, grad, n_slices, m_total, taps, c_total, m_keep, c_keep, fs_m, fs_t, fs_c, accumulate);
   } else {
     launch_chain(wgrad_reduce_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, 1,
-        partial, grad, n_slices, m_total, taps, c_total, m_keep, c_keep, fs_m, fs_t, fs_c, accumulate);
+        partial, grad, n_slices, m_total, taps, c_total, m_keep, c_keep, fs_m, fs_t, fs_c, accumulate, 1 << 30, 0);
   }
 }
 

@@ -34,7 +34,9 @@ struct WgradHaloParams {
   int taps_first[3], taps_count[3], tap_groups;  // taps handled by tap group g
   int tap_sign;            // +1: B read at p + (dy, dx);  -1: at p - (dy, dx)   (operand swap)
   int c_total, c_blocks_per_group, c_groups;
-  int n_slices, k_tiles, stages, tmem_cols;
+  int n_slices, k_tiles, stages, tmem_cols;   // n_slices = max over tap groups (slice stride of `partial`)
+  int slices_g[3], slice_base[3], slices_total;   // pixel slices per tap group (groups with more taps per CTA
+                                                  // get more CTAs), first CTA index of each group, their sum
   float* partial;          // [n_slices][m_total][9][c_total]
 };
 
@@ -84,15 +86,17 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
 
   int g = blockIdx.x;
-  const int slice = g % p.n_slices;
-  g /= p.n_slices;
+  const int sidx = g % p.slices_total;
+  g /= p.slices_total;
   const int cg = g % p.c_groups;
   g /= p.c_groups;
-  const int tg = g % p.tap_groups;
-  g /= p.tap_groups;
   const int mc = g;
-  const int kt0 = static_cast<int>((static_cast<long long>(p.k_tiles) * slice) / p.n_slices);
-  const int kt1 = static_cast<int>((static_cast<long long>(p.k_tiles) * (slice + 1)) / p.n_slices);
+  int tg = 0;
+  while (tg + 1 < p.tap_groups && sidx >= p.slice_base[tg + 1]) ++tg;
+  const int slice = sidx - p.slice_base[tg];
+  const int nsl = p.slices_g[tg];
+  const int kt0 = static_cast<int>((static_cast<long long>(p.k_tiles) * slice) / nsl);
+  const int kt1 = static_cast<int>((static_cast<long long>(p.k_tiles) * (slice + 1)) / nsl);
   const int t_first = p.taps_first[tg], t_count = p.taps_count[tg];
   const int ncol = p.c_blocks_per_group * p.blk_b;  // columns per tap
   // whole kernel rows of a single-block operand: the three dx taps of a row run as one MMA (see below)
@@ -207,6 +211,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     };
     switch (t_count) {
       case 9: run(std::integral_constant<int, 9>{}); break;
+      case 6: run(std::integral_constant<int, 6>{}); break;
       case 5: run(std::integral_constant<int, 5>{}); break;
       case 4: run(std::integral_constant<int, 4>{}); break;
       default: run(std::integral_constant<int, 3>{}); break;
