@@ -54,6 +54,16 @@ int rovr_repack_convT2x2_fprop(const float* w, void* wk, int Cin, int Cout, void
 /* ConvTranspose2d 2x2 weight -> [Cin][4*Cout] */
 int rovr_repack_convT2x2_dgrad(const float* w, void* wk, int Cin, int Cout, void* stream);
 
+/* Every weight tensor of a network re-packed by ONE launch (after an optimizer step; same layouts as the
+ * single calls above). kind: 0 = Conv2d 3x3 forward operand (a = Cout, b = Cin, c = cin_pad), 1 = Conv2d 3x3
+ * data-gradient operand (same), 2 = ConvTranspose2d 2x2 forward operand (a = Cin, b = Cout), 3 = its
+ * data-gradient operand (same). n <= 40. */
+typedef struct rovr_repack_item {
+  const float* w;
+  void* wk;
+  int kind, a, b, c;
+} rovr_repack_item;
+int rovr_repack_batch(const rovr_repack_item* items, int n, void* stream);
 /* nn.Linear / Conv2d 1x1 weight [N][K] -> bf16 [n_pad][k_pad], or transposed [k_pad][n_pad] */
 int rovr_repack_linear(const float* w, void* wk, int N, int K, int n_pad, int k_pad, int transpose,
                        void* stream);

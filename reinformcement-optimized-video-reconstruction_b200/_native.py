@@ -37,6 +37,7 @@ SIGNATURES = {
     "rovr_repack_convT2x2_fprop": (_i, [_p, _p, _i, _i, _p]),
     "rovr_repack_convT2x2_dgrad": (_i, [_p, _p, _i, _i, _p]),
     "rovr_repack_linear": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "rovr_repack_batch": (_i, [_p, _i, _p]),
     "rovr_gemm_wgrad_workspace": (_sz, [_ll, _i, _i]),
     "rovr_gemm_wgrad": (_i, [_p, _i, _p, _i, _p, _ll, _i, _i, _i, _i, _p, _sz, _p]),
     "rovr_conv3x3_fprop": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),

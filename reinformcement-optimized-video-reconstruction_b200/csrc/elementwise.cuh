@@ -525,4 +525,36 @@ __global__ void repack_weights_kernel(const float* __restrict__ src, __nv_bfloat
   dst[i] = __float2bfloat16_rn(v);
 }
 
+// The same for up to REPACK_MAX weight tensors in ONE launch (all layers of a network after an optimizer
+// step): entry e covers flat output elements [start_e, start_{e+1}).
+constexpr int REPACK_MAX = 40;
+struct RepackEntry {
+  const float* src;
+  __nv_bfloat16* dst;
+  long long s0, s1, s2, start;
+  int d0, d1, d2, v0, v2, pad;
+};
+struct RepackTable {
+  int n;
+  int pad;
+  long long total;
+  RepackEntry e[REPACK_MAX];
+};
+__global__ void repack_batch_kernel(const __grid_constant__ RepackTable tab) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= tab.total) return;
+  int e = 0;
+  while (e + 1 < tab.n && i >= tab.e[e + 1].start) ++e;
+  const RepackEntry& t = tab.e[e];
+  const long long k = i - t.start;
+  const int i2 = static_cast<int>(k % t.d2);
+  const int i1 = static_cast<int>((k / t.d2) % t.d1);
+  const int i0 = static_cast<int>(k / (static_cast<long long>(t.d1) * t.d2));
+  float v = 0.f;
+  if (i2 < t.v2 && i0 < t.v0) v = t.src[i0 * t.s0 + i1 * t.s1 + i2 * t.s2];
+  t.dst[k] = __float2bfloat16_rn(v);
+}
+
 }  // namespace rovr

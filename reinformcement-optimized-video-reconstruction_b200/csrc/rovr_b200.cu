@@ -294,6 +294,38 @@ extern "C" int rovr_repack_convT2x2_dgrad(const float* w, void* wk, int Cin, int
   return repack(w, wk, Cin, 4, Cout, 1ll * Cout * 4, 1, 4, Cin, Cout, stream);
 }
 
+// All weight tensors of a network in one launch. kind: 0 = Conv2d 3x3 forward operand (a = Cout, b = Cin,
+// c = cin_pad), 1 = Conv2d 3x3 data-gradient operand (same), 2 = ConvTranspose2d 2x2 forward operand
+// (a = Cin, b = Cout), 3 = ConvTranspose2d 2x2 data-gradient operand (same); layouts as the single calls above.
+extern "C" int rovr_repack_batch(const rovr_repack_item* items, int n, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  ROVR_REQUIRE(n >= 1 && n <= REPACK_MAX, "repack_batch: %d items (max %d)", n, REPACK_MAX);
+  RepackTable tab;
+  memset(&tab, 0, sizeof(tab));
+  tab.n = n;
+  long long start = 0;
+  for (int i = 0; i < n; ++i) {
+    const rovr_repack_item& it = items[i];
+    RepackEntry& e = tab.e[i];
+    e.src = it.w;
+    e.dst = static_cast<__nv_bfloat16*>(it.wk);
+    switch (it.kind) {
+      case 0: e.d0 = it.a; e.d1 = 9; e.d2 = it.c; e.s0 = 9ll * it.b; e.s1 = 1; e.s2 = 9; e.v0 = it.a; e.v2 = it.b; break;
+      case 1: e.d0 = it.c; e.d1 = 9; e.d2 = it.a; e.s0 = 9; e.s1 = -1; e.s2 = 9ll * it.b; e.v0 = it.b; e.v2 = it.a;
+              e.src += 8; break;
+      case 2: e.d0 = 4; e.d1 = it.b; e.d2 = it.a; e.s0 = 1; e.s1 = 4; e.s2 = 4ll * it.b; e.v0 = 4; e.v2 = it.a; break;
+      case 3: e.d0 = it.a; e.d1 = 4; e.d2 = it.b; e.s0 = 4ll * it.b; e.s1 = 1; e.s2 = 4; e.v0 = it.a; e.v2 = it.b; break;
+      default: return fail(-2, "repack_batch: unknown kind %d", it.kind);
+    }
+    e.start = start;
+    start += 1ll * e.d0 * e.d1 * e.d2;
+  }
+  tab.total = start;
+  launch_chain(repack_batch_kernel, dim3(static_cast<unsigned>((start + 255) / 256)), dim3(256), 0,
+               static_cast<cudaStream_t>(stream), 1, tab);
+  return launch_check("repack_batch");
+}
+
 // nn.Linear / 1x1-conv weight [N][K] fp32 -> bf16 [n_pad][k_pad] (transpose = 0) or its transpose
 // [k_pad][n_pad] (transpose = 1, the operand of the data gradient), zero padded.
 extern "C" int rovr_repack_linear(const float* w, void* wk, int N, int K, int n_pad, int k_pad,

@@ -60,6 +60,23 @@ class _PackedWeights:
         self._cache[key] = (ver, wk)
         return wk
 
+    def refresh(self, layers, with_dgrad):
+        """layers: [(name, param, kind)]. Re-packs every stale operand copy (forward operands, and the
+        data-gradient operands of all layers but the first when `with_dgrad`) with ONE launch, so that
+        the per-layer get() calls of the step only hit the cache."""
+        todo = []
+        for i, (name, param, kind) in enumerate(layers):
+            ver = (param.data_ptr(), param._version)
+            for for_dgrad in ((False, True) if (with_dgrad and i > 0) else (False,)):
+                hit = self._cache.get((name, for_dgrad))
+                if hit is None or hit[0] != ver:
+                    todo.append((name, for_dgrad, ver, param.detach(), kind))
+        if not todo:
+            return
+        outs = ops.repack_batch([(w, kind, fd) for _, fd, _, w, kind in todo])
+        for (name, fd, ver, _, _), wk in zip(todo, outs):
+            self._cache[(name, fd)] = (ver, wk)
+
 
 def _flat_bucket(params, names, device):
     """One flat fp32 buffer holding weight+bias grads of `names`; returns (flat, {pname: view})."""
@@ -84,6 +101,8 @@ class _LocalNetFunction(torch.autograd.Function):
         B, _, H, W = x.shape
         bf = torch.bfloat16
         pk = net._packed
+        # all stale bf16 operand copies (forward and, if a backward will follow, data-gradient) in one launch
+        pk.refresh([(n, P[n + ".weight"], k) for n, k, _, _ in _LAYERS if k != "bn"], any(ctx.needs_input_grad))
 
         def wk(name, kind="conv"):
             return pk.get(name, P[name + ".weight"], kind, False)

@@ -138,6 +138,35 @@ def repack_convT2x2(w, for_dgrad=False):
     return wk
 
 
+class _RepackItem(ctypes.Structure):
+    _fields_ = [("w", ctypes.c_void_p), ("wk", ctypes.c_void_p), ("kind", ctypes.c_int), ("a", ctypes.c_int),
+                ("b", ctypes.c_int), ("c", ctypes.c_int)]
+
+
+def repack_batch(requests):
+    """requests: list of (w, kind, for_dgrad) with kind "conv" (Conv2d 3x3) or "up" (ConvTranspose2d 2x2).
+    Returns the bf16 operand copies, all written by ONE kernel launch (rovr_repack_batch)."""
+    assert 1 <= len(requests) <= 40
+    items = (_RepackItem * len(requests))()
+    outs = []
+    for it, (w, kind, for_dgrad) in zip(items, requests):
+        _f32(w, "weight")
+        if kind == "up":
+            Cin, Cout = w.shape[0], w.shape[1]
+            shape = (Cin, 4 * Cout) if for_dgrad else (4 * Cout, Cin)
+            it.kind, it.a, it.b, it.c = (3 if for_dgrad else 2), Cin, Cout, 0
+        else:
+            Cout, Cin = w.shape[0], w.shape[1]
+            cin_pad = pad16(Cin)
+            shape = (cin_pad, 9 * Cout) if for_dgrad else (Cout, 9 * cin_pad)
+            it.kind, it.a, it.b, it.c = (1 if for_dgrad else 0), Cout, Cin, cin_pad
+        wk = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
+        it.w, it.wk = _ptr(w), _ptr(wk)
+        outs.append(wk)
+    _launch("rovr_repack_batch", ctypes.cast(items, ctypes.c_void_p), len(requests), _stream())
+    return outs
+
+
 # ---------------------------------------------------------------------------------------------
 # Conv2d 3x3
 # ---------------------------------------------------------------------------------------------
