@@ -265,6 +265,21 @@ def test_convT2x2_wgrad(B, H, W, Cin, Cout):
     _report(f"convT2x2_wgrad{(B, H, W, Cin, Cout)}", dw, ref, 2e-3)
 
 
+def test_repack_batch_matches_single_calls():
+    """One launch for every weight tensor of a network == the per-tensor repack calls, bit for bit
+    (all four layouts, a padded input-channel count among them)."""
+    import ops
+    dev = _dev()
+    gen = torch.Generator().manual_seed(3)
+    convs = [torch.randn(64, 9, 3, 3, generator=gen).to(dev), torch.randn(128, 64, 3, 3, generator=gen).to(dev)]
+    ups = [torch.randn(128, 64, 2, 2, generator=gen).to(dev), torch.randn(32, 16, 2, 2, generator=gen).to(dev)]
+    req = [(w, "conv", fd) for w in convs for fd in (False, True)] + [(w, "up", fd) for w in ups for fd in (False, True)]
+    got = ops.repack_batch(req)
+    for (w, kind, fd), g in zip(req, got):
+        ref = ops.repack_convT2x2(w, fd) if kind == "up" else ops.repack_conv3x3(w, fd)
+        assert g.shape == ref.shape and torch.equal(g, ref), (kind, fd, tuple(w.shape))
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 256, 128), (25, 768, 2048), (1000, 48, 32)])
 def test_gemm(M, N, K):
     import ops
