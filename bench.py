@@ -246,7 +246,7 @@ def run_cuda(args, rank, local_rank, world):
         sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    # The compute of a step (a fixed sequence of ~65 launches) is captured once into a CUDA graph and
+    # The compute of a step (a fixed sequence of 56 launches) is captured once into a CUDA graph and
     # replayed; when N > 1 the two flat gradient buckets are all-reduced with NCCL right after each
     # replay (inside the timed region). The per-kernel CUDA events behind `roofline` /
     # `kernel_classes` come from an eager pass over the same K steps (events cannot be read inside a
