@@ -178,17 +178,8 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]; bf16 inputs, fp32 accumulate. One thread issues.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Same, issued by the elected lane of a converged warp: elect.sync and the predicated MMA sit in
+// D[tmem] (+)= A[smem] * B[smem]; bf16 inputs, fp32 accumulate, issued by the elected lane of a converged
+// warp: elect.sync and the predicated MMA sit in
 // one asm block so that no branch is generated and ptxas can keep the (warp-uniform) operands in
 // uniform registers. All 32 lanes must execute this with identical arguments.
 __device__ __forceinline__ void umma_bf16_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
@@ -199,32 +190,6 @@ __device__ __forceinline__ void umma_bf16_elect(uint32_t d_tmem, uint64_t adesc,
       "setp.ne.b32 pa, %4, 0;\n\t"
       "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// One (tap, k-chunk) sub-tile = `ksteps` (1, 2 or 4) K=16 MMAs whose descriptors advance by 32
-// bytes (2 x 16-byte units). Issuing them from a single asm block keeps the compiler-generated
-// glue (register moves into the uniform file) to once per sub-tile instead of once per MMA.
-__device__ __forceinline__ void umma_bf16_x4_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
-                                                   uint32_t idesc, uint32_t accumulate,
-                                                   uint32_t ksteps) {
-  asm volatile(
-      "{\n\t.reg .pred pe, pa, pt, p1, p2;\n\t"
-      ".reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
-      "elect.sync _|pe, 0xffffffff;\n\t"
-      "setp.ne.b32 pa, %4, 0;\n\t"
-      "setp.eq.u32 pt, 0, 0;\n\t"
-      "setp.gt.u32 p1, %5, 1;\n\t"
-      "setp.gt.u32 p2, %5, 2;\n\t"
-      "and.pred p1, p1, pe;\n\t"
-      "and.pred p2, p2, pe;\n\t"
-      "add.u64 a1, %1, 2;\n\tadd.u64 b1, %2, 2;\n\t"
-      "add.u64 a2, %1, 4;\n\tadd.u64 b2, %2, 4;\n\t"
-      "add.u64 a3, %1, 6;\n\tadd.u64 b3, %2, 6;\n\t"
-      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t"
-      "@p1 tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, pt;\n\t"
-      "@p2 tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, pt;\n\t"
-      "@p2 tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, pt;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(ksteps)
       : "memory");
 }
 // One (tap, k-chunk) sub-tile: KS (1, 2 or 4) K=16 MMAs whose descriptors advance by 32 bytes.
@@ -333,6 +298,7 @@ __device__ __forceinline__ void umma_tap_pair<4>(uint32_t d_tmem, uint32_t a_lo,
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// mbarrier arrives once every tcgen05.mma issued so far by this thread has retired (elected lane of a warp)
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"
@@ -340,12 +306,6 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
       "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
           smem_u32(bar))
       : "memory");
-}
-// mbarrier arrives once every tcgen05.mma issued so far by this thread has retired.
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
 }
 // 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (thread t <-> lane base+t).
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
