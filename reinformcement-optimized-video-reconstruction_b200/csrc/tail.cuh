@@ -102,7 +102,7 @@ tail_bwd_kernel(const __nv_bfloat16* __restrict__ y7, const float* __restrict__ 
                 const float* __restrict__ yout, const float* __restrict__ gout,
                 const float* __restrict__ target, float mse_scale,
                 const float* __restrict__ gloss, __nv_bfloat16* __restrict__ g7,
-                float* __restrict__ partial, int B, int HW) {
+                float* __restrict__ partial, int B, int HW, int chunks) {
   pdl_trigger();
   pdl_wait();
   __shared__ float sacc[TAILB_COLS];
@@ -121,8 +121,8 @@ tail_bwd_kernel(const __nv_bfloat16* __restrict__ y7, const float* __restrict__ 
   for (int c = 0; c < 8; ++c) { dw[0][c] = dw[1][c] = dw[2][c] = 0.f; dbc[c] = 0.f; }
   float db[3] = {0.f, 0.f, 0.f};
   __syncthreads();
-  const long long wbase = (static_cast<long long>(blockIdx.x) * (TAIL_THREADS / 32) + warp) * 32ll * TAIL_CHUNKS;
-  for (int ch = 0; ch < TAIL_CHUNKS; ++ch) {
+  const long long wbase = (static_cast<long long>(blockIdx.x) * (TAIL_THREADS / 32) + warp) * 32ll * chunks;
+  for (int ch = 0; ch < chunks; ++ch) {
     const long long cbase = wbase + ch * 32;
     if (cbase >= npix) break;
     uint4 q[8];
