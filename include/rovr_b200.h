@@ -303,6 +303,9 @@ int rovr_softmax_bwd(const float* dp, const void* p, void* ds, long long rows, i
 /* exact GELU on bf16 (F.gelu, rovr/common_layers.py:91) and its gradient */
 int rovr_gelu_fwd(const void* h, void* a, long long n, void* stream);
 int rovr_gelu_bwd(const void* da, const void* h, void* dh, long long n, void* stream);
+/* Host-only self-test of the index arithmetic shared by host and kernels (multiply-shift division); no GPU
+ * needed. 0 = ok. */
+int rovr_host_selftest(void);
 /* Tuning knob (no reference counterpart): CTA-pair (cta_group::2, 256-row MMA) launches of the igemm engine.
  * 0 = never, 1 = where measured to pay (default; env ROVR_PAIR overrides at load), 2 = whenever the shape
  * allows (even number of 128-pixel tiles, N tile a multiple of 32). Returns the previous mode. */

@@ -99,6 +99,7 @@ SIGNATURES = {
     "rovr_cast_f32_bf16": (_i, [_p, _p, _ll, _p]),
     "rovr_add_f32": (_i, [_p, _p, _p, _ll, _p]),
     "rovr_set_pair_mode": (_i, [_i]),
+    "rovr_host_selftest": (_i, []),
     "rovr_posenc_add": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "rovr_posenc_grad": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "rovr_colsum_workspace": (_sz, [_i]),

@@ -52,3 +52,10 @@ def test_no_cpu_fallback():
     net = LocalNetworkUNetNorm()
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 3, 8, 8), torch.zeros(1, 2, 3, 8, 8))
+
+
+def test_host_selftest_index_arithmetic():
+    """The multiply-shift division used for tile indices (host-computed magic numbers, device-side
+    umulhi + add + shift) agrees with integer division — checked on the host, no GPU involved."""
+    import _native
+    assert _native.lib.rovr_host_selftest() == 0
