@@ -169,12 +169,16 @@ def cpu_step_rate(steps, warmup, sample_b=None, budget_s=None):
 def run_reference(args, rank):
     if rank != 0:
         return
-    base, ms = cpu_step_rate(args.steps, args.warmup)
+    # the stated config: B = 24 frames of 256x256 per step (~2.5 s per step on 16 host threads); the step
+    # count is bounded so that the arm ends within a few minutes whatever --steps asks for
+    base, ms = cpu_step_rate(min(args.steps, 8), min(args.warmup, 1), sample_b=B_PER_GPU, budget_s=120.0)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "LocalNet U-Net fwd+L2+bwd, 256x256 masked frames (CPU sample of configs[1])",
+            "config": {"workload": "LocalNet U-Net fwd+L2+bwd (configs[1]): B=24 frames, 256x256, synthetic masked "
+                                   "clips, random-init weights — on the host cores",
+                       "global_batch": B_PER_GPU,
                        "note": "reference is pure PyTorch; its modules cannot travel to the GPU box, so the "
                                "oracle port (pinned to the reference by tests/golden) is what is timed"},
             "cpu_baseline": base,
@@ -305,8 +309,10 @@ def run_cuda(args, rank, local_rank, world):
             e2e_graph_loop(2)
             ms_g = timed(lambda: e2e_graph_loop(args.steps), 1)
             e2e_graph = {"value": frames / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g / args.steps,
-                         "api": "rb = ScalarReadback(lag=1); for batch in DeviceFeeder(pinned_host_batches): "
-                                "rb.exchange(GraphedTrainingStep(net, ...)(*batch))"}
+                         "api": "step = GraphedTrainingStep(net, ...); rb = ScalarReadback(lag=1); for batch in "
+                                "DeviceFeeder(pinned_host_batches): rb.exchange(step(*batch))  # host fp32 inputs copied H2D "
+                                "every step, all 19 weight tensors re-packed to bf16 inside the graph every step (as after an "
+                                "optimizer update), every step's loss read back on the host"}
 
     if rank != 0:
         if world > 1:
@@ -351,16 +357,21 @@ def run_cuda(args, rank, local_rank, world):
     ig_flops_per_launch = 2.0 * macs["igemm"] * frames_rank0 / ig_calls
     ig_avg_s = dur["igemm"] * 1e-3 / ig_calls
     achieved = ig_flops_per_launch / ig_avg_s / 1e12 if ig_avg_s > 0 else 0.0
-    traffic = None
+    # dram__bytes_read.sum + dram__bytes_write.sum per igemm launch: a STATIC figure taken from the committed
+    # `ncu --set full` capture named in profiles/roofline_traffic.json (it cannot be measured in an un-profiled run)
+    traffic, traffic_source = None, None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("igemm_dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("igemm_dram_bytes_per_launch")
+            traffic_source = "static (ncu capture %s)" % tj.get("source", "profiles/")
         except Exception:
             traffic = None
     roofline = {"kernel": "igemm_kernel (tcgen05 implicit GEMM: conv/convT fprop + dgrad)",
                 "bound": "tensor", "achieved": achieved, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tensor_tflops"], "traffic": traffic,
+                "frac": achieved / peaks["tensor_tflops"], "traffic": traffic, "traffic_source": traffic_source,
+                "frac_of_burst_peak": achieved / peaks["tensor_tflops_burst"] if peaks.get("tensor_tflops_burst") else None,
                 "launches_per_step": cnt["igemm"] / args.steps,
                 "avg_launch_ms": ig_avg_s * 1e3, "flops_per_launch": ig_flops_per_launch,
                 "peak_source": peaks["source"]}
@@ -374,19 +385,23 @@ def run_cuda(args, rank, local_rank, world):
                                    "synthetic masked clips, random-init weights",
                        "global_batch": B_PER_GPU * world, "parallelism": f"dp{world}",
                        "launch": (("one CUDA graph per step (GraphedTrainingStep)" +
-                                   (" + NCCL all-reduce of 2 gradient buckets after each replay" if world > 1 else ""))
+                                   ((" with the NCCL all-reduces of the 2 gradient buckets captured inside it on a forked "
+                                     "stream (decoder bucket overlapped with the encoder backward)"
+                                     if graphed.allreduce_mode == "captured-overlapped" else
+                                     " + NCCL all-reduce of 2 gradient buckets after each replay") if world > 1 else ""))
                                   if graphed is not None else "eager launches, bucketed all-reduce overlapped with backward"),
                        "eager_ms_per_step_with_per_kernel_events": ms_eager / args.steps,
                        "l2": "each step streams ~2.5 GB of activations/gradients (>> 126 MB L2); no explicit flush",
                        "precision": "bf16 operands + bf16 activation storage, fp32 accumulate, fp32 master weights/grads"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+            "e2e": (dict(e2e_graph, h2d_bytes_per_step=(xh.numel() + ch.numel() + th.numel()) * 4, d2h_bytes_per_step=4)
+                    if e2e_graph is not None else None),
+            "e2e_module_call": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": (xh.numel() + ch.numel() + th.numel()) * 4, "d2h_bytes_per_step": 4,
                     "api": "for frame, context, target in DeviceFeeder(pinned_host_batches): y = LocalNetworkUNetNorm()"
                            "(frame, context); loss = F.mse_loss(y, target); loss.backward(); ScalarReadback.exchange(loss)  "
                            "# every step's loss is read on the host, one step behind the enqueue point; the weights do not "
                            "change between bench steps, so the module's cached bf16 operand copies are reused here, while "
                            "`value` (graph replay) re-packs all 19 weight tensors every step as a training loop would"},
-            "e2e_graphed_step": e2e_graph,
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
             "clocks": clocks, "roofline": roofline, "kernel_classes": kc,
             "model_tflops": total_flops_per_frame * value / world / 1e12,

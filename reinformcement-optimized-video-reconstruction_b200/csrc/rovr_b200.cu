@@ -98,25 +98,49 @@ static void init_device() {
     return;
   }
   g_dev.encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-  cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(igemm_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(igemm_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(igemm_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(igemm_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(igemm_kernel<true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   g_dev.ok = 1;
 }
+// Function attributes (227 KB of dynamic shared memory) belong to a (function, device) pair: they are set
+// once on EVERY device a call is made on, not just on the first one (a second GPU used by the same process
+// would otherwise fail its launches).
+static std::mutex g_attr_mutex;
+static unsigned long long g_attr_mask = 0;   // bit d: device d has its attributes
+template <typename K>
+static void set_max_smem(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+static void init_function_attributes();
 static int ensure_device() {
   std::call_once(g_dev_once, init_device);
   if (!g_dev.ok) {
     if (g_err[0] == 0) fail(-4, "device initialisation failed earlier (not sm_100 or no driver)");
     return g_dev_rc ? g_dev_rc : -4;
   }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail(-4, "cudaGetDevice failed");
+  if (!(__atomic_load_n(&g_attr_mask, __ATOMIC_ACQUIRE) >> dev & 1ull)) {
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
+    if (!(g_attr_mask >> dev & 1ull)) {
+      int major = 0;
+      cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+      if (major != 10) return fail(-4, "device %d is not sm_100: this library is built for sm_100a (B200) only", dev);
+      init_function_attributes();
+      __atomic_store_n(&g_attr_mask, g_attr_mask | (1ull << dev), __ATOMIC_RELEASE);
+    }
+  }
   return 0;
+}
+static void init_function_attributes() {
+  set_max_smem(igemm_kernel<true>);
+  set_max_smem(igemm_kernel<false>);
+  set_max_smem(igemm_kernel<true, true>);
+  set_max_smem(igemm_kernel<true, false, true>);
+  set_max_smem(igemm_kernel<true, false, false, true>);
+  set_max_smem(igemm_kernel<false, false, false, true>);
+  set_max_smem(igemm_kernel<true, true, false, true>);
+  set_max_smem(igemm_kernel<true, false, true, true>);
+  set_max_smem(wgrad_kernel);
+  set_max_smem(wgrad_halo_kernel);
 }
 extern "C" int rovr_device_check(void) { return ensure_device(); }
 extern "C" int rovr_hang_code(unsigned int* code) {

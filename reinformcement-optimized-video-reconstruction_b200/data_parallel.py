@@ -37,7 +37,7 @@ class GradientBuckets:
         self.world = dist.get_world_size(process_group)
         self.backend = dist.get_backend(process_group)
         self.on_gpu = self.backend == "nccl"
-        self.stream = torch.cuda.Stream() if self.on_gpu else None
+        self.stream = torch.cuda.Stream() if self.on_gpu else None   # on the process's current device
         self.pending = []
         self.launched = 0
         module._grad_bucket_hook = self.ready
@@ -51,7 +51,8 @@ class GradientBuckets:
         if self.on_gpu:
             main = torch.cuda.current_stream()
             self.stream.wait_stream(main)          # the bucket's producers have been enqueued
-            flat.record_stream(self.stream)
+            if not torch.cuda.is_current_stream_capturing():
+                flat.record_stream(self.stream)    # (a captured graph owns its buffers for its lifetime)
             with torch.cuda.stream(self.stream):
                 dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
             self.pending.append(flat)
@@ -85,6 +86,13 @@ class GradientBuckets:
 
 
 def broadcast_parameters(module, src=0, process_group=None):
-    """Make every replica start from rank `src`'s parameters and buffers."""
-    for t in list(module.parameters()) + list(module.buffers()):
-        dist.broadcast(t.data, src=src, group=process_group)
+    """Make every replica start from rank `src`'s parameters and buffers. The broadcast writes the
+    parameter itself (under no_grad), which bumps its version counter, so the cached bf16 operand
+    copies keyed on (data_ptr, _version) are re-packed on the next forward."""
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t, src=src, group=process_group)
+    for m in module.modules():
+        cache = getattr(m, "_packed", None)
+        if cache is not None and hasattr(cache, "_cache"):
+            cache._cache.clear()

@@ -91,58 +91,153 @@ def _flat_bucket(params, names, device):
     return flat, views
 
 
+def _forward_impl(net, x, context, target, P, with_dgrad):
+    """The forward launch sequence. P: {live parameter name: tensor}. Returns (out, loss | None, acts)."""
+    dev = x.device
+    B, _, H, W = x.shape
+    bf = torch.bfloat16
+    pk = net._packed
+    # all stale bf16 operand copies (forward and, if a backward will follow, data-gradient) in one launch
+    pk.refresh([(n, P[n + ".weight"], k) for n, k, _, _ in _LAYERS if k != "bn"], with_dgrad)
+
+    def wk(name, kind="conv"):
+        return pk.get(name, P[name + ".weight"], kind, False)
+
+    a = {}
+    a["in16"] = ops.pack_nchw([x, context.reshape(B, 6, H, W)], 16)
+    a["cat7"] = torch.empty((B, H, W, 128), dtype=bf, device=dev)
+    a["cat6"] = torch.empty((B, H // 2, W // 2, 256), dtype=bf, device=dev)
+    a["cat5"] = torch.empty((B, H // 4, W // 4, 512), dtype=bf, device=dev)
+    x1, x2, x3 = a["cat7"][..., 64:], a["cat6"][..., 128:], a["cat5"][..., 256:]
+    def conv_pool(src, name, dst, pooled):
+        # conv + ReLU + MaxPool2d(2,2) in one kernel when the halo tiling applies (W >= 8, H >= 16)
+        if src.shape[1] >= 16 and src.shape[2] >= 8:
+            ops.conv3x3_fprop(src, wk(name), P[name + ".bias"], dst, pooled=pooled)
+        else:
+            ops.conv3x3_fprop(src, wk(name), P[name + ".bias"], dst)
+            ops.maxpool_fwd(dst, pooled, 2)
+
+    a["p1"] = torch.empty((B, H // 2, W // 2, 64), dtype=bf, device=dev)
+    conv_pool(a["in16"], "conv1", x1, a["p1"])
+    a["p2"] = torch.empty((B, H // 4, W // 4, 128), dtype=bf, device=dev)
+    conv_pool(a["p1"], "conv2", x2, a["p2"])
+    a["p3"] = torch.empty((B, H // 8, W // 8, 256), dtype=bf, device=dev)
+    conv_pool(a["p2"], "conv3", x3, a["p3"])
+    a["x4"] = torch.empty((B, H // 8, W // 8, 512), dtype=bf, device=dev)
+    ops.conv3x3_fprop(a["p3"], wk("conv4"), P["conv4.bias"], a["x4"])
+
+    ops.convT2x2_fprop(a["x4"], wk("upconv1", "up"), P["upconv1.bias"], a["cat5"][..., :256])
+    a["y5"] = torch.empty((B, H // 4, W // 4, 256), dtype=bf, device=dev)
+    ops.conv3x3_fprop(a["cat5"], wk("conv5"), P["conv5.bias"], a["y5"])
+    ops.convT2x2_fprop(a["y5"], wk("upconv2", "up"), P["upconv2.bias"], a["cat6"][..., :128])
+    a["y6"] = torch.empty((B, H // 2, W // 2, 128), dtype=bf, device=dev)
+    ops.conv3x3_fprop(a["cat6"], wk("conv6"), P["conv6.bias"], a["y6"])
+    ops.convT2x2_fprop(a["y6"], wk("upconv3", "up"), P["upconv3.bias"], a["cat7"][..., :64])
+    a["y7"] = torch.empty((B, H, W, 64), dtype=bf, device=dev)
+    # conv7 + ReLU + conv8 (1x1) + sigmoid (+ L2 loss) in one kernel: the conv7 epilogue thread owns
+    # a whole pixel of y7, so the 64 -> 3 projection needs no second pass over it
+    out, loss = ops.conv3x3_fprop_tail(a["cat7"], wk("conv7"), P["conv7.bias"], a["y7"], P["conv8.weight"],
+                                       P["conv8.bias"], target)
+    a["out"] = out
+    return out, loss, a
+
+
+def _backward_impl(net, a, P, target, g_out, g_loss, buckets=None):
+    """The backward launch sequence. Writes every parameter gradient into two flat fp32 buckets
+    (decoder, encoder — `buckets` = (dec_flat, enc_flat, views) to reuse static ones) and returns
+    {parameter name: gradient view}."""
+    dev = a["out"].device
+    bf = torch.bfloat16
+    pk = net._packed
+    if g_out is not None:
+        g_out = g_out.contiguous()
+    B, H, W, _ = a["y7"].shape
+
+    def wd(name, kind="conv"):
+        return pk.get(name, P[name + ".weight"], kind, True)
+
+    if buckets is None:
+        dec_flat, G = _flat_bucket(P, _DECODER, dev)
+        enc_flat, Ge = _flat_bucket(P, _ENCODER, dev)
+        G.update(Ge)
+    else:
+        dec_flat, enc_flat, G = buckets
+    net._last_buckets = (dec_flat, enc_flat)
+
+    def el(t):
+        return torch.empty_like(t)
+
+    # ---- tail: conv8 + sigmoid (+L2) ----
+    g7 = el(a["y7"])
+    use_loss = target is not None and g_loss is not None
+    ops.tail_bwd(a["y7"], P["conv8.weight"], a["out"], g7, G["conv8.weight"], G["conv8.bias"],
+                 gout=g_out, target=target if use_loss else None,
+                 mse_scale=2.0 / a["out"].numel(),
+                 gloss=g_loss.contiguous() if use_loss else None, db7=G["conv7.bias"])
+    # ---- conv7 (its bias gradient came out of the tail kernel) ----
+    ops.conv3x3_wgrad(g7, a["cat7"], G["conv7.weight"])
+    gcat7 = el(a["cat7"])
+    # the ReLU mask is only needed on the up-conv half: the skip half (x1) is masked by pool1's backward
+    ops.conv3x3_dgrad(g7, wd("conv7"), gcat7, mask=a["cat7"], mask_cols=64, colsum=G["upconv3.bias"])
+    # ---- upconv3 ----
+    gu3 = gcat7[..., :64]
+    ops.convT2x2_wgrad(gu3, a["y6"], G["upconv3.weight"])
+    g6 = el(a["y6"])
+    ops.convT2x2_dgrad(gu3, wd("upconv3", "up"), g6, mask=a["y6"], colsum=G["conv6.bias"])
+    # ---- conv6 ----
+    ops.conv3x3_wgrad(g6, a["cat6"], G["conv6.weight"])
+    gcat6 = el(a["cat6"])
+    ops.conv3x3_dgrad(g6, wd("conv6"), gcat6, mask=a["cat6"], mask_cols=128, colsum=G["upconv2.bias"])
+    # ---- upconv2 ----
+    gu2 = gcat6[..., :128]
+    ops.convT2x2_wgrad(gu2, a["y5"], G["upconv2.weight"])
+    g5 = el(a["y5"])
+    ops.convT2x2_dgrad(gu2, wd("upconv2", "up"), g5, mask=a["y5"], colsum=G["conv5.bias"])
+    # ---- conv5 ----
+    ops.conv3x3_wgrad(g5, a["cat5"], G["conv5.weight"])
+    gcat5 = el(a["cat5"])
+    ops.conv3x3_dgrad(g5, wd("conv5"), gcat5, mask=a["cat5"], mask_cols=256, colsum=G["upconv1.bias"])
+    # ---- upconv1 ----
+    gu1 = gcat5[..., :256]
+    ops.convT2x2_wgrad(gu1, a["x4"], G["upconv1.weight"])
+    g4 = el(a["x4"])
+    ops.convT2x2_dgrad(gu1, wd("upconv1", "up"), g4, mask=a["x4"], colsum=G["conv4.bias"])
+    net._bucket_ready(0, dec_flat)
+    # ---- conv4 ----
+    ops.conv3x3_wgrad(g4, a["p3"], G["conv4.weight"])
+    gp3 = el(a["p3"])
+    ops.conv3x3_dgrad(g4, wd("conv4"), gp3)
+    g3 = torch.empty((B, H // 4, W // 4, 256), dtype=bf, device=dev)
+    ops.maxpool_bwd(a["cat5"][..., 256:], gp3, g3, 2, gskip=gcat5[..., 256:], relu_mask=True,
+                    colsum=G["conv3.bias"])             # bias gradient from the same pass over g3
+    # ---- conv3 ----
+    ops.conv3x3_wgrad(g3, a["p2"], G["conv3.weight"])
+    gp2 = el(a["p2"])
+    ops.conv3x3_dgrad(g3, wd("conv3"), gp2)
+    g2 = torch.empty((B, H // 2, W // 2, 128), dtype=bf, device=dev)
+    ops.maxpool_bwd(a["cat6"][..., 128:], gp2, g2, 2, gskip=gcat6[..., 128:], relu_mask=True,
+                    colsum=G["conv2.bias"])
+    # ---- conv2 ----
+    ops.conv3x3_wgrad(g2, a["p1"], G["conv2.weight"])
+    gp1 = el(a["p1"])
+    ops.conv3x3_dgrad(g2, wd("conv2"), gp1)
+    g1 = torch.empty((B, H, W, 64), dtype=bf, device=dev)
+    ops.maxpool_bwd(a["cat7"][..., 64:], gp1, g1, 2, gskip=gcat7[..., 64:], relu_mask=True,
+                    colsum=G["conv1.bias"])
+    # ---- conv1 (input needs no gradient: no dgrad, as in the reference's autograd graph) ----
+    ops.conv3x3_wgrad(g1, a["in16"], G["conv1.weight"])
+    net._bucket_ready(1, enc_flat)
+    net._buckets_wait()
+    return G
+
+
 class _LocalNetFunction(torch.autograd.Function):
     """forward: (x, context, target_or_None, *live_params) -> (y_hat, loss_or_zero)."""
 
     @staticmethod
     def forward(ctx, net, x, context, target, *plist):
         P = dict(zip(net._live_names, plist))
-        dev = x.device
-        B, _, H, W = x.shape
-        bf = torch.bfloat16
-        pk = net._packed
-        # all stale bf16 operand copies (forward and, if a backward will follow, data-gradient) in one launch
-        pk.refresh([(n, P[n + ".weight"], k) for n, k, _, _ in _LAYERS if k != "bn"], any(ctx.needs_input_grad))
-
-        def wk(name, kind="conv"):
-            return pk.get(name, P[name + ".weight"], kind, False)
-
-        a = {}
-        a["in16"] = ops.pack_nchw([x, context.reshape(B, 6, H, W)], 16)
-        a["cat7"] = torch.empty((B, H, W, 128), dtype=bf, device=dev)
-        a["cat6"] = torch.empty((B, H // 2, W // 2, 256), dtype=bf, device=dev)
-        a["cat5"] = torch.empty((B, H // 4, W // 4, 512), dtype=bf, device=dev)
-        x1, x2, x3 = a["cat7"][..., 64:], a["cat6"][..., 128:], a["cat5"][..., 256:]
-        def conv_pool(src, name, dst, pooled):
-            # conv + ReLU + MaxPool2d(2,2) in one kernel when the halo tiling applies (W >= 8, H >= 16)
-            if src.shape[1] >= 16 and src.shape[2] >= 8:
-                ops.conv3x3_fprop(src, wk(name), P[name + ".bias"], dst, pooled=pooled)
-            else:
-                ops.conv3x3_fprop(src, wk(name), P[name + ".bias"], dst)
-                ops.maxpool_fwd(dst, pooled, 2)
-
-        a["p1"] = torch.empty((B, H // 2, W // 2, 64), dtype=bf, device=dev)
-        conv_pool(a["in16"], "conv1", x1, a["p1"])
-        a["p2"] = torch.empty((B, H // 4, W // 4, 128), dtype=bf, device=dev)
-        conv_pool(a["p1"], "conv2", x2, a["p2"])
-        a["p3"] = torch.empty((B, H // 8, W // 8, 256), dtype=bf, device=dev)
-        conv_pool(a["p2"], "conv3", x3, a["p3"])
-        a["x4"] = torch.empty((B, H // 8, W // 8, 512), dtype=bf, device=dev)
-        ops.conv3x3_fprop(a["p3"], wk("conv4"), P["conv4.bias"], a["x4"])
-
-        ops.convT2x2_fprop(a["x4"], wk("upconv1", "up"), P["upconv1.bias"], a["cat5"][..., :256])
-        a["y5"] = torch.empty((B, H // 4, W // 4, 256), dtype=bf, device=dev)
-        ops.conv3x3_fprop(a["cat5"], wk("conv5"), P["conv5.bias"], a["y5"])
-        ops.convT2x2_fprop(a["y5"], wk("upconv2", "up"), P["upconv2.bias"], a["cat6"][..., :128])
-        a["y6"] = torch.empty((B, H // 2, W // 2, 128), dtype=bf, device=dev)
-        ops.conv3x3_fprop(a["cat6"], wk("conv6"), P["conv6.bias"], a["y6"])
-        ops.convT2x2_fprop(a["y6"], wk("upconv3", "up"), P["upconv3.bias"], a["cat7"][..., :64])
-        a["y7"] = torch.empty((B, H, W, 64), dtype=bf, device=dev)
-        # conv7 + ReLU + conv8 (1x1) + sigmoid (+ L2 loss) in one kernel: the conv7 epilogue thread owns
-        # a whole pixel of y7, so the 64 -> 3 projection needs no second pass over it
-        out, loss = ops.conv3x3_fprop_tail(a["cat7"], wk("conv7"), P["conv7.bias"], a["y7"], P["conv8.weight"],
-                                           P["conv8.bias"], target)
-        a["out"] = out
+        out, loss, a = _forward_impl(net, x, context, target, P, any(ctx.needs_input_grad))
         ctx.net = net
         ctx.acts = a
         ctx.params = P
@@ -156,88 +251,9 @@ class _LocalNetFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out, g_loss):
         net, a, P, target = ctx.net, ctx.acts, ctx.params, ctx.target
-        dev = a["out"].device
-        bf = torch.bfloat16
-        pk = net._packed
         if g_out is None and (g_loss is None or target is None):
             return (None,) * (4 + len(net._live_names))
-        if g_out is not None:
-            g_out = g_out.contiguous()
-        B, H, W, _ = a["y7"].shape
-
-        def wd(name, kind="conv"):
-            return pk.get(name, P[name + ".weight"], kind, True)
-
-        dec_flat, G = _flat_bucket(P, _DECODER, dev)
-        enc_flat, Ge = _flat_bucket(P, _ENCODER, dev)
-        G.update(Ge)
-        net._last_buckets = (dec_flat, enc_flat)
-
-        def el(t):
-            return torch.empty_like(t)
-
-        # ---- tail: conv8 + sigmoid (+L2) ----
-        g7 = el(a["y7"])
-        use_loss = target is not None and g_loss is not None
-        ops.tail_bwd(a["y7"], P["conv8.weight"], a["out"], g7, G["conv8.weight"], G["conv8.bias"],
-                     gout=g_out, target=target if use_loss else None,
-                     mse_scale=2.0 / a["out"].numel(),
-                     gloss=g_loss.contiguous() if use_loss else None, db7=G["conv7.bias"])
-        # ---- conv7 (its bias gradient came out of the tail kernel) ----
-        ops.conv3x3_wgrad(g7, a["cat7"], G["conv7.weight"])
-        gcat7 = el(a["cat7"])
-        # the ReLU mask is only needed on the up-conv half: the skip half (x1) is masked by pool1's backward
-        ops.conv3x3_dgrad(g7, wd("conv7"), gcat7, mask=a["cat7"], mask_cols=64, colsum=G["upconv3.bias"])
-        # ---- upconv3 ----
-        gu3 = gcat7[..., :64]
-        ops.convT2x2_wgrad(gu3, a["y6"], G["upconv3.weight"])
-        g6 = el(a["y6"])
-        ops.convT2x2_dgrad(gu3, wd("upconv3", "up"), g6, mask=a["y6"], colsum=G["conv6.bias"])
-        # ---- conv6 ----
-        ops.conv3x3_wgrad(g6, a["cat6"], G["conv6.weight"])
-        gcat6 = el(a["cat6"])
-        ops.conv3x3_dgrad(g6, wd("conv6"), gcat6, mask=a["cat6"], mask_cols=128, colsum=G["upconv2.bias"])
-        # ---- upconv2 ----
-        gu2 = gcat6[..., :128]
-        ops.convT2x2_wgrad(gu2, a["y5"], G["upconv2.weight"])
-        g5 = el(a["y5"])
-        ops.convT2x2_dgrad(gu2, wd("upconv2", "up"), g5, mask=a["y5"], colsum=G["conv5.bias"])
-        # ---- conv5 ----
-        ops.conv3x3_wgrad(g5, a["cat5"], G["conv5.weight"])
-        gcat5 = el(a["cat5"])
-        ops.conv3x3_dgrad(g5, wd("conv5"), gcat5, mask=a["cat5"], mask_cols=256, colsum=G["upconv1.bias"])
-        # ---- upconv1 ----
-        gu1 = gcat5[..., :256]
-        ops.convT2x2_wgrad(gu1, a["x4"], G["upconv1.weight"])
-        g4 = el(a["x4"])
-        ops.convT2x2_dgrad(gu1, wd("upconv1", "up"), g4, mask=a["x4"], colsum=G["conv4.bias"])
-        net._bucket_ready(0, dec_flat)
-        # ---- conv4 ----
-        ops.conv3x3_wgrad(g4, a["p3"], G["conv4.weight"])
-        gp3 = el(a["p3"])
-        ops.conv3x3_dgrad(g4, wd("conv4"), gp3)
-        g3 = torch.empty((B, H // 4, W // 4, 256), dtype=bf, device=dev)
-        ops.maxpool_bwd(a["cat5"][..., 256:], gp3, g3, 2, gskip=gcat5[..., 256:], relu_mask=True,
-                        colsum=G["conv3.bias"])             # bias gradient from the same pass over g3
-        # ---- conv3 ----
-        ops.conv3x3_wgrad(g3, a["p2"], G["conv3.weight"])
-        gp2 = el(a["p2"])
-        ops.conv3x3_dgrad(g3, wd("conv3"), gp2)
-        g2 = torch.empty((B, H // 2, W // 2, 128), dtype=bf, device=dev)
-        ops.maxpool_bwd(a["cat6"][..., 128:], gp2, g2, 2, gskip=gcat6[..., 128:], relu_mask=True,
-                        colsum=G["conv2.bias"])
-        # ---- conv2 ----
-        ops.conv3x3_wgrad(g2, a["p1"], G["conv2.weight"])
-        gp1 = el(a["p1"])
-        ops.conv3x3_dgrad(g2, wd("conv2"), gp1)
-        g1 = torch.empty((B, H, W, 64), dtype=bf, device=dev)
-        ops.maxpool_bwd(a["cat7"][..., 64:], gp1, g1, 2, gskip=gcat7[..., 64:], relu_mask=True,
-                        colsum=G["conv1.bias"])
-        # ---- conv1 (input needs no gradient: no dgrad, as in the reference's autograd graph) ----
-        ops.conv3x3_wgrad(g1, a["in16"], G["conv1.weight"])
-        net._bucket_ready(1, enc_flat)
-        net._buckets_wait()
-
+        G = _backward_impl(net, a, P, target, g_out, g_loss)
         ctx.acts = None
         grads = tuple(G[n] if P[n].requires_grad else None for n in net._live_names)
         return (None, None, None, None) + grads
@@ -297,7 +313,8 @@ class LocalNetworkUNetNorm(nn.Module):
         context = context.float().contiguous()
         if target is not None:
             target = target.float().contiguous()
-        return _LocalNetFunction.apply(self, x, context, target, *self._live_params())
+        with torch.cuda.device(x.device):   # launches go to the tensors' GPU, not the thread's current one
+            return _LocalNetFunction.apply(self, x, context, target, *self._live_params())
 
     def forward(self, x, context):
         out, _ = self._run(x, context, None)
@@ -312,48 +329,100 @@ class LocalNetworkUNetNorm(nn.Module):
 class GraphedTrainingStep:
     """forward + fused L2 loss + backward of a LocalNetworkUNetNorm captured ONCE into a CUDA graph.
 
-    A step is a fixed sequence of ~65 kernel launches of 20-400 us each; replaying it as a graph
-    removes the per-launch CPU cost and the gaps between kernels. Usage:
+    A step is a fixed sequence of ~56 kernel launches of 20-400 us each; replaying it as a graph
+    removes the per-launch CPU cost and the gaps between kernels. Usage
+    (the loop of rovr/train_local_net_unet.py:102-116, `zero_grad()` included):
 
         step = GraphedTrainingStep(net, frame, context, target)     # captures with these shapes
-        loss = step(frame, context, target)                         # copies into the static inputs, replays
-        # net.<param>.grad now hold this step's gradients (static tensors, overwritten by every replay)
+        for frame, context, target in batches:
+            optimizer.zero_grad()
+            loss = step(frame, context, target)      # copies into the static inputs, replays
+            optimizer.step()                         # net.<param>.grad are this step's gradients
+
+    The launch sequence is captured WITHOUT the autograd engine (`_forward_impl` / `_backward_impl`
+    called directly): every gradient is written into two static flat fp32 buckets and each replay
+    re-binds `param.grad` to its view of them, so the step survives `zero_grad(set_to_none=True)`
+    (which drops `.grad`) and the gradients provably alias the buckets that are all-reduced.
 
     The bf16 operand copies of the weights are re-packed inside the graph (`repack_weights=True`, the
-    default: a training loop's optimizer changes the fp32 masters every step, 19 small kernels);
+    default: a training loop's optimizer changes the fp32 masters every step, one launch);
     with False they are packed once before capture — only valid while the weights never change.
-    With data_parallel.GradientBuckets installed, the graph holds the compute only and the two
-    flat gradient buckets are all-reduced right after each replay (15 MB over NVLink, ~0.1 ms; the
-    backward/all-reduce overlap of the eager path is traded for the removal of ~65 launch gaps).
+
+    With data_parallel.GradientBuckets installed the two NCCL all-reduces are captured INSIDE the
+    graph on a forked stream: the decoder bucket is reduced while the encoder half of backward is
+    still running, the encoder bucket at the end (`allreduce_mode == "captured-overlapped"`). If the
+    collective cannot be captured (backend without graph support) the buckets are all-reduced right
+    after each replay instead (`"after-replay"`).
     """
 
-    def __init__(self, net, x, context, target, repack_weights=True, warmup=2):
+    def __init__(self, net, x, context, target, repack_weights=True, warmup=2, capture_collectives=True):
         self.net = net
-        self._hooks = (net._grad_bucket_hook, net._grad_bucket_wait, getattr(net, "_grad_bucket_reduce", None))
-        net._grad_bucket_hook = net._grad_bucket_wait = None     # capture compute only
         self.repack_weights = repack_weights
+        dev = x.device
         self.x, self.context, self.target = x.clone(), context.clone(), target.clone()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):         # allocates the scratch workspace, packs the weights
-                net.zero_grad(set_to_none=True)
-                _, loss = net.forward_with_mse(self.x, self.context, self.target)
-                loss.backward()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        net.zero_grad(set_to_none=True)
-        if repack_weights:
-            net._packed._cache.clear()
+        named = dict(net.named_parameters())
+        self.P = {n: named[n] for n in net._live_names}
+        Pd = {n: p.detach() for n, p in self.P.items()}
+        dec_flat, G = _flat_bucket(Pd, _DECODER, dev)
+        enc_flat, Ge = _flat_bucket(Pd, _ENCODER, dev)
+        G.update(Ge)
+        self.buckets = (dec_flat, enc_flat)
+        self.grad_views = G
+        self._g_loss = torch.ones((), dtype=torch.float32, device=dev)
+        hooks = (net._grad_bucket_hook, net._grad_bucket_wait, net._grad_bucket_reduce)
+        self._reduce_after = None
+        self.allreduce_mode = "none"
+
+        def run():
+            y, loss, acts = _forward_impl(net, self.x, self.context, self.target, Pd, True)
+            _backward_impl(net, acts, Pd, self.target, None, self._g_loss, buckets=(dec_flat, enc_flat, G))
+            return y, loss
+
         import _native
-        n0 = _native.lib.rovr_launch_count()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.y, self.loss = net.forward_with_mse(self.x, self.context, self.target)
-            self.loss.backward()
-        self.launches_per_step = int(_native.lib.rovr_launch_count() - n0)
-        self.buckets = net._last_buckets                          # static flat gradient buffers of the graph
-        net._grad_bucket_hook, net._grad_bucket_wait = self._hooks[0], self._hooks[1]
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):     # packs the weights, warms the allocator and NCCL
+                    run()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            want_collectives = hooks[0] is not None and capture_collectives
+            for attempt in ((True, False) if want_collectives else (False,)):
+                if not attempt:
+                    net._grad_bucket_hook = net._grad_bucket_wait = None     # capture compute only
+                if repack_weights:
+                    net._packed._cache.clear()
+                n0 = _native.lib.rovr_launch_count()
+                self.graph = torch.cuda.CUDAGraph()
+                try:
+                    with torch.cuda.graph(self.graph):
+                        self.y, self.loss = run()
+                except Exception as exc:      # noqa: BLE001 — a collective that cannot be captured
+                    if not attempt:
+                        net._grad_bucket_hook, net._grad_bucket_wait = hooks[0], hooks[1]
+                        raise
+                    self._capture_error = repr(exc)
+                    torch.cuda.synchronize(dev)
+                    continue
+                self.launches_per_step = int(_native.lib.rovr_launch_count() - n0)
+                if hooks[0] is not None:
+                    self.allreduce_mode = "captured-overlapped" if attempt else "after-replay"
+                    self._reduce_after = None if attempt else hooks[2]
+                break
+        net._grad_bucket_hook, net._grad_bucket_wait = hooks[0], hooks[1]
+        self._bind_grads()
+
+    def _bind_grads(self):
+        for n, p in self.P.items():
+            if p.requires_grad:
+                p.grad = self.grad_views[n]
+
+    def grads_alias_buckets(self):
+        """True iff every live `param.grad` is a view into the static buckets (checked by the tests)."""
+        spans = [(b.data_ptr(), b.data_ptr() + b.numel() * 4) for b in self.buckets]
+        return all(p.grad is not None and any(lo <= p.grad.data_ptr() < hi for lo, hi in spans)
+                   for p in self.P.values() if p.requires_grad)
 
     def __call__(self, x=None, context=None, target=None):
         if x is not None:
@@ -363,6 +432,7 @@ class GraphedTrainingStep:
         if target is not None:
             self.target.copy_(target, non_blocking=True)
         self.graph.replay()
-        if self._hooks[2] is not None:
-            self._hooks[2](self.buckets)                          # NCCL all-reduce (AVG) of the two buckets
+        if self._reduce_after is not None:
+            self._reduce_after(self.buckets)                      # NCCL all-reduce (AVG) of the two buckets
+        self._bind_grads()      # the reference loop's zero_grad() sets .grad to None: re-attach the static views
         return self.loss

@@ -14,12 +14,23 @@ import _native as N
 _vp = ctypes.c_void_p
 
 
+# Device of the tensors of the call being assembled: every tensor argument goes through _ptr(), the
+# stream argument is evaluated last, and _launch() switches the CUDA context if that device is not the
+# thread's current one (the reference picks `torch.device(f'cuda:{id}')` without set_device,
+# rovr/train_local_net_unet.py:73-75, so a model may live on a non-current GPU).
+_DEV = [None]
+
+
 def _ptr(t):
-    return _vp(t.data_ptr()) if t is not None else _vp(0)
+    if t is None:
+        return _vp(0)
+    if t.is_cuda:
+        _DEV[0] = t.device.index
+    return _vp(t.data_ptr())
 
 
 def _stream():
-    return _vp(torch.cuda.current_stream().cuda_stream)
+    return _vp(torch.cuda.current_stream(_DEV[0]).cuda_stream)
 
 
 # Optional per-call timing for bench.py's roofline: when a list is installed with
@@ -34,6 +45,14 @@ def set_profile(sink):
 
 
 def _launch(name, *args):
+    dev = _DEV[0]
+    if dev is not None and dev != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            return _launch_here(name, *args)
+    return _launch_here(name, *args)
+
+
+def _launch_here(name, *args):
     if _PROFILE is None:
         return N.call(name, *args)
     e0 = torch.cuda.Event(enable_timing=True)
@@ -63,16 +82,25 @@ def _f32(t, name):
 
 
 # ---------------------------------------------------------------------------------------------
-# shared scratch workspace (one per device; ops on one stream run in order so it can be reused)
+# scratch workspace: one per (device, stream) — ops on one stream run in order, so they can share
+# it; two streams never do. A buffer that has been handed out is NEVER freed: a CUDA graph captured
+# earlier has its address baked in, so when a later call needs more the old buffer is retired (kept
+# alive) and a new one of at least twice the size takes over (total retired bytes < the live size).
+# During a capture the capture stream is its own key, so a graph gets a workspace of its own.
 # ---------------------------------------------------------------------------------------------
 _WS = {}
+_WS_RETIRED = []
 
 
 def workspace(nbytes, device):
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (index, torch.cuda.current_stream(index).cuda_stream)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        if buf is not None:
+            _WS_RETIRED.append(buf)
+        size = max(int(nbytes), 1 << 20, 2 * buf.numel() if buf is not None else 0)
+        buf = torch.empty(size, dtype=torch.uint8, device=torch.device("cuda", index))
         _WS[key] = buf
     return buf
 

@@ -87,7 +87,10 @@ class ResnetFeatureExtractor(torch.nn.Module):
         return wk, bias
 
     def _check_trunk_mode(self):
-        if self.resnet.training:
+        # decided from the BatchNorm layers themselves: `self.resnet` is a fresh nn.Sequential built AFTER the
+        # reference's `.eval()` (rovr/resnet_extractor.py:11-16), so its own `training` flag is True even
+        # though every child is in eval mode
+        if any(m.training for m in self.resnet.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)):
             raise NotImplementedError(
                 "ResnetFeatureExtractor (B200): the trunk must be in eval mode (frozen, as with pretrained=True, "
                 "rovr/resnet_extractor.py:11-14); a train-mode trunk is outside the ROVR hot path")

@@ -154,3 +154,30 @@ def test_resnet_encode_insert_extract(golden_dir):
     with pytest.raises(RuntimeError):
         m.resnet.eval()
         m(x.cpu())
+
+
+def test_resnet_built_like_the_reference(monkeypatch):
+    """The ONLY way the reference builds the extractor is `ResnetFeatureExtractor(pretrained=True)`
+    (rovr/rovr.py:31, rovr/imitation_learning.py:39): `.eval()` + frozen trunk inside the ctor, then
+    a fresh nn.Sequential around the children (whose own `training` flag is True). No extra .eval()
+    here. (There is no network for the weight download, so torchvision's factory is patched to
+    ignore `pretrained`; the ctor path under test is unchanged.)"""
+    import resnet_extractor as M
+    real = M.models.resnet50
+    monkeypatch.setattr(M.models, "resnet50", lambda pretrained=False: real())
+    warnings.filterwarnings("ignore")
+    torch.manual_seed(0)
+    m = M.ResnetFeatureExtractor(pretrained=True).to(_dev())
+    assert m.resnet.training and not any(c.training for c in m.resnet.children())   # the trap of ADVICE r1
+    assert m.training                                   # the module itself was never put in eval mode
+    x = torch.rand((1, 2, 3, 64, 64), generator=torch.Generator().manual_seed(1)).to(_dev())
+    fmap = m(x)
+    assert fmap.shape == (1, 3, 80, 80) and torch.isfinite(fmap).all()
+    fmap.sum().backward()
+    assert m.linear.weight.grad is not None and all(p.grad is None for p in m.resnet.parameters())
+    tile = m.encode(x[0, 0])
+    assert tile.shape == (3, 16, 16)
+    # a default-constructed (train-mode, trainable) trunk is outside the hot path and says so
+    m2 = M.ResnetFeatureExtractor().to(_dev())
+    with pytest.raises(NotImplementedError):
+        m2(x)

@@ -1,0 +1,107 @@
+"""the reference's training loop (rovr/train_local_net_unet.py:71,102-116 —
+`optimizer.zero_grad(); y = net(x, ctx); loss = mse(y, t); loss.backward(); optimizer.step()` with
+torch.optim.Adam, lr 1e-4) stepped over the drop-in, eager and through GraphedTrainingStep, against
+the same loop over the CPU fp32 oracle. Adam stays torch.optim (not a kernel target); what is
+checked here is that the drop-in's gradients arrive where the optimizer looks for them —
+including after the loop's own `zero_grad()` (set_to_none) — and that the bf16 operand copies
+follow the updated fp32 masters."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+STEPS, LR = 20, 1e-4        # rovr/train_local_net_unet.py:71 (lr), 20 steps of its loop
+TOL = 2e-2
+
+
+def _oracle_loop(sd, batches):
+    import rovr_oracle as O
+    leaf = {k: (v.clone().requires_grad_(True) if k in O.LOCALNET_LIVE else v.clone()) for k, v in sd.items()}
+    opt = torch.optim.Adam([leaf[k] for k in O.LOCALNET_LIVE], lr=LR)
+    losses = []
+    for x, c, t in batches:
+        opt.zero_grad()
+        loss = F.mse_loss(O.localnet_forward(leaf, x, c), t)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    return losses, {k: leaf[k].detach() for k in O.LOCALNET_LIVE}
+
+
+def _rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-20)).item()
+
+
+@pytest.mark.parametrize("mode", ["eager", "graphed"])
+def test_adam_loop_matches_oracle(mode):
+    import _native
+    import rovr_oracle as O
+    from local_net import GraphedTrainingStep, LocalNetworkUNetNorm
+    _native.require_device()
+    dev = torch.device("cuda:0")
+    sd = O.localnet_state_dict(0)
+    batches = [O.synthetic_localnet_batch(4, 64, 64, seed=300 + (i % 4)) for i in range(STEPS)]
+    ref_losses, ref_w = _oracle_loop(sd, batches)
+
+    net = LocalNetworkUNetNorm()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=LR)          # all 72-key parameters, like the reference
+    w0 = {n: p.detach().clone() for n, p in net.named_parameters()}
+    step = None
+    if mode == "graphed":
+        step = GraphedTrainingStep(net, *[v.to(dev) for v in batches[0]])
+        assert step.grads_alias_buckets()
+    losses = []
+    for x, c, t in batches:
+        x, c, t = x.to(dev), c.to(dev), t.to(dev)
+        opt.zero_grad()                                      # set_to_none=True in torch 2.x
+        if step is None:
+            loss = F.mse_loss(net(x, c), t)                  # the reference's own lines :105-107
+            loss.backward()
+        else:
+            loss = step(x, c, t)
+            assert step.grads_alias_buckets()                # .grad re-attached to the static buckets
+        opt.step()
+        losses.append(float(loss))
+    named = dict(net.named_parameters())
+    for i, (a, b) in enumerate(zip(losses, ref_losses)):
+        assert abs(a - b) <= TOL * abs(b), f"step {i}: loss {a} vs oracle {b}"
+    assert losses[-1] < losses[0]
+    for k, wr in ref_w.items():
+        assert not torch.equal(named[k].detach(), w0[k]), f"{k} was never updated"
+        # the update itself (w - w0) is what Adam produced: compare it, not just the weights
+        du, dr = named[k].detach().cpu() - w0[k].cpu(), wr - sd[k]
+        assert _rel(named[k], wr) < TOL, f"{k}: weights differ {_rel(named[k], wr):.3e}"
+        assert (du - dr).norm() <= 0.15 * dr.norm(), f"{k}: Adam update differs {_rel(du, dr):.3e}"
+    # the never-applied BatchNorm parameters stay without gradient, exactly as in the reference
+    assert all(p.grad is None for n, p in net.named_parameters() if n.startswith("bn"))
+
+
+def test_graphed_step_survives_larger_eager_call():
+    """a later eager call that needs a bigger scratch workspace must not free the buffer a
+    captured graph has baked in."""
+    import rovr_oracle as O
+    from local_net import GraphedTrainingStep, LocalNetworkUNetNorm
+    dev = torch.device("cuda:0")
+    net = LocalNetworkUNetNorm()
+    net.load_state_dict(O.localnet_state_dict(0), strict=True)
+    net = net.to(dev)
+    small = [v.to(dev) for v in O.synthetic_localnet_batch(1, 32, 32, seed=7)]
+    step = GraphedTrainingStep(net, *small)
+    l0 = step().clone()
+    g0 = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    big = [v.to(dev) for v in O.synthetic_localnet_batch(6, 128, 128, seed=8)]
+    _, loss = net.forward_with_mse(*big)                      # eager, much larger workspace
+    loss.backward()
+    junk = [torch.full((1 << 22,), 7.0, device=dev) for _ in range(8)]   # reuse whatever was freed
+    net.zero_grad()
+    l1 = step().clone()
+    torch.cuda.synchronize()
+    assert torch.equal(l0, l1)
+    for n, p in net.named_parameters():
+        if n in g0:
+            assert torch.equal(p.grad, g0[n]), n
+    del junk
