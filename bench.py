@@ -316,7 +316,8 @@ def run_cuda(args, rank, local_rank, world):
 
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            from data_parallel import shutdown
+            shutdown(graphed)
         return
 
     # ---- per-kernel-class roofline from the events recorded inside the timed region ----
@@ -409,7 +410,8 @@ def run_cuda(args, rank, local_rank, world):
             "cpu_baseline": cpu_base, "calls_us": call_table}
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        from data_parallel import shutdown
+        shutdown(graphed)
 
 
 def main():

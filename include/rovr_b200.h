@@ -331,6 +331,89 @@ size_t rovr_colsum_rows_workspace(int C);
 int rovr_colsum_rows(const void* g, long long ld, long long M, int C, float* out, void* ws, size_t ws_bytes,
                      void* stream);
 
+/* ---- emulated-fp32 policy trunks (csrc/fp32x.cuh) ------------------------------------------------
+ * PolicyNetwork1UNet.unet (rovr/policy_net_1.py:60-84) and PolicyNetwork2UNet.video_conv
+ * (rovr/policy_net_2.py:41-60) keep fp32 NHWC activations (`*_ld` in floats, multiples of 4) and run
+ * their convolutions as split-bf16 products on the tensor cores: an fp32 value is v = hi + mid + lo
+ * (three bf16 pieces) and the pieces are stacked along the contraction dimension, so one pass of the
+ * implicit-GEMM kernel accumulates hi*hi + mid*hi + lo*hi + hi*mid + mid*mid + hi*lo in fp32. */
+/* dst[b][oy][ox][t*cb + c_off + c] = piece(t) of max over the kh x kw window (stride sh, sw) of
+ * src[b][.][.][c] for c < C, zero for C <= c < cw; t < nterms. nterms 6: pieces [h m l h m h] (forward
+ * operand), 3: [h m h] (gradient operand), 2: [h m]. src is addressed through element strides (batch, row,
+ * column, channel), so NHWC views and NCHW tensors both work; with src2 != NULL channels c_split .. C are
+ * read from src2 (same strides): torch.cat([image, context], 1) of rovr/policy_net_1.py:88 without the
+ * copy. kh = kw = sh = sw = 1: no pooling.
+ * Replaces F.max_pool2d + the operand conversion in front of every convolution of the trunks. */
+int rovr_split_stack(const float* src, const float* src2, int c_split, long long s_b, long long s_y,
+                     long long s_x, long long s_c, int B, int H, int W, int C, int kh, int kw, int sh, int sw,
+                     void* dst, int dst_ld, int cb, int c_off, int cw, int nterms, void* stream);
+/* weight side of the same products: w fp32 [d0][d1][inner] -> out fp32 with dim stack_dim (0 / 1) replaced
+ * by nterms blocks of cb entries holding pieces [h h h m m l] (nterms 6) or [h h m] (3); zero padding for
+ * entries >= the original extent. The rovr_repack_* calls then make the bf16 operands (exactly). */
+int rovr_split_weights(const float* w, float* out, int d0, int d1, int inner, int stack_dim, int nterms,
+                       int cb, void* stream);
+/* weight gradient of a stacked product: dwp fp32 [2*cb0][2*cb1][inner] -> dw[i][j][t] = sum of its four
+ * blocks (i < d0, j < d1) */
+int rovr_blocksum4(const float* dwp, float* dw, int d0, int d1, int inner, int cb0, int cb1, void* stream);
+/* Conv2d 3x3 pad 1 with fp32 NHWC output (forward; or, with the rovr_repack_conv3x3_dgrad operand and
+ * Cin / Cout swapped by the caller, the data gradient) */
+int rovr_conv3x3_f32out(const void* x, int x_ld, const void* wk, const float* bias, float* y, int y_ld,
+                        int B, int H, int W, int Cin, int Cout, int relu, void* stream);
+/* ConvTranspose2d k2 s2 with fp32 NHWC output / input gradient */
+int rovr_convT2x2_fprop_f32out(const void* x, int x_ld, const void* wk, const float* bias, float* y, int y_ld,
+                               int B, int H, int W, int Cin, int Cout, int relu, void* stream);
+int rovr_convT2x2_dgrad_f32out(const void* dy, int dy_ld, const void* wk_d, float* dx, int dx_ld, int B, int H,
+                               int W, int Cin, int Cout, void* stream);
+/* nn.BatchNorm2d (+ReLU) on fp32 NHWC views, semantics of rovr_bn_train_fwd / rovr_bn_eval_fwd /
+ * rovr_bn_train_bwd (two-pass centred variance, fp64 combine). ws >= rovr_bn_workspace(C). */
+int rovr_bn_f32_train_fwd(const float* x, int x_ld, float* y, int y_ld, long long npix, int C, int c_valid,
+                          const float* gamma, const float* beta, float eps, float momentum,
+                          float* running_mean, float* running_var, long long* num_batches_tracked,
+                          float* mean, float* rstd, int relu, void* ws, size_t ws_bytes, void* stream);
+int rovr_bn_f32_eval_fwd(const float* x, int x_ld, float* y, int y_ld, long long npix, int C, int c_valid,
+                         const float* gamma, const float* beta, float eps, const float* running_mean,
+                         const float* running_var, float* rstd, int relu, void* stream);
+int rovr_bn_f32_bwd(const float* dy, int dy_ld, const float* y, int y_ld, const float* x, int x_ld, float* dx,
+                    int dx_ld, long long npix, int C, int c_valid, const float* gamma, const float* mean,
+                    const float* rstd, float* dgamma, float* dbeta, int relu, int eval_mode, void* ws,
+                    size_t ws_bytes, void* stream);
+/* out[c] = sum over pixels of an fp32 NHWC view; ws >= rovr_bn_workspace(C) */
+int rovr_colsum_f32(const float* g, int ld, long long npix, int C, float* out, void* ws, size_t ws_bytes,
+                    void* stream);
+/* nn.MaxPool2d on fp32 NHWC views (arg-max = first maximum in row-major window order, like ATen);
+ * bwd: gx = [gskip +] scatter of gp to the arg-max of each window */
+int rovr_maxpool_f32_fwd(const float* x, int x_ld, float* y, int y_ld, int B, int H, int W, int C, int kh,
+                         int kw, int sh, int sw, void* stream);
+int rovr_maxpool_f32_bwd(const float* x, int x_ld, const float* gp, int gp_ld, const float* gskip, int gs_ld,
+                         float* gx, int gx_ld, int B, int H, int W, int C, int kh, int kw, int sh, int sw,
+                         void* stream);
+/* nn.Flatten on the NCHW view of an fp32 NHWC tensor and its inverse: rows[b][c*HW + p] <-> x[b][p][c] */
+int rovr_flatten_f32(const float* x, int ld, float* rows, long long rows_ld, int B, int HW, int C, void* stream);
+int rovr_unflatten_f32(const float* rows, long long rows_ld, float* x, int ld, int B, int HW, int C, int cpad,
+                       void* stream);
+
+/* ---- LPIPS(net='vgg') perceptual loss (csrc/lpips.cuh) ------------------------------
+ * lpips.LPIPS(net='vgg')(in0, in1[, normalize=True]) of rovr/train_local_net_unet.py:91,109 and
+ * rovr/rovr.py:54,255. The VGG16 convolutions run through rovr_conv3x3_fprop[_pool2] / rovr_conv3x3_dgrad /
+ * rovr_maxpool_bwd on a 2N batch ([in0 ; in1]); these are the remaining pieces. */
+/* ScalingLayer + pack: dst [2N][H][W][16] bf16, channel c < 3 = ((normalize ? 2v-1 : v) - shift[c]) / scale[c];
+ * shift3 / scale3 are HOST pointers to three floats. */
+int rovr_lpips_pack(const float* in0, const float* in1, void* dst, int N, int H, int W, const float* shift3,
+                    const float* scale3, int normalize, void* stream);
+/* one tap: feats [2N][hw][C] bf16, lin_w fp32 [C]; partial [N][nblocks] receives per-block sums of
+ * sum_c w_c (f0_c/(|f0|+1e-10) - f1_c/(|f1|+1e-10))^2; grad (optional, [N][hw][C] bf16) = (1/hw) * d/d f0 of it,
+ * masked by f0 > 0. nblocks = rovr_lpips_head_blocks(N, hw). */
+int rovr_lpips_head_blocks(int N, long long hw);
+int rovr_lpips_head(const void* feats, int N, long long hw, int C, const float* lin_w, void* grad, float* partial,
+                    int nblocks, void* stream);
+/* val[n] = sum over taps of (sum of partial blocks) / hw; partials / nblocks / hws are HOST arrays of ntaps entries */
+int rovr_lpips_finalize(const float* const* partials, const int* nblocks, const long long* hws, int ntaps, int N,
+                        float* val, void* stream);
+/* gradient w.r.t. the packed input [N][H][W][16] bf16 -> d/d in0 NCHW fp32, times the per-image upstream
+ * gradient gval[n] (device, fp32) */
+int rovr_lpips_unpack_grad(const void* gx16, const float* gval, float* gout, int N, int H, int W,
+                           const float* shift3, const float* scale3, int normalize, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -548,3 +548,72 @@ def resnet_extractor_forward(resnet_seq, linear_w, linear_b, x):
             r, c = s // 5 * 16, s % 5 * 16
             fmap[bi, :, r:r + 16, c:c + 16] = tile
     return fmap
+
+
+# ------------------------------------------------------------------------------------------------
+# LPIPS (net='vgg') perceptual loss — SURVEY §8f-1. Call sites: rovr/train_local_net_unet.py:91,109
+# (`lpips.LPIPS(net='vgg')(y_hat, target).mean()`, normalize=False) and rovr/rovr.py:54,84,255
+# (normalize=True). The `lpips` package (version unpinned by the reference) is NOT in this image and
+# its trained weights need a download: PARITY UNPINNED against the package. This is a restatement of
+# its published v0.1 algorithm (Zhang et al. 2018, `lpips/lpips.py`):
+#     ScalingLayer: (x - shift) / scale, shift = [-.030, -.088, -.188], scale = [.458, .448, .450]
+#     torchvision VGG16 `features` tapped after relu1_2, relu2_2, relu3_3, relu4_3, relu5_3
+#     normalize_tensor: x / (sqrt(sum_c x^2) + 1e-10)
+#     per tap: 1x1 conv (no bias, lin weights [1, C, 1, 1]) of (f0 - f1)^2, spatial mean; sum over taps
+#     (the package runs in eval mode: its Dropout in front of the 1x1 conv is inactive)
+# The VGG16 structure is pinned to torchvision.models.vgg16 (tests/golden/lpips.npz is generated by
+# running torchvision's own `features` with the seeded weights below).
+# ------------------------------------------------------------------------------------------------
+LPIPS_SHIFT = (-0.030, -0.088, -0.188)
+LPIPS_SCALE = (0.458, 0.448, 0.450)
+# torchvision vgg16().features indices of the 13 convolutions, grouped by LPIPS slice; a MaxPool2d(2, 2)
+# precedes every slice but the first
+VGG16_SLICES = [[(0, 3, 64), (2, 64, 64)], [(5, 64, 128), (7, 128, 128)],
+                [(10, 128, 256), (12, 256, 256), (14, 256, 256)],
+                [(17, 256, 512), (19, 512, 512), (21, 512, 512)],
+                [(24, 512, 512), (26, 512, 512), (28, 512, 512)]]
+LPIPS_CHNS = [64, 128, 256, 512, 512]
+
+
+def lpips_state_dict(seed=0):
+    """Deterministic weights in the key layout of lpips.LPIPS(net='vgg').state_dict():
+    net.slice{k}.{idx}.weight/bias (torchvision feature indices), lin{k}.model.1.weight [1, C, 1, 1]
+    (non-negative, like the trained ones), scaling_layer.shift / scale."""
+    gen = torch.Generator().manual_seed(seed)
+    sd = {"scaling_layer.shift": torch.tensor(LPIPS_SHIFT).view(1, 3, 1, 1),
+          "scaling_layer.scale": torch.tensor(LPIPS_SCALE).view(1, 3, 1, 1)}
+    for k, convs in enumerate(VGG16_SLICES):
+        for idx, cin, cout in convs:
+            sd[f"net.slice{k + 1}.{idx}.weight"] = _fill(gen, (cout, cin, 3, 3), math.sqrt(6.0 / (cin * 9)))
+            sd[f"net.slice{k + 1}.{idx}.bias"] = _fill(gen, (cout,), 0.1)
+    for k, c in enumerate(LPIPS_CHNS):
+        sd[f"lin{k}.model.1.weight"] = (_fill(gen, (1, c, 1, 1), 1.0).abs() + 0.05) * (4.0 / c)
+    return sd
+
+
+def lpips_vgg_features(sd, x):
+    """The five tapped activations of torchvision VGG16 `features` for an already-scaled input."""
+    feats = []
+    for k, convs in enumerate(VGG16_SLICES):
+        if k > 0:
+            x = F.max_pool2d(x, 2, 2)
+        for idx, _, _ in convs:
+            x = F.relu(F.conv2d(x, sd[f"net.slice{k + 1}.{idx}.weight"], sd[f"net.slice{k + 1}.{idx}.bias"], padding=1))
+        feats.append(x)
+    return feats
+
+
+def lpips_vgg(sd, in0, in1, normalize=False):
+    """lpips.LPIPS(net='vgg').forward(in0, in1, normalize=normalize) -> [N, 1, 1, 1]."""
+    if normalize:
+        in0, in1 = 2 * in0 - 1, 2 * in1 - 1
+    shift, scale = sd["scaling_layer.shift"], sd["scaling_layer.scale"]
+    f0s = lpips_vgg_features(sd, (in0 - shift) / scale)
+    f1s = lpips_vgg_features(sd, (in1 - shift) / scale)
+    val = 0.0
+    for k, (f0, f1) in enumerate(zip(f0s, f1s)):
+        n0 = f0 / (torch.sqrt(torch.sum(f0 ** 2, dim=1, keepdim=True)) + 1e-10)
+        n1 = f1 / (torch.sqrt(torch.sum(f1 ** 2, dim=1, keepdim=True)) + 1e-10)
+        d = F.conv2d((n0 - n1) ** 2, sd[f"lin{k}.model.1.weight"])
+        val = val + d.mean([2, 3], keepdim=True)
+    return val

@@ -106,6 +106,25 @@ SIGNATURES = {
     "rovr_colsum_rows_workspace": (_sz, [_i]),
     "rovr_colsum_rows": (_i, [_p, _ll, _ll, _i, _p, _p, _sz, _p]),
     "rovr_colsum": (_i, [_p, _i, _ll, _i, _p, _p, _sz, _p]),
+    "rovr_split_stack": (_i, [_p, _p, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p]),
+    "rovr_split_weights": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_blocksum4": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "rovr_conv3x3_f32out": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_convT2x2_fprop_f32out": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_convT2x2_dgrad_f32out": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_bn_f32_train_fwd": (_i, [_p, _i, _p, _i, _ll, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
+    "rovr_bn_f32_eval_fwd": (_i, [_p, _i, _p, _i, _ll, _i, _i, _p, _p, _f, _p, _p, _p, _i, _p]),
+    "rovr_bn_f32_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _i, _ll, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p, _sz, _p]),
+    "rovr_colsum_f32": (_i, [_p, _i, _ll, _i, _p, _p, _sz, _p]),
+    "rovr_maxpool_f32_fwd": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_maxpool_f32_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_flatten_f32": (_i, [_p, _i, _p, _ll, _i, _i, _i, _p]),
+    "rovr_unflatten_f32": (_i, [_p, _ll, _p, _i, _i, _i, _i, _i, _p]),
+    "rovr_lpips_pack": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _i, _p]),
+    "rovr_lpips_head_blocks": (_i, [_i, _ll]),
+    "rovr_lpips_head": (_i, [_p, _i, _ll, _i, _p, _p, _p, _i, _p]),
+    "rovr_lpips_finalize": (_i, [_p, _p, _p, _i, _i, _p, _p]),
+    "rovr_lpips_unpack_grad": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _i, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

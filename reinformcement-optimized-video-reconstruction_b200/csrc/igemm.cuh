@@ -112,7 +112,8 @@ struct IgemmParams {
                           // gradient is masked later by the pool backward that consumes it)
   int cs_cols;            // column sums are wanted for columns < cs_cols only
   long long mstride[4];   // mask element stride per tiled dim
-  float* out_f32;         // non-null: direct fp32 epilogue (plain mode) instead of the TMA store
+  float* out_f32;         // non-null: direct fp32 epilogue (dimM / ostride address the rows; with IG_EPI_PIXSHUF the
+                          // quadrant offsets are ostride[0] (qx) and ostride[2] (qy)) instead of the TMA store
   float* colsum_partial;  // non-null: per-(M tile, lane quarter) column sums of the bf16 output,
                           // [m_tiles * 4][n_total] fp32 — the bias gradient of the layer that
                           // consumes this gradient tensor, reduced afterwards in a fixed order
@@ -537,7 +538,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tmem_ld16(t_row + static_cast<uint32_t>(c * 16), v);
           tmem_ld_wait();
           if (valid) {
-            float4* op = reinterpret_cast<float4*>(p.out_f32 + obase + n0);
+            // pixel-shuffle (ConvTranspose2d k2 s2): column n = q * Cout + c lands in sub-pixel q = (qy, qx) of
+            // the 2x2 block of this input pixel; a 16-column chunk never straddles two quadrants (Cout % 16 == 0)
+            long long ocol = n0;
+            if (p.epi_mode == IG_EPI_PIXSHUF) {
+              const int q = n0 / p.shuf_cout;
+              ocol = (n0 - q * p.shuf_cout) + (q & 1) * p.ostride[0] + (q >> 1) * p.ostride[2];
+            }
+            float4* op = reinterpret_cast<float4*>(p.out_f32 + obase + ocol);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float f[4];

@@ -15,6 +15,8 @@
 #include <mutex>
 
 #include "elementwise.cuh"
+#include "fp32x.cuh"
+#include "lpips.cuh"
 #include "igemm.cuh"
 #include "norm.cuh"
 #include "policy.cuh"
@@ -442,6 +444,8 @@ extern "C" int rovr_maxpool_bwd(const void* x, int x_ld, const void* gp, int gp_
 // normalisation, fp32 linear layers, policy heads, LSTM
 // ------------------------------------------------------------------------------------------------
 #include "api_policy.inc"
+#include "api_fp32x.inc"
+#include "api_lpips.inc"
 #include "api_resnet.inc"
 #include "api_attention.inc"
 

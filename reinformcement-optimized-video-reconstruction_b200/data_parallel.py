@@ -85,6 +85,85 @@ class GradientBuckets:
         self.pending = []
 
 
+class GradientAverager:
+    """Gradient averaging for ANY module after `loss.backward()` (policy networks, the frame-feature
+    projection, attention blocks): the IL / PPO steps of rovr/imitation_learning.py:83-100 and
+    rovr/rovr.py:299-334 sharded by whole clip (train-mode BatchNorm and the batch-dim
+    standardisation keep per-replica statistics = the reference's per-clip batch; only gradients are
+    reduced).
+
+    The trunk Functions write all their parameter gradients into one flat arena (_blocks.GradArena), so
+    every gradient that shares a storage with others is reduced by ONE collective over that storage; the
+    remaining (head) gradients are flattened together into one more. Call `average()` after backward."""
+
+    def __init__(self, module, process_group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.module = module
+        self.group = process_group
+        self.world = dist.get_world_size(process_group)
+        self.on_gpu = dist.get_backend(process_group) == "nccl"
+        self.collectives = 0
+
+    def _allreduce(self, flat):
+        self.collectives += 1
+        if self.on_gpu:
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(self.world)
+
+    def average(self):
+        if self.world == 1:
+            return
+        shared, loose = {}, []
+        for p in self.module.parameters():
+            g = p.grad
+            if g is None:
+                continue
+            st = g.untyped_storage()
+            if st.nbytes() > g.numel() * g.element_size() and g.dtype == torch.float32:
+                shared.setdefault(st.data_ptr(), (st, g))
+            else:
+                loose.append(g)
+        for st, g in shared.values():          # a whole arena: one collective, in place
+            flat = torch.empty(0, dtype=torch.float32, device=g.device).set_(st)
+            self._allreduce(flat)
+        if loose:
+            flat = torch.cat([g.reshape(-1) for g in loose])
+            self._allreduce(flat)
+            off = 0
+            for g in loose:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+
+
+def shutdown(*graphed_steps, grace_s=30.0):
+    """Orderly end of a data-parallel process: destroy the CUDA graphs that captured collectives, then the
+    process group. NCCL's communicator teardown can block if anything still references captured
+    collectives, so a daemon timer ends the process (exit code 0, all results are already written by
+    then) if the teardown has not returned after `grace_s` seconds."""
+    import os
+    import sys
+    import threading
+    for g in graphed_steps:
+        if g is not None:
+            g.close()
+    if not dist.is_initialized():
+        return
+    sys.stdout.flush()
+    sys.stderr.flush()
+    timer = threading.Timer(grace_s, lambda: os._exit(0))
+    timer.daemon = True
+    timer.start()
+    try:
+        torch.cuda.synchronize() if torch.cuda.is_available() else None
+        dist.barrier()
+        dist.destroy_process_group()
+    finally:
+        timer.cancel()
+
+
 def broadcast_parameters(module, src=0, process_group=None):
     """Make every replica start from rank `src`'s parameters and buffers. The broadcast writes the
     parameter itself (under no_grad), which bumps its version counter, so the cached bf16 operand

@@ -413,6 +413,15 @@ class GraphedTrainingStep:
         net._grad_bucket_hook, net._grad_bucket_wait = hooks[0], hooks[1]
         self._bind_grads()
 
+    def close(self):
+        """Destroy the captured graph. With NCCL collectives captured inside it this MUST happen before
+        `dist.destroy_process_group()`: NCCL does not tear a communicator down while a CUDA graph that
+        captured its collectives is alive (the teardown blocks forever)."""
+        if getattr(self, "graph", None) is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+
     def _bind_grads(self):
         for n, p in self.P.items():
             if p.requires_grad:

@@ -921,3 +921,253 @@ def posenc_grad(g, n1, which):
     gb = torch.empty(D, dtype=torch.float32, device=g.device)
     _launch("rovr_posenc_grad", _ptr(g), B, P, D, n1, which, _ptr(gw), _ptr(gb), _stream())
     return gw, gb
+
+
+# ---------------------------------------------------------------------------------------------
+# emulated-fp32 policy trunks (csrc/fp32x.cuh): fp32 NHWC activations, split-bf16 stacked operands
+# ---------------------------------------------------------------------------------------------
+def _actf(t, name="activation"):
+    """Validate an NHWC fp32 view and return (B, H, W, C, ld)."""
+    if t.dtype != torch.float32 or not t.is_cuda or t.dim() != 4:
+        raise ValueError(f"{name}: expected a 4-D CUDA fp32 NHWC tensor, got {t.dtype} {tuple(t.shape)}")
+    B, H, W, C = t.shape
+    ld = t.stride(2)
+    if t.stride(3) != 1 or t.stride(1) != W * ld or (B > 1 and t.stride(0) != H * W * ld) or ld % 4:
+        raise ValueError(f"{name}: not a dense-pixel NHWC view, strides={t.stride()}")
+    return B, H, W, C, ld
+
+
+def pad8(c):
+    return (c + 7) // 8 * 8
+
+
+def split_stack(src, nterms, cb, layout="nhwc", pool=None, out=None, src2=None):
+    """Stacked bf16 pieces of an fp32 tensor: out[b, y, x, t*cb + c] = piece_t(maxpool(src)[b, y, x, c]),
+    zero for c >= C. src: NHWC fp32 view (layout "nhwc") or NCHW fp32 tensor ("nchw"; src2 = a second
+    NCHW tensor of the same shape concatenated behind it along C). pool: None or (kh, kw, sh, sw).
+    nterms 6 -> forward operand [h m l h m h], 3 -> gradient operand [h m h]."""
+    c_split = 0
+    if layout == "nhwc":
+        B, H, W, C, ld = _actf(src, "split source")
+        sb, sy, sx, sc = H * W * ld, W * ld, ld, 1
+        assert src2 is None
+    else:
+        _f32(src, "split source")
+        B, C, H, W = src.shape
+        sb, sy, sx, sc = C * H * W, W, 1, H * W
+        if src2 is not None:
+            _f32(src2, "split source 2")
+            assert src2.shape == src.shape
+            c_split, C = C, 2 * C
+    kh, kw, sh, sw = pool if pool is not None else (1, 1, 1, 1)
+    Ho, Wo = (H - kh) // sh + 1, (W - kw) // sw + 1
+    assert cb >= C and cb % 2 == 0
+    if out is None:
+        out = torch.empty((B, Ho, Wo, nterms * cb), dtype=torch.bfloat16, device=src.device)
+    _launch("rovr_split_stack", _ptr(src), _ptr(src2), c_split, sb, sy, sx, sc, B, H, W, C, kh, kw, sh, sw, _ptr(out), out.stride(2), cb, 0,
+            cb, nterms, _stream())
+    return out
+
+
+def split_weights(w, stack_dim, nterms, cb):
+    """fp32 weight [d0, d1, ...] -> fp32 [.., nterms*cb, ..] stacked pieces along dim 0 or 1 (zero padded)."""
+    _f32(w, "weight")
+    d0, d1 = w.shape[0], w.shape[1]
+    inner = w.numel() // (d0 * d1)
+    shape = list(w.shape)
+    shape[stack_dim] = nterms * cb
+    out = torch.empty(shape, dtype=torch.float32, device=w.device)
+    _launch("rovr_split_weights", _ptr(w), _ptr(out), d0, d1, inner, stack_dim, nterms, cb, _stream())
+    return out
+
+
+def blocksum4(dwp, dw, cb0, cb1):
+    """dw[i, j, ...] = sum of the four [cb0, cb1] blocks of dwp [2*cb0, 2*cb1, ...]."""
+    _f32(dwp, "dwp")
+    _f32(dw, "dw")
+    d0, d1 = dw.shape[0], dw.shape[1]
+    inner = dw.numel() // (d0 * d1)
+    assert dwp.shape[0] == 2 * cb0 and dwp.shape[1] == 2 * cb1 and dwp.numel() == 4 * cb0 * cb1 * inner
+    _launch("rovr_blocksum4", _ptr(dwp), _ptr(dw), d0, d1, inner, cb0, cb1, _stream())
+    return dw
+
+
+def conv3x3_f32out(x, wk, bias, y, relu=False):
+    """y (fp32 NHWC view) = conv3x3(x bf16 stacked operand) + bias; also the data gradient when wk is the
+    dgrad-packed operand (then x = stacked dy and y = dx)."""
+    B, H, W, Cin, x_ld = _act(x, "x")
+    By, Hy, Wy, Cout, y_ld = _actf(y, "y")
+    assert (B, H, W) == (By, Hy, Wy) and wk.shape == (Cout, 9 * Cin), (x.shape, y.shape, wk.shape)
+    _f32(bias, "bias")
+    _launch("rovr_conv3x3_f32out", _ptr(x), x_ld, _ptr(wk), _ptr(bias), _ptr(y), y_ld, B, H, W, Cin, Cout, int(relu),
+            _stream())
+    return y
+
+
+def convT2x2_fprop_f32out(x, wk, bias, y, relu=False):
+    B, H, W, Cin, x_ld = _act(x, "x")
+    By, Hy, Wy, Cout, y_ld = _actf(y, "y")
+    assert (By, Hy, Wy) == (B, 2 * H, 2 * W) and wk.shape == (4 * Cout, Cin), (x.shape, y.shape, wk.shape)
+    _f32(bias, "bias")
+    _launch("rovr_convT2x2_fprop_f32out", _ptr(x), x_ld, _ptr(wk), _ptr(bias), _ptr(y), y_ld, B, H, W, Cin, Cout,
+            int(relu), _stream())
+    return y
+
+
+def convT2x2_dgrad_f32out(dy, wk_d, dx):
+    By, Hy, Wy, Cout, dy_ld = _act(dy, "dy")
+    B, H, W, Cin, dx_ld = _actf(dx, "dx")
+    assert (By, Hy, Wy) == (B, 2 * H, 2 * W) and wk_d.shape == (Cin, 4 * Cout), (dy.shape, dx.shape, wk_d.shape)
+    _launch("rovr_convT2x2_dgrad_f32out", _ptr(dy), dy_ld, _ptr(wk_d), _ptr(dx), dx_ld, B, H, W, Cin, Cout, _stream())
+    return dx
+
+
+def bn_f32_train_fwd(x, y, gamma, beta, c_valid, eps, momentum, running_mean, running_var, nbt, relu=True):
+    B, H, W, C, x_ld = _actf(x, "x")
+    _, _, _, Cy, y_ld = _actf(y, "y")
+    assert Cy == C
+    mean = torch.empty(C, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(C, dtype=torch.float32, device=x.device)
+    ws = workspace(N.lib.rovr_bn_workspace(C), x.device)
+    _launch("rovr_bn_f32_train_fwd", _ptr(x), x_ld, _ptr(y), y_ld, B * H * W, C, c_valid, _ptr(gamma), _ptr(beta),
+            ctypes.c_float(eps), ctypes.c_float(momentum), _ptr(running_mean), _ptr(running_var), _ptr(nbt),
+            _ptr(mean), _ptr(rstd), int(relu), _ptr(ws), ws.numel(), _stream())
+    return mean, rstd
+
+
+def bn_f32_eval_fwd(x, y, gamma, beta, c_valid, eps, running_mean, running_var, relu=True):
+    B, H, W, C, x_ld = _actf(x, "x")
+    _, _, _, Cy, y_ld = _actf(y, "y")
+    assert Cy == C
+    rstd = torch.empty(C, dtype=torch.float32, device=x.device)
+    _launch("rovr_bn_f32_eval_fwd", _ptr(x), x_ld, _ptr(y), y_ld, B * H * W, C, c_valid, _ptr(gamma), _ptr(beta),
+            ctypes.c_float(eps), _ptr(running_mean), _ptr(running_var), _ptr(rstd), int(relu), _stream())
+    return rstd
+
+
+def bn_f32_bwd(dy, y, x, dx, gamma, mean, rstd, c_valid, dgamma, dbeta, relu=True, eval_mode=False):
+    B, H, W, C, dy_ld = _actf(dy, "dy")
+    _, _, _, _, y_ld = _actf(y, "y")
+    _, _, _, _, x_ld = _actf(x, "x")
+    _, _, _, _, dx_ld = _actf(dx, "dx")
+    ws = workspace(N.lib.rovr_bn_workspace(C), x.device)
+    _launch("rovr_bn_f32_bwd", _ptr(dy), dy_ld, _ptr(y), y_ld, _ptr(x), x_ld, _ptr(dx), dx_ld, B * H * W, C, c_valid,
+            _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dgamma), _ptr(dbeta), int(relu), int(eval_mode), _ptr(ws),
+            ws.numel(), _stream())
+    return dx
+
+
+def colsum_f32(g, out):
+    B, H, W, C, ld = _actf(g, "g")
+    _f32(out, "out")
+    assert out.numel() == C
+    ws = workspace(N.lib.rovr_bn_workspace(C), g.device)
+    _launch("rovr_colsum_f32", _ptr(g), ld, B * H * W, C, _ptr(out), _ptr(ws), ws.numel(), _stream())
+    return out
+
+
+def maxpool_f32_fwd(x, kernel, stride=None, out=None):
+    kh, kw = _pair(kernel)
+    sh, sw = _pair(stride if stride is not None else kernel)
+    B, H, W, C, x_ld = _actf(x, "x")
+    Ho, Wo = (H - kh) // sh + 1, (W - kw) // sw + 1
+    if out is None:
+        out = torch.empty((B, Ho, Wo, C), dtype=torch.float32, device=x.device)
+    _, _, _, _, y_ld = _actf(out, "y")
+    _launch("rovr_maxpool_f32_fwd", _ptr(x), x_ld, _ptr(out), y_ld, B, H, W, C, kh, kw, sh, sw, _stream())
+    return out
+
+
+def maxpool_f32_bwd(x, gp, gx, kernel, stride=None, gskip=None):
+    """gx = [gskip +] maxpool_backward(gp) with the arg-max recomputed from the fp32 activation x."""
+    kh, kw = _pair(kernel)
+    sh, sw = _pair(stride if stride is not None else kernel)
+    B, H, W, C, x_ld = _actf(x, "x")
+    _, _, _, _, gp_ld = _actf(gp, "gp")
+    _, _, _, _, gx_ld = _actf(gx, "gx")
+    gs_ld = 0
+    if gskip is not None:
+        _, _, _, _, gs_ld = _actf(gskip, "gskip")
+    _launch("rovr_maxpool_f32_bwd", _ptr(x), x_ld, _ptr(gp), gp_ld, _ptr(gskip), gs_ld, _ptr(gx), gx_ld, B, H, W, C,
+            kh, kw, sh, sw, _stream())
+    return gx
+
+
+def flatten_f32(x, C, out, col_off=0):
+    """out[b, col_off + c*H*W + p] = x[b, p, c] for c < C (nn.Flatten of the NCHW view)."""
+    B, H, W, _, ld = _actf(x, "x")
+    _, _, out_ld = _rows(out, "out")
+    _launch("rovr_flatten_f32", _ptr(x), ld, _ptr(out[:, col_off:]), out_ld, B, H * W, C, _stream())
+    return out
+
+
+def unflatten_f32(rows, C, out, col_off=0):
+    B, H, W, cpad, ld = _actf(out, "out")
+    _, _, src_ld = _rows(rows, "rows")
+    _launch("rovr_unflatten_f32", _ptr(rows[:, col_off:]), src_ld, _ptr(out), ld, B, H * W, C, cpad, _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# LPIPS(net='vgg') head (csrc/lpips.cuh)
+# ---------------------------------------------------------------------------------------------
+def _f3(vals):
+    return (ctypes.c_float * 3)(*[float(v) for v in vals])
+
+
+def lpips_pack(in0, in1, shift, scale, normalize):
+    """ScalingLayer of both images -> one NHWC bf16 batch [2N, H, W, 16] (in0 first)."""
+    _f32(in0, "in0")
+    _f32(in1, "in1")
+    N, C, H, W = in0.shape
+    assert C == 3 and in1.shape == in0.shape
+    out = torch.empty((2 * N, H, W, 16), dtype=torch.bfloat16, device=in0.device)
+    _launch("rovr_lpips_pack", _ptr(in0), _ptr(in1), _ptr(out), N, H, W, _f3(shift), _f3(scale), int(normalize), _stream())
+    return out
+
+
+def lpips_head(feats, lin_w, want_grad):
+    """feats [2N, h, w, C] bf16 -> (partial [N, nblocks] fp32, grad [N, h, w, C] bf16 | None)."""
+    B2, h, w, C, ld = _act(feats, "feats")
+    assert ld == C and B2 % 2 == 0 and feats.is_contiguous()
+    N = B2 // 2
+    _f32(lin_w, "lin_w")
+    assert lin_w.numel() == C
+    nb = N_lib_head_blocks(N, h * w)
+    partial = torch.empty((N, nb), dtype=torch.float32, device=feats.device)
+    grad = torch.empty((N, h, w, C), dtype=torch.bfloat16, device=feats.device) if want_grad else None
+    _launch("rovr_lpips_head", _ptr(feats), N, h * w, C, _ptr(lin_w), _ptr(grad), _ptr(partial), nb, _stream())
+    return partial, grad
+
+
+def N_lib_head_blocks(N_img, hw):
+    nb = N.lib.rovr_lpips_head_blocks(N_img, hw)
+    if nb <= 0:
+        raise N.RovrError("lpips_head_blocks: " + N.last_error())
+    return nb
+
+
+def lpips_finalize(partials, hws, n_img):
+    """partials: list of [N, nblocks] fp32 tensors (one per tap), hws: pixels per tap -> val [N] fp32."""
+    k = len(partials)
+    ptrs = (ctypes.c_void_p * k)(*[p.data_ptr() for p in partials])
+    nbs = (ctypes.c_int * k)(*[p.shape[1] for p in partials])
+    hw = (ctypes.c_longlong * k)(*[int(v) for v in hws])
+    val = torch.empty(n_img, dtype=torch.float32, device=partials[0].device)
+    for p in partials:
+        _ptr(p)
+    _launch("rovr_lpips_finalize", ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(nbs, ctypes.c_void_p),
+            ctypes.cast(hw, ctypes.c_void_p), k, n_img, _ptr(val), _stream())
+    return val
+
+
+def lpips_unpack_grad(gx16, gval, shift, scale, normalize):
+    """gradient w.r.t. the packed input [N, H, W, 16] bf16 -> d/d in0 [N, 3, H, W] fp32, times gval[n]."""
+    Nn, H, W, C, ld = _act(gx16, "gx16")
+    assert C == 16 and ld == 16
+    _f32(gval, "gval")
+    assert gval.numel() == Nn
+    out = torch.empty((Nn, 3, H, W), dtype=torch.float32, device=gx16.device)
+    _launch("rovr_lpips_unpack_grad", _ptr(gx16), _ptr(gval), _ptr(out), Nn, H, W, _f3(shift), _f3(scale),
+            int(normalize), _stream())
+    return out

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 import ops
-from _blocks import BF, PackedWeights, TrunkOps
+from _blocks import BF, F32, PackedWeights, TrunkOps, TrunkOpsF32
 from _heads import GumbelLogProb, LinearF32, MaskedLogits, Standardize, exponential_like
 
 _VC = [("video_conv.0", "video_conv.1"), ("video_conv.4", "video_conv.5"),
@@ -92,6 +92,74 @@ class _VideoConvStacked(torch.autograd.Function):
         return (None, None, gfeat) + tuple(T.G[n] for n in _LIVE)
 
 
+class _VideoConvStackedF32(torch.autograd.Function):
+    """The same on the emulated-fp32 path (_blocks.TrunkOpsF32): the 8x8 and 4x4 max-pools decide their
+    arg-max on fp32-class convolution outputs, so the gradients match the fp32 reference."""
+
+    @staticmethod
+    def forward(ctx, net, image, feat, *plist):
+        P = dict(zip(_LIVE, plist))
+        T = TrunkOpsF32(P, dict(net.named_buffers()), net._packed, training=net.training)
+        dev = image.device
+        b, _, H, W = image.shape
+
+        def buf(h, w, c):
+            return torch.empty((b, h, w, c), dtype=F32, device=dev)
+
+        a = {}
+        xs = ops.split_stack(image, 6, 8, layout="nchw")                 # [b, H, W, 48]: 1 valid channel per block
+        a["a0"] = buf(H, W, 64)
+        a["r0"] = T.cbr3_fwd(*_VC[0], xs, a["a0"])
+        h1, w1 = H // 8, W // 8
+        a["a4"] = buf(h1, w1, 128)
+        a["r4"] = T.cbr3_fwd(*_VC[1], T.stack6(a["a0"], (8, 8, 8, 8)), a["a4"])      # MaxPool2d(8, 8) (:46)
+        h2, w2 = h1 // 4, w1 // 4
+        a["a8"] = buf(h2, w2, 256)
+        a["r8"] = T.cbr3_fwd(*_VC[2], T.stack6(a["a4"], (4, 4, 4, 4)), a["a8"])      # MaxPool2d(4, 4) (:50)
+        a["a12"] = buf(h2, w2, 512)                                      # MaxPool2d(1, 1) is the identity (:53)
+        a["r12"] = T.cbr3_fwd(*_VC[3], T.stack6(a["a8"]), a["a12"])
+        a["q"] = ops.maxpool_f32_fwd(a["a12"], 2, (2, 1))                # :57
+        a["r"] = ops.maxpool_f32_fwd(a["q"], 2, (2, 2))                  # :58
+        h4, w4 = a["r"].shape[1], a["r"].shape[2]
+        nvid = 512 * h4 * w4
+        stacked = torch.empty((b, nvid + feat.shape[1]), dtype=F32, device=dev)
+        ops.flatten_f32(a["r"], 512, stacked, 0)                         # nn.Flatten on NCHW (:59)
+        ops.copy2d_f32(feat, stacked[:, nvid:])                          # torch.cat([vector_out, image_out], 1) (:92)
+        ctx.net, ctx.acts, ctx.T, ctx.nvid = net, a, T, nvid
+        ctx.feat_needs_grad = feat.requires_grad
+        ctx.dims = (h1, w1)
+        return stacked
+
+    @staticmethod
+    def backward(ctx, g):
+        a, T, nvid = ctx.acts, ctx.T, ctx.nvid
+        g = g.contiguous().float()
+        b = g.shape[0]
+        h1, w1 = ctx.dims
+
+        def like(t):
+            return torch.empty(t.shape, dtype=F32, device=t.device)
+
+        gr = ops.unflatten_f32(g, 512, like(a["r"]), 0)
+        gq = ops.maxpool_f32_bwd(a["q"], gr, like(a["q"]), 2, (2, 2))
+        ga12 = ops.maxpool_f32_bwd(a["a12"], gq, like(a["a12"]), 2, (2, 1))
+        ga8 = like(a["a8"])
+        T.cbr3_bwd(*_VC[3], a["r12"], a["a12"], ga12, ga8)
+        gp4 = torch.empty((b, a["a8"].shape[1], a["a8"].shape[2], 128), dtype=F32, device=g.device)
+        T.cbr3_bwd(*_VC[2], a["r8"], a["a8"], ga8, gp4)
+        ga4 = ops.maxpool_f32_bwd(a["a4"], gp4, like(a["a4"]), 4)
+        gp0 = torch.empty((b, h1, w1, 64), dtype=F32, device=g.device)
+        T.cbr3_bwd(*_VC[1], a["r4"], a["a4"], ga4, gp0)
+        ga0 = ops.maxpool_f32_bwd(a["a0"], gp0, like(a["a0"]), 8)
+        T.cbr3_bwd(*_VC[0], a["r0"], a["a0"], ga0, None)                 # the mosaic needs no gradient
+        gfeat = None
+        if ctx.feat_needs_grad:
+            gfeat = torch.empty((g.shape[0], g.shape[1] - nvid), dtype=F32, device=g.device)
+            ops.copy2d_f32(g[:, nvid:], gfeat)
+        ctx.acts = None
+        return (None, None, gfeat) + tuple(T.G[n] for n in _LIVE)
+
+
 class PolicyNetwork2UNet(nn.Module):
     """Reference: rovr/policy_net_2.py:10-141."""
 
@@ -126,6 +194,8 @@ class PolicyNetwork2UNet(nn.Module):
             nn.Linear(2048, 1024), nn.Linear(1024, 512), nn.Linear(512, 256), nn.Linear(256, 64),
             nn.Linear(64, self.output_size))
         self._packed = PackedWeights()
+        from policy_net_1 import default_trunk_precision
+        self.trunk_precision = default_trunk_precision()
 
     # -- trunk -----------------------------------------------------------------------------------
     def _stacked(self, image, context):
@@ -137,7 +207,9 @@ class PolicyNetwork2UNet(nn.Module):
                              f"{tuple(context.shape)}")
         named = dict(self.named_parameters())
         plist = [named[n] for n in _LIVE]
-        return _VideoConvStacked.apply(self, image.float().contiguous(), feat.float().contiguous(), *plist)
+        fn = _VideoConvStackedF32 if self.trunk_precision == "fp32x" else _VideoConvStacked
+        with torch.cuda.device(image.device):
+            return fn.apply(self, image.float().contiguous(), feat.float().contiguous(), *plist)
 
     def compute_logits(self, x, device=None):
         """x: (b, 2048) -> final_fc(x)  (rovr/policy_net_2.py:71-79)."""

@@ -304,7 +304,61 @@ def gen_resnet():
     print("resnet.npz", len(out), "arrays")
 
 
+def gen_lpips():
+    """LPIPS(net='vgg'): the `lpips` package is not in this image (parity unpinned against it); what IS
+    pinned is the VGG16 trunk — torchvision.models.vgg16().features run as torchvision wrote it, with the
+    oracle's seeded weights loaded by their feature indices — plus the published LPIPS head arithmetic
+    written out literally here (independent of oracle.lpips_vgg, which the CPU test compares with this)."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    import torchvision
+    sd = O.lpips_state_dict(0)
+    vgg = torchvision.models.vgg16(weights=None).features.eval()
+    tv = {}
+    for k, convs in enumerate(O.VGG16_SLICES):
+        for idx, _, _ in convs:
+            tv[f"{idx}.weight"] = sd[f"net.slice{k + 1}.{idx}.weight"]
+            tv[f"{idx}.bias"] = sd[f"net.slice{k + 1}.{idx}.bias"]
+    vgg.load_state_dict(tv, strict=True)
+    taps = [3, 8, 15, 22, 29]                      # relu1_2, relu2_2, relu3_3, relu4_3, relu5_3 (lpips/pretrained_networks.py)
+
+    def feats(x):
+        out = []
+        for i, layer in enumerate(vgg):
+            x = layer(x)
+            if i in taps:
+                out.append(x)
+            if i == taps[-1]:
+                break
+        return out
+
+    def lpips(in0, in1, normalize):
+        if normalize:
+            in0, in1 = 2 * in0 - 1, 2 * in1 - 1
+        shift = torch.Tensor([-.030, -.088, -.188])[None, :, None, None]
+        scale = torch.Tensor([.458, .448, .450])[None, :, None, None]
+        o0, o1 = feats((in0 - shift) / scale), feats((in1 - shift) / scale)
+        val = 0
+        for k in range(5):
+            a = o0[k] / (torch.sqrt(torch.sum(o0[k] ** 2, dim=1, keepdim=True)) + 1e-10)
+            b = o1[k] / (torch.sqrt(torch.sum(o1[k] ** 2, dim=1, keepdim=True)) + 1e-10)
+            val = val + torch.nn.functional.conv2d((a - b) ** 2, sd[f"lin{k}.model.1.weight"]).mean([2, 3], keepdim=True)
+        return val
+
+    out = {"keys": np.array(list(sd.keys()))}
+    for tag, (n, h, w, normalize) in {"a": (2, 32, 32, False), "b": (1, 64, 48, True)}.items():
+        g = torch.Generator().manual_seed(71 + n)
+        in0 = torch.rand((n, 3, h, w), generator=g).requires_grad_(True)
+        in1 = torch.rand((n, 3, h, w), generator=g)
+        val = lpips(in0, in1, normalize)
+        val.mean().backward()
+        out[f"{tag}/val"] = val.detach().numpy()
+        out[f"{tag}/grad_in0"] = in0.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "lpips.npz"), **out)
+    print("lpips.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["localnet", "pn1", "pn2", "common", "action_lstm", "resnet"]
+    which = sys.argv[1:] or ["localnet", "pn1", "pn2", "common", "action_lstm", "resnet", "lpips"]
     for w in which:
         globals()["gen_" + w]()

@@ -79,6 +79,60 @@ def test_gradient_buckets_gloo_world2():
     assert [(r[8], r[9]) for r in res] == [(0, 25), (25, 50)]
 
 
+def _avg_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                    "reinformcement-optimized-video-reconstruction_b200"))
+    from data_parallel import GradientAverager
+    # a module whose first three gradients are views of one flat arena (what the trunk Functions of the
+    # policy networks produce, _blocks.GradArena) and whose last two are separate tensors (the fp32 heads)
+    m = torch.nn.Module()
+    shapes = [(4, 3, 3, 3), (4,), (5, 4), (7, 5), (7,)]
+    for i, sh in enumerate(shapes):
+        m.register_parameter(f"p{i}", torch.nn.Parameter(torch.zeros(sh)))
+    params = list(m.parameters())
+    arena = torch.empty(sum(p.numel() for p in params[:3]))
+    off = 0
+    for i, p in enumerate(params):
+        val = float((rank + 1) * (i + 1))
+        if i < 3:
+            p.grad = arena[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+            p.grad.fill_(val)
+        else:
+            p.grad = torch.full(p.shape, val)
+    frozen = torch.nn.Parameter(torch.zeros(3))
+    m.register_parameter("frozen", frozen)                  # no gradient: must be skipped
+    avg = GradientAverager(m)
+    avg.average()
+    mean = sum(r + 1 for r in range(world)) / world
+    ok = all(torch.allclose(p.grad, torch.full(p.shape, mean * (i + 1))) for i, p in enumerate(params))
+    q.put((rank, ok, avg.collectives, frozen.grad is None))
+    dist.destroy_process_group()
+
+
+def test_gradient_averager_gloo_world2():
+    """Generic gradient averaging (policy networks): one collective per shared gradient arena + one for the
+    loose head gradients."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_avg_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, collectives, frozen_none in res:
+        assert ok and frozen_none
+        assert collectives == 2
+
+
 def test_shard_range_covers_everything():
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),

@@ -51,7 +51,7 @@ def _worker(rank, world, port, q):
     _, loss = net.forward_with_mse(x.to(dev), c.to(dev), t.to(dev))
     loss.backward()
     full = {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None}
-    full_loss = float(loss)
+    full_loss = float(loss.detach())
     ref = {n: g.clone() for n, g in full.items()}
     for g in ref.values():
         dist.broadcast(g, src=0)
@@ -98,8 +98,8 @@ def _worker(rank, world, port, q):
     dist.broadcast(other, src=0)
     out["replicas_equal"] = bool(torch.equal(other, flat))
     q.put(out)
-    dist.barrier()
-    dist.destroy_process_group()
+    from data_parallel import shutdown
+    shutdown(step, step2)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
@@ -112,11 +112,14 @@ def test_two_gpu_gradients_equal_single_gpu():
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=600) for _ in range(world)), key=lambda d: d["rank"])
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
     for r in res:
         print(r)
+    for p in procs:
+        p.join(timeout=120)
+        if p.exitcode is None:
+            p.kill()
+        assert p.exitcode == 0, "a rank did not exit cleanly (process-group teardown hung?)"
+    for r in res:
         assert r["same_truth"], "broadcast_parameters left the replicas different (stale bf16 operand cache?)"
         assert r["eager_launched"] == 2
         assert r["loss_rel"] < 1e-5

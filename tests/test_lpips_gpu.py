@@ -1,0 +1,140 @@
+"""GPU parity of the LPIPS(net='vgg') replacement (lpips_vgg.py) against the oracle
+restatement (oracle.lpips_vgg, pinned to torchvision's VGG16 by tests/golden/lpips.npz): the value
+per image and the gradient w.r.t. the first image within the bf16 tolerance of north_star (2e-2),
+the head kernels alone at fp32 accuracy, and the combined LocalNet + gamma-mixed loss step of
+rovr/train_local_net_unet.py:105-115."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import rovr_oracle as O
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+TOL = 2e-2
+
+
+def _dev():
+    import _native
+    _native.require_device()
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-300)).item()
+
+
+def _module(dev):
+    from lpips_vgg import LPIPS
+    m = LPIPS(net="vgg")
+    sd = O.lpips_state_dict(0)
+    missing = m.load_state_dict(sd, strict=True)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    return m.to(dev), sd
+
+
+@pytest.mark.parametrize("C,hw", [(64, (16, 24)), (128, (8, 8)), (256, (5, 7)), (512, (2, 2))])
+def test_lpips_head_kernel(C, hw):
+    """unit-normalise + weighted squared difference + spatial mean, and its gradient, vs PyTorch on the
+    same bf16-rounded features."""
+    import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(C)
+    N = 3
+    f = torch.relu(torch.randn((2 * N, *hw, C), generator=g)).to(BF).to(dev)
+    f[0, 0, 0] = 0                                                   # an all-zero feature vector: value finite, gradient 0
+    w = (torch.rand(C, generator=g) * 0.1).to(dev)
+    partial, grad = ops.lpips_head(f, w, True)
+    val = ops.lpips_finalize([partial], [hw[0] * hw[1]], N)
+    f0 = f[:N].float().clone().requires_grad_(True)
+    f1 = f[N:].float()
+    n0 = f0 / (torch.sqrt((f0 ** 2).sum(-1, keepdim=True)) + 1e-10)
+    n1 = f1 / (torch.sqrt((f1 ** 2).sum(-1, keepdim=True)) + 1e-10)
+    ref = (((n0 - n1) ** 2) * w).sum(-1).mean((1, 2))
+    assert _rel(val, ref) < 1e-5
+    f0z = f0.detach().clone()
+    f0z[0, 0, 0] = 1e-3                                              # keep autograd away from sqrt'(0) = inf
+    f0z.requires_grad_(True)
+    n0z = f0z / (torch.sqrt((f0z ** 2).sum(-1, keepdim=True)) + 1e-10)
+    (((n0z - n1) ** 2) * w).sum(-1).mean((1, 2)).sum().backward()
+    gref = f0z.grad * (f0.detach() > 0)
+    gref[0, 0, 0] = 0
+    assert torch.count_nonzero(grad[0, 0, 0]) == 0
+    assert _rel(grad.float(), gref) < 6e-3                            # bf16 storage of the gradient
+    p2, g2 = ops.lpips_head(f, w, False)
+    assert g2 is None and torch.equal(p2, partial)
+
+
+@pytest.mark.parametrize("tag,shape,normalize", [("a", (2, 32, 32), False), ("b", (1, 64, 48), True)])
+def test_lpips_matches_golden_and_oracle(golden_dir, tag, shape, normalize):
+    import os
+    dev = _dev()
+    G = np.load(os.path.join(golden_dir, "lpips.npz"))
+    m, sd = _module(dev)
+    n, h, w = shape
+    g = torch.Generator().manual_seed(71 + n)
+    in0 = torch.rand((n, 3, h, w), generator=g)
+    in1 = torch.rand((n, 3, h, w), generator=g)
+    x0 = in0.to(dev).requires_grad_(True)
+    val = m(x0, in1.to(dev), normalize=normalize)
+    assert val.shape == (n, 1, 1, 1)
+    val.mean().backward()
+    print(f"lpips {tag}: value rel {_rel(val, torch.from_numpy(G[tag + '/val'])):.3e} grad rel "
+          f"{_rel(x0.grad, torch.from_numpy(G[tag + '/grad_in0'])):.3e}")
+    assert _rel(val, torch.from_numpy(G[f"{tag}/val"])) < TOL
+    assert _rel(x0.grad, torch.from_numpy(G[f"{tag}/grad_in0"])) < 5 * TOL    # tiny maps: few pixels per tap (see below)
+    with torch.no_grad():
+        v2 = m(in0.to(dev), in1.to(dev), normalize=normalize)
+    assert torch.equal(v2, val.detach())
+    assert float(m(in1.to(dev), in1.to(dev)).abs().max()) == 0.0
+
+
+def test_lpips_full_size_vs_oracle():
+    """256x256 (the training resolution): value and gradient within 2e-2 of the fp32 oracle (evaluated by
+    PyTorch on the GPU in fp32, TF32 off)."""
+    dev = _dev()
+    m, sd = _module(dev)
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+    x, c, t = O.synthetic_localnet_batch(4, 256, 256, seed=9)
+    y_hat = (0.6 * t + 0.4 * torch.rand(t.shape, generator=torch.Generator().manual_seed(1))).to(dev)
+    x0 = y_hat.clone().requires_grad_(True)
+    val = m(x0, t.to(dev))
+    val.mean().backward()
+    xr = y_hat.clone().requires_grad_(True)
+    ref = O.lpips_vgg(sdd, xr, t.to(dev))
+    ref.mean().backward()
+    print(f"lpips 256x256: value rel {_rel(val, ref):.3e}, grad rel {_rel(x0.grad, xr.grad):.3e}")
+    assert _rel(val, ref) < TOL
+    assert _rel(x0.grad, xr.grad) < TOL
+
+
+def test_localnet_gamma_mixed_loss_step():
+    """rovr/train_local_net_unet.py:105-115: total = gamma * mse + (1 - gamma) * lpips(y_hat, target).mean();
+    total.backward() — all 22 LocalNet gradients against the fp32 oracle."""
+    from local_net import LocalNetworkUNetNorm
+    dev = _dev()
+    lp, sdl = _module(dev)
+    sd = O.localnet_state_dict(0)
+    net = LocalNetworkUNetNorm()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev)
+    gamma = 0.4
+    x, c, t = O.synthetic_localnet_batch(4, 128, 128, seed=31)
+    y_hat = net(x.to(dev), c.to(dev))
+    mse = F.mse_loss(y_hat, t.to(dev))
+    lpl = lp(y_hat, t.to(dev)).mean()
+    total = mse * gamma + lpl * (1 - gamma)
+    total.backward()
+    sdd = {k: v.to(dev) for k, v in sdl.items()}
+    leaf = {k: (v.to(dev).clone().requires_grad_(True) if k in O.LOCALNET_LIVE else v.to(dev)) for k, v in sd.items()}
+    yr = O.localnet_forward(leaf, x.to(dev), c.to(dev))
+    tr = F.mse_loss(yr, t.to(dev)) * gamma + O.lpips_vgg(sdd, yr, t.to(dev)).mean() * (1 - gamma)
+    tr.backward()
+    assert abs(float(total) - float(tr)) < TOL * abs(float(tr))
+    named = dict(net.named_parameters())
+    worst = max(_rel(named[k].grad, leaf[k].grad) for k in O.LOCALNET_LIVE)
+    print("gamma-mixed step: worst gradient l2-rel", worst)
+    for k in O.LOCALNET_LIVE:
+        assert _rel(named[k].grad, leaf[k].grad) < TOL, (k, _rel(named[k].grad, leaf[k].grad))

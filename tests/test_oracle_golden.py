@@ -313,3 +313,26 @@ def test_resnet_extractor_matches_reference(golden_dir):
     assert np.allclose(y.numpy(), G["a/y"], rtol=1e-4, atol=1e-5)
     keys = ["resnet." + k for k in seq.state_dict().keys()] + ["linear.weight", "linear.bias"]
     assert keys == list(G["keys"])
+
+
+def test_lpips_oracle_matches_torchvision_golden(golden_dir):
+    """oracle.lpips_vgg vs tests/golden/lpips.npz (torchvision's own VGG16 `features` + the published LPIPS
+    head written out literally by make_golden.py). The `lpips` package itself is absent: parity unpinned
+    against it, pinned against torchvision's VGG16 structure."""
+    G = np.load(os.path.join(golden_dir, "lpips.npz"))
+    sd = O.lpips_state_dict(0)
+    assert list(sd.keys()) == list(G["keys"])
+    for tag, (n, h, w, nz) in {"a": (2, 32, 32, False), "b": (1, 64, 48, True)}.items():
+        g = torch.Generator().manual_seed(71 + n)
+        in0 = torch.rand((n, 3, h, w), generator=g).requires_grad_(True)
+        in1 = torch.rand((n, 3, h, w), generator=g)
+        v = O.lpips_vgg(sd, in0, in1, nz)
+        v.mean().backward()
+        assert v.shape == (n, 1, 1, 1)
+        assert np.allclose(v.detach().numpy(), G[f"{tag}/val"], rtol=1e-5, atol=1e-8)
+        assert np.allclose(in0.grad.numpy(), G[f"{tag}/grad_in0"], rtol=1e-4, atol=1e-8)
+    # identical images have distance 0; the distance is symmetric
+    x = torch.rand((1, 3, 32, 32), generator=torch.Generator().manual_seed(3))
+    y = torch.rand((1, 3, 32, 32), generator=torch.Generator().manual_seed(4))
+    assert float(O.lpips_vgg(sd, x, x)) == 0.0
+    assert abs(float(O.lpips_vgg(sd, x, y)) - float(O.lpips_vgg(sd, y, x))) < 1e-7
