@@ -325,6 +325,15 @@ class LocalNetworkUNetNorm(nn.Module):
         kernel: the `mse_loss_fn(y_hat, target)` of rovr/train_local_net_unet.py:107."""
         return self._run(x, context, target)
 
+    def forward_with_loss(self, x, context, target, gamma, lpips_fn, normalize=False):
+        """The full loss of rovr/train_local_net_unet.py:105-113: returns (y_hat, mse, lpips, total) with
+        total = gamma * mse + (1 - gamma) * lpips_fn(y_hat, target).mean(); `lpips_fn` is a
+        lpips_vgg.LPIPS. `total.backward()` runs the LPIPS dgrad chain into y_hat and then this network's
+        backward with both the perceptual gradient and the fused L2 gradient."""
+        y_hat, mse = self._run(x, context, target)
+        lp = lpips_fn(y_hat, target, normalize=normalize).mean()
+        return y_hat, mse, lp, mse * gamma + lp * (1.0 - gamma)
+
 
 class GraphedTrainingStep:
     """forward + fused L2 loss + backward of a LocalNetworkUNetNorm captured ONCE into a CUDA graph.
@@ -355,9 +364,14 @@ class GraphedTrainingStep:
     after each replay instead (`"after-replay"`).
     """
 
-    def __init__(self, net, x, context, target, repack_weights=True, warmup=2, capture_collectives=True):
+    def __init__(self, net, x, context, target, repack_weights=True, warmup=2, capture_collectives=True,
+                 lpips_fn=None, gamma=1.0, normalize=False):
+        """lpips_fn (a lpips_vgg.LPIPS) adds the perceptual term of rovr/train_local_net_unet.py:109-113 to
+        the captured step: loss = gamma * mse + (1 - gamma) * lpips(y_hat, target).mean(); `gamma` may be
+        changed per step with `set_gamma()` (the reference anneals it, :111)."""
         self.net = net
         self.repack_weights = repack_weights
+        self.lpips_fn = lpips_fn
         dev = x.device
         self.x, self.context, self.target = x.clone(), context.clone(), target.clone()
         named = dict(net.named_parameters())
@@ -368,14 +382,23 @@ class GraphedTrainingStep:
         G.update(Ge)
         self.buckets = (dec_flat, enc_flat)
         self.grad_views = G
-        self._g_loss = torch.ones((), dtype=torch.float32, device=dev)
+        self._g_loss = torch.ones((), dtype=torch.float32, device=dev)        # d total / d mse  (= gamma)
+        self._g_lpips = torch.zeros(x.shape[0], dtype=torch.float32, device=dev)  # d total / d lpips[n] (= (1-gamma)/N)
+        self.lpips = None                                                        # static per-image LPIPS values
+        if lpips_fn is not None:
+            self.set_gamma(gamma)
         hooks = (net._grad_bucket_hook, net._grad_bucket_wait, net._grad_bucket_reduce)
         self._reduce_after = None
         self.allreduce_mode = "none"
 
         def run():
             y, loss, acts = _forward_impl(net, self.x, self.context, self.target, Pd, True)
-            _backward_impl(net, acts, Pd, self.target, None, self._g_loss, buckets=(dec_flat, enc_flat, G))
+            g_out = None
+            if lpips_fn is not None:
+                import lpips_vgg
+                self.lpips, saved = lpips_vgg._forward_impl(lpips_fn, y, self.target, normalize, True)
+                g_out = lpips_vgg._backward_impl(lpips_fn, saved, self._g_lpips)
+            _backward_impl(net, acts, Pd, self.target, g_out, self._g_loss, buckets=(dec_flat, enc_flat, G))
             return y, loss
 
         import _native
@@ -412,6 +435,12 @@ class GraphedTrainingStep:
                 break
         net._grad_bucket_hook, net._grad_bucket_wait = hooks[0], hooks[1]
         self._bind_grads()
+
+    def set_gamma(self, gamma):
+        """Loss weights of the next replays: total = gamma * mse + (1 - gamma) * mean(lpips) (two tiny fills,
+        stream-ordered before the replay)."""
+        self._g_loss.fill_(float(gamma))
+        self._g_lpips.fill_((1.0 - float(gamma)) / self._g_lpips.numel())
 
     def close(self):
         """Destroy the captured graph. With NCCL collectives captured inside it this MUST happen before

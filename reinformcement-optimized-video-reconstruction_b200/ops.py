@@ -926,13 +926,13 @@ def posenc_grad(g, n1, which):
 # ---------------------------------------------------------------------------------------------
 # emulated-fp32 policy trunks (csrc/fp32x.cuh): fp32 NHWC activations, split-bf16 stacked operands
 # ---------------------------------------------------------------------------------------------
-def _actf(t, name="activation"):
-    """Validate an NHWC fp32 view and return (B, H, W, C, ld)."""
+def _actf(t, name="activation", align=4):
+    """Validate an NHWC fp32 view (pixel stride a multiple of `align` floats) and return (B, H, W, C, ld)."""
     if t.dtype != torch.float32 or not t.is_cuda or t.dim() != 4:
         raise ValueError(f"{name}: expected a 4-D CUDA fp32 NHWC tensor, got {t.dtype} {tuple(t.shape)}")
     B, H, W, C = t.shape
     ld = t.stride(2)
-    if t.stride(3) != 1 or t.stride(1) != W * ld or (B > 1 and t.stride(0) != H * W * ld) or ld % 4:
+    if t.stride(3) != 1 or t.stride(1) != W * ld or (B > 1 and t.stride(0) != H * W * ld) or ld % align:
         raise ValueError(f"{name}: not a dense-pixel NHWC view, strides={t.stride()}")
     return B, H, W, C, ld
 
@@ -948,7 +948,7 @@ def split_stack(src, nterms, cb, layout="nhwc", pool=None, out=None, src2=None):
     nterms 6 -> forward operand [h m l h m h], 3 -> gradient operand [h m h]."""
     c_split = 0
     if layout == "nhwc":
-        B, H, W, C, ld = _actf(src, "split source")
+        B, H, W, C, ld = _actf(src, "split source", align=1)     # scalar loads: any pixel stride
         sb, sy, sx, sc = H * W * ld, W * ld, ld, 1
         assert src2 is None
     else:

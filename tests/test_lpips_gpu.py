@@ -138,3 +138,37 @@ def test_localnet_gamma_mixed_loss_step():
     print("gamma-mixed step: worst gradient l2-rel", worst)
     for k in O.LOCALNET_LIVE:
         assert _rel(named[k].grad, leaf[k].grad) < TOL, (k, _rel(named[k].grad, leaf[k].grad))
+
+
+def test_graphed_step_with_lpips_matches_eager():
+    """GraphedTrainingStep(lpips_fn=...): the whole gamma-mixed step (LocalNet fwd, fused L2, VGG16 x 2N,
+    LPIPS heads, VGG dgrad chain, LocalNet bwd) as ONE graph replay equals the eager autograd step bit for
+    bit, and follows set_gamma()."""
+    from local_net import GraphedTrainingStep, LocalNetworkUNetNorm
+    dev = _dev()
+    lp, _ = _module(dev)
+    net = LocalNetworkUNetNorm()
+    net.load_state_dict(O.localnet_state_dict(0), strict=True)
+    net = net.to(dev)
+    x, c, t = [v.to(dev) for v in O.synthetic_localnet_batch(2, 64, 64, seed=41)]
+
+    def eager(gamma):
+        net.zero_grad(set_to_none=True)
+        _, mse, lpl, total = net.forward_with_loss(x, c, t, gamma, lp)
+        total.backward()
+        return mse.detach().clone(), lpl.detach().clone(), {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+
+    m1, l1, g1 = eager(0.4)
+    m2, l2, g2 = eager(0.9)
+    step = GraphedTrainingStep(net, x, c, t, lpips_fn=lp, gamma=0.4)
+    for gamma, (m, l, g) in ((0.4, (m1, l1, g1)), (0.9, (m2, l2, g2)), (0.4, (m1, l1, g1))):
+        step.set_gamma(gamma)
+        net.zero_grad()
+        mse = step()
+        torch.cuda.synchronize()
+        assert torch.equal(mse, m)
+        assert abs(float(step.lpips.mean()) - float(l)) < 1e-6 * abs(float(l))
+        for n, p in net.named_parameters():
+            if n in g:
+                assert torch.equal(p.grad, g[n]), (gamma, n)
+    assert not torch.equal(g1["conv7.weight"], g2["conv7.weight"])
