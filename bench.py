@@ -414,12 +414,304 @@ def run_cuda(args, rank, local_rank, world):
         shutdown(graphed)
 
 
+
+# ------------------------------------------------------------------------------------------------
+# other workloads of the hot path (BASELINE.json configs[2..4] shapes; --workload)
+# ------------------------------------------------------------------------------------------------
+def _vgg_lpips_gflop_per_frame():
+    """LPIPS(net='vgg') at 256x256: VGG16 `features` forward on y_hat AND target (2 x 20.05 GMAC) plus the
+    data-gradient chain back to y_hat (20.05 GMAC; VGG is frozen: no weight gradients)."""
+    convs = [(3, 64, 1), (64, 64, 1), (64, 128, 2), (128, 128, 2), (128, 256, 4), (256, 256, 4), (256, 256, 4),
+             (256, 512, 8), (512, 512, 8), (512, 512, 8), (512, 512, 16), (512, 512, 16), (512, 512, 16)]
+    fwd = sum((H // d) * (W // d) * 9 * ci * co for ci, co, d in convs)
+    return 2.0 * 3 * fwd / 1e9
+
+
+WORKLOADS = {
+    # name: (metric, unit, description)
+    "localnet_lpips": ("masked frames/sec (LocalNet fwd + gamma*L2 + (1-gamma)*LPIPS-VGG + bwd)", "frames/s"),
+    "pn2_il": ("policy samples/sec (PolicyNetwork2UNet imitation-learning step fwd+bwd)", "samples/s"),
+    "pn1": ("policy samples/sec (PolicyNetwork1UNet logprob fwd+bwd)", "samples/s"),
+    "resnet": ("frames/sec (ResnetFeatureExtractor forward + linear fwd/bwd)", "frames/s"),
+    "encoder": ("sequences/sec (EncoderBlock E=3072 S=256 fwd+bwd)", "sequences/s"),
+}
+
+
+def build_workload(name, dev, rank, world, args):
+    """Returns dict(step=callable (device-resident inputs), e2e=callable(n) -> None (host inputs, n steps),
+    units, gflop_per_unit, h2d, d2h, config, close=callable, launches=int|None)."""
+    import _native
+    from feeder import DeviceFeeder, ScalarReadback
+    from graphs import GraphedFunction
+    g = torch.Generator().manual_seed(4321 + rank)
+    averager = None
+
+    def dp(module):
+        nonlocal averager
+        if world > 1:
+            from data_parallel import GradientAverager, broadcast_parameters
+            broadcast_parameters(module)
+            averager = GradientAverager(module)
+
+    def reduce_():
+        if averager is not None:
+            averager.average()
+
+    if name == "localnet_lpips":
+        from local_net import GraphedTrainingStep, LocalNetworkUNetNorm
+        from lpips_vgg import LPIPS
+        from data_parallel import GradientBuckets, broadcast_parameters
+        torch.manual_seed(0)
+        net = LocalNetworkUNetNorm().to(dev)
+        lp = LPIPS(net="vgg").to(dev)
+        if world > 1:
+            broadcast_parameters(net)
+            broadcast_parameters(lp)
+            GradientBuckets(net)
+        from synthetic import masked_frame_batch
+        host = [t.pin_memory() for t in masked_frame_batch(B_PER_GPU, H, W, seed=1234 + rank)]
+        x, c, t = [v.to(dev) for v in host]
+        gamma = 0.1 + 0.9 * (0.9993 ** 1000)           # rovr/train_local_net_unet.py:111 at iteration 1000
+        step = GraphedTrainingStep(net, x, c, t, lpips_fn=lp, gamma=gamma)
+
+        def e2e(n):
+            rb = ScalarReadback(dev, lag=1)
+            for xd, cd, td in DeviceFeeder((tuple(host) for _ in range(n)), dev):
+                rb.exchange(step(xd, cd, td))
+            rb.drain()
+        return dict(step=lambda: step(), e2e=e2e, units=B_PER_GPU, gflop_per_unit=119.81 + _vgg_lpips_gflop_per_frame(),
+                    h2d=sum(v.numel() for v in host) * 4, d2h=4, close=step.close, launches=step.launches_per_step,
+                    config={"workload": "LocalNet U-Net training step with the reference's full loss (rovr/train_local_net_unet.py:"
+                                        "105-115): B=24 frames/GPU, 256x256, gamma*MSE + (1-gamma)*LPIPS-VGG (random-init VGG16, "
+                                        "frozen), forward + backward, one CUDA graph per step",
+                            "gamma": gamma, "allreduce": step.allreduce_mode})
+
+    if name == "pn2_il":
+        from policy_net_2 import PolicyNetwork2UNet
+        torch.manual_seed(0)
+        net = PolicyNetwork2UNet().to(dev).train()
+        dp(net)
+        b = 20                                           # one clip of 20 frames = the reference's batch (imitation_learning.py:83-87)
+        enc_h = torch.rand((b, 1, 160, 160), generator=g).pin_memory()
+        flat_h = torch.randn((b, 1, 1024), generator=g).pin_memory()
+        pos = torch.randint(0, 20, (b, 16, 2), generator=g)
+        neg = torch.randint(0, 20, (b, 3, 2), generator=g)
+        # multi-hot BCE targets of imitation_learning.py:88-94, built once (they do not depend on the network)
+        pos_t = torch.stack([torch.nn.functional.one_hot(pos[:, i], 20).sum(1) for i in range(pos.shape[1])]).float().to(dev)
+        neg_t = torch.stack([torch.nn.functional.one_hot(neg[:, i], 20).sum(1) for i in range(neg.shape[1])]).float().to(dev)
+        target = torch.arange(20).unsqueeze(1).unsqueeze(1).to(dev)
+        bce = torch.nn.functional.binary_cross_entropy_with_logits
+
+        def fn(enc, flat):
+            out = net(enc, flat, target, extra=True)
+            loss = sum(bce(out, pos_t[i]) * 1.5 for i in range(pos_t.shape[0])) - sum(bce(out, neg_t[i]) for i in range(neg_t.shape[0]))
+            loss.backward()
+            return loss.detach()
+        gstep = GraphedFunction(fn, (enc_h.to(dev), flat_h.to(dev)), modules=[net])
+        clips = max(1, args.clips)
+
+        def step():
+            for _ in range(clips):                       # clips are independent optimizer steps in the reference
+                gstep(None, None)
+                reduce_()
+
+        def e2e(n):
+            rb = ScalarReadback(dev, lag=1)
+            for encd, flatd in DeviceFeeder(((enc_h, flat_h) for _ in range(n * clips)), dev):
+                loss = gstep(encd, flatd)
+                reduce_()
+                rb.exchange(loss)
+            rb.drain()
+        return dict(step=step, e2e=e2e, units=b * clips, gflop_per_unit=0.503, h2d=(enc_h.numel() + flat_h.numel()) * 4 * clips,
+                    d2h=4 * clips, close=lambda: None, launches=gstep.launches * clips,
+                    config={"workload": f"imitation-learning step of rovr/imitation_learning.py:83-100 on PolicyNetwork2UNet: "
+                                        f"{clips} clip(s) per GPU per step, each clip = 20 samples of [1,160,160] + [1024] "
+                                        "(one forward + BCE loss + backward per clip, per-clip BatchNorm statistics as in the "
+                                        "reference; gradients averaged over ranks per clip), emulated-fp32 trunk, one CUDA graph "
+                                        "replay per clip", "clips_per_gpu": clips, "precision": net.trunk_precision})
+
+    if name == "pn1":
+        from policy_net_1 import PolicyNetwork1UNet
+        torch.manual_seed(0)
+        net = PolicyNetwork1UNet().to(dev).train()
+        dp(net)
+        b = 25
+        img_h = torch.rand((b, 3, 80, 80), generator=g).pin_memory()
+        ctx_h = torch.rand((b, 3, 80, 80), generator=g).pin_memory()
+        act = torch.randint(0, 25, (b,), generator=g).to(dev)
+
+        def fn(img, ctx):
+            lp = net.logprob(img, ctx, act)
+            lp.sum().backward()
+            return lp.detach().sum()
+        gstep = GraphedFunction(fn, (img_h.to(dev), ctx_h.to(dev)), modules=[net])
+
+        def step():
+            gstep(None, None)
+            reduce_()
+
+        def e2e(n):
+            rb = ScalarReadback(dev, lag=1)
+            for i_d, c_d in DeviceFeeder(((img_h, ctx_h) for _ in range(n)), dev):
+                v = gstep(i_d, c_d)
+                reduce_()
+                rb.exchange(v)
+            rb.drain()
+        return dict(step=step, e2e=e2e, units=b, gflop_per_unit=2.960, h2d=(img_h.numel() + ctx_h.numel()) * 4, d2h=4,
+                    close=lambda: None, launches=gstep.launches,
+                    config={"workload": "PolicyNetwork1UNet.logprob forward + backward, b=25 mosaics of 80x80 (rovr/rovr.py:312 "
+                                        "shape), emulated-fp32 trunk, one CUDA graph replay per step",
+                            "precision": net.trunk_precision})
+
+    if name == "resnet":
+        import warnings
+        warnings.filterwarnings("ignore")
+        from resnet_extractor import ResnetFeatureExtractor
+        torch.manual_seed(0)
+        net = ResnetFeatureExtractor(pretrained=False)
+        net.resnet.eval()
+        for p_ in net.resnet.parameters():
+            p_.requires_grad = False
+        net = net.to(dev)
+        dp(net)
+        fr_h = torch.rand((1, 25, 3, 224, 224), generator=g).pin_memory()
+
+        def fn(fr):
+            out = net(fr)
+            loss = (out ** 2).sum()
+            loss.backward()
+            return loss.detach()
+        gstep = GraphedFunction(fn, (fr_h.to(dev),), modules=[net])
+
+        def step():
+            gstep(None)
+            reduce_()
+
+        def e2e(n):
+            rb = ScalarReadback(dev, lag=1)
+            for (fd,) in DeviceFeeder(((fr_h,) for _ in range(n)), dev):
+                v = gstep(fd)
+                reduce_()
+                rb.exchange(v)
+            rb.drain()
+        return dict(step=step, e2e=e2e, units=25, gflop_per_unit=8.174, h2d=fr_h.numel() * 4, d2h=4, close=lambda: None,
+                    launches=gstep.launches,
+                    config={"workload": "ResnetFeatureExtractor forward of one clip (25 frames, 224x224; frozen eval-mode ResNet-50 "
+                                        "trunk as with pretrained=True) + Linear(2048,768) forward/backward + mosaic paste"})
+
+    if name == "encoder":
+        from common_layers import EncoderBlock
+        torch.manual_seed(0)
+        E, S, Bq = 3072, 256, 24
+        net = EncoderBlock(E, 8, 0.0).to(dev)
+        dp(net)
+        x_h = torch.randn((Bq, S, E), generator=g).pin_memory()
+
+        def fn(xx):
+            out = net(xx)
+            loss = (out ** 2).mean()
+            loss.backward()
+            return loss.detach()
+        gstep = GraphedFunction(fn, (x_h.to(dev).requires_grad_(True),), modules=[net])
+
+        def step():
+            gstep(None)
+            reduce_()
+
+        def e2e(n):
+            rb = ScalarReadback(dev, lag=1)
+            for (xd,) in DeviceFeeder(((x_h,) for _ in range(n)), dev):
+                v = gstep(xd)
+                reduce_()
+                rb.exchange(v)
+            rb.drain()
+        return dict(step=step, e2e=e2e, units=Bq, gflop_per_unit=3 * (20.13 + 2.42), h2d=x_h.numel() * 4, d2h=4,
+                    close=lambda: None, launches=gstep.launches,
+                    config={"workload": "EncoderBlock(hidden 3072, 8 heads) forward + backward on B=24 sequences of 256 tokens "
+                                        "(rovr/common_layers.py:94-104 at the token shape of :8-9)"})
+    raise ValueError(name)
+
+
+def run_workload(args, rank, local_rank, world):
+    """The generic arm: same timing contract as run_cuda (W >= 3 warm-up steps, K timed steps between barriers +
+    synchronize, CUDA events, max over ranks), model-level roofline (algorithmic FLOPs of SURVEY §8d / step time)."""
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import _native
+    _native.require_device()
+    wl = build_workload(args.workload, dev, rank, world, args)
+    metric, unit = WORKLOADS[args.workload]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tms = torch.tensor([ms], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        wl["step"]()
+    ms_total = timed(lambda: [wl["step"]() for _ in range(args.steps)])
+    clocks = sampler.stop() if rank == 0 else {}
+    wl["e2e"](2)
+    ms_e2e = timed(lambda: wl["e2e"](args.steps))
+    units = wl["units"] * world * args.steps
+    value = units / (ms_total * 1e-3)
+    if rank == 0:
+        peaks = measured_peaks()
+        tflops = wl["gflop_per_unit"] * value / world / 1e3
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": dict(wl["config"], parallelism=f"dp{world}",
+                               l2="activations of a step exceed the 126 MB L2 only for the LocalNet / ResNet workloads; the "
+                                  "policy workloads are launch-bound (working set < L2): no flush applies"),
+                "e2e": {"value": units / (ms_e2e * 1e-3), "unit": unit, "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": wl["h2d"], "d2h_bytes_per_step": wl["d2h"],
+                        "api": "pinned host inputs -> DeviceFeeder -> graph replay of the module's forward + backward -> "
+                               "ScalarReadback of the loss, every step"},
+                "gpu_launches": int((wl["launches"] or 0) * args.steps), "gpu_launches_per_step": wl["launches"],
+                "clocks": clocks,
+                "roofline": {"kernel": "whole step (model-level): algorithmic GEMM FLOPs of SURVEY §8d / step time",
+                             "bound": "tensor", "achieved": tflops, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
+                             "frac": tflops / peaks["tensor_tflops"], "traffic": None, "peak_source": peaks["source"],
+                             "gflop_per_unit": wl["gflop_per_unit"]},
+                "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    wl["close"]()
+    if world > 1:
+        from data_parallel import shutdown
+        shutdown()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="localnet", choices=["localnet"] + sorted(WORKLOADS),
+                    help="localnet (default) = BASELINE.json configs[1], the headline; the others are the remaining "
+                         "hot-path rows (SURVEY §8d configs 2-5)")
+    ap.add_argument("--clips", type=int, default=1, help="pn2_il: clips per GPU per step (sweep 1/8/64/512)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph replay")
     ap.add_argument("--profile-run", action="store_true",
                     help="for runs under ncu: skip the e2e and cpu_baseline legs (their numbers are null)")
@@ -434,8 +726,12 @@ def main():
         # launched without torchrun: re-exec under torch.distributed.run on this node
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__),
-               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
+               "--workload", args.workload, "--clips", str(args.clips)]
         sys.exit(subprocess.call(cmd))
+    if args.workload != "localnet":
+        run_workload(args, rank, local_rank, world)
+        return
     run_cuda(args, rank, local_rank, world)
 
 

@@ -47,7 +47,7 @@ def _forward_impl(mod, in0, in1, normalize, want_grad):
     inputs, feats = [], []
     for k, convs in enumerate(_SLICES):
         for j, (idx, cin, cout) in enumerate(convs):
-            conv = getattr(mod.net, f"slice{k + 1}")[str(idx)]
+            conv = getattr(getattr(mod.net, f"slice{k + 1}"), str(idx))
             wk = pk.get((k, idx, "f"), conv.weight, lambda t: ops.repack_conv3x3(t, False))
             B2, h, w, _ = x.shape
             y = torch.empty((B2, h, w, cout), dtype=BF, device=dev)
@@ -90,7 +90,7 @@ def _backward_impl(mod, saved, gval):
         for j in range(len(convs) - 1, -1, -1):
             idx, cin, cout = convs[j]
             ci -= 1
-            conv = getattr(mod.net, f"slice{k + 1}")[str(idx)]
+            conv = getattr(getattr(mod.net, f"slice{k + 1}"), str(idx))
             wd = pk.get((k, idx, "d"), conv.weight, lambda t: ops.repack_conv3x3(t, True))
             xin = inputs[ci][:N]
             dx = torch.empty(xin.shape, dtype=BF, device=dev)
