@@ -47,6 +47,24 @@ __global__ void pack_nchw_to_nhwc_kernel(PackSrc src, __nv_bfloat16* __restrict_
   }
 }
 
+// torchvision ToTensor on the device: uint8 -> fp32 * scale (1/255), 16 values per thread. Video frames are
+// decoded to uint8 (rovr/video_ds.py:107-114: cv2.imread / resize, then the ToTensor transform on the host);
+// shipping the uint8 frames and converting here cuts the host -> device bytes of a step 4x.
+__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long long n, float scale) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 16;
+  if (i + 16 <= n) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + i));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float4* o = reinterpret_cast<float4*>(dst + i);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      o[j] = make_float4((w[j] & 0xffu) * scale, ((w[j] >> 8) & 0xffu) * scale, ((w[j] >> 16) & 0xffu) * scale,
+                         (w[j] >> 24) * scale);
+  } else {
+    for (long long k = i; k < n; ++k) dst[k] = src[k] * scale;
+  }
+}
+
 // NHWC bf16 (ld) -> NCHW fp32, used to hand results back at the module boundary.
 __global__ void unpack_nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int ld,
                                            float* __restrict__ dst, int B, int HW, int C) {

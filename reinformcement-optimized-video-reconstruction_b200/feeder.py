@@ -13,11 +13,16 @@ import torch
 
 
 class DeviceFeeder:
-    def __init__(self, batches, device, depth=2):
-        """batches: iterable of tuples of equally-shaped host tensors (pinned memory recommended)."""
+    def __init__(self, batches, device, depth=2, to_float=True):
+        """batches: iterable of tuples of equally-shaped host tensors (pinned memory recommended).
+        uint8 tensors (frames as decoded by cv2, rovr/video_ds.py:107-114) are shipped as uint8 — a quarter
+        of the fp32 bytes — and converted to fp32 / 255 on the device (torchvision's ToTensor) by a kernel
+        behind the copy on the feeder's stream, unless to_float=False."""
         self.it = iter(batches)
         self.device = device
         self.depth = depth
+        self.to_float = to_float
+        self.staging = [None] * depth     # uint8 landing buffers of the slots that convert
         self.stream = torch.cuda.Stream(device=device)
         self.slots = [None] * depth       # static device buffers
         self.count = 0
@@ -32,14 +37,23 @@ class DeviceFeeder:
             return
         k = self.count % self.depth
         self.count += 1
+        conv = [self.to_float and t.dtype == torch.uint8 for t in host]
         if self.slots[k] is None:
-            self.slots[k] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host)
+            self.slots[k] = tuple(torch.empty(t.shape, dtype=torch.float32 if c else t.dtype, device=self.device)
+                                  for t, c in zip(host, conv))
+            self.staging[k] = tuple(torch.empty(t.shape, dtype=torch.uint8, device=self.device) if c else None
+                                    for t, c in zip(host, conv))
         # slot k was last read by the step issued `depth` batches ago, whose kernels are already
         # enqueued on the consumer's stream: order the overwrite after them
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
-            for d, h in zip(self.slots[k], host):
-                d.copy_(h, non_blocking=True)
+            for d, st, h in zip(self.slots[k], self.staging[k], host):
+                if st is None:
+                    d.copy_(h, non_blocking=True)
+                else:
+                    import ops
+                    st.copy_(h, non_blocking=True)
+                    ops.u8_to_f32(st, d)
             ev = torch.cuda.Event()
             ev.record(self.stream)
         self._next = (self.slots[k], ev)
