@@ -418,6 +418,14 @@ int rovr_lpips_finalize(const float* const* partials, const int* nblocks, const 
 int rovr_lpips_unpack_grad(const void* gx16, const float* gval, float* gout, int N, int H, int W,
                            const float* shift3, const float* scale3, int normalize, void* stream);
 
+/* ---- dropout (rovr/common_layers.py:58,70: nn.MultiheadAttention(dropout=p) on the attention probabilities;
+ * :87,91: nn.Dropout after the GELU). out = x * keep / (1 - p); the keep mask is a pure function of
+ * state = {seed, counter} (device int64 [2]), the call site and the element index, so backward recomputes it
+ * instead of storing it. rovr_dropout_advance increments the counter (stream-ordered, graph-capturable). */
+int rovr_dropout(const void* x, void* out, long long n, int is_f32, float p, const long long* state, int site,
+                 void* stream);
+int rovr_dropout_advance(long long* state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

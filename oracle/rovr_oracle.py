@@ -375,9 +375,11 @@ def layer_norm(sd, name, t):
     return F.layer_norm(t, (t.shape[-1],), sd[name + ".weight"], sd[name + ".bias"])
 
 
-def mha(sd, name, q, kv, num_heads):
-    """nn.MultiheadAttention(batch_first=True), eval-mode (dropout inactive): packed in-proj
-    [3E, E], per-head softmax(QK^T / sqrt(d)) V, out-proj. Returns the attention output only."""
+def mha(sd, name, q, kv, num_heads, drop_mask=None):
+    """nn.MultiheadAttention(batch_first=True): packed in-proj [3E, E], per-head
+    softmax(QK^T / sqrt(d)) V, out-proj. Returns the attention output only. drop_mask (optional,
+    [B, heads, S, T], entries 0 or 1 / (1 - p)) multiplies the attention probabilities — the training-mode
+    dropout of F.multi_head_attention_forward with the mask made explicit."""
     E = q.shape[-1]
     w, b = sd[name + ".in_proj_weight"], sd[name + ".in_proj_bias"]
     Q = F.linear(q, w[:E], b[:E])
@@ -390,14 +392,16 @@ def mha(sd, name, q, kv, num_heads):
     K = K.view(B, T, num_heads, d).transpose(1, 2)
     V = V.view(B, T, num_heads, d).transpose(1, 2)
     att = torch.softmax(Q @ K.transpose(-1, -2) / math.sqrt(d), dim=-1)
+    if drop_mask is not None:
+        att = att * drop_mask
     o = (att @ V).transpose(1, 2).reshape(B, S, E)
     return F.linear(o, sd[name + ".out_proj.weight"], sd[name + ".out_proj.bias"])
 
 
-def self_attention_block(sd, prefix, x, num_heads):
+def self_attention_block(sd, prefix, x, num_heads, drop_mask=None):
     """rovr/common_layers.py:54-64: x = LN(x); x = x + MHA(x, x, x) (residual on the normalised x)."""
     x = layer_norm(sd, prefix + "layer_norm", x)
-    return x + mha(sd, prefix + "attention", x, x, num_heads)
+    return x + mha(sd, prefix + "attention", x, x, num_heads, drop_mask)
 
 
 def cross_attention_block(sd, prefix, x, enc, num_heads):
@@ -407,10 +411,13 @@ def cross_attention_block(sd, prefix, x, enc, num_heads):
     return x + mha(sd, prefix + "attention", x, enc, num_heads)
 
 
-def feed_forward_block(sd, prefix, x):
-    """rovr/common_layers.py:80-92: LN -> fc1 (E -> E/4) -> exact GELU -> (dropout) -> fc2."""
+def feed_forward_block(sd, prefix, x, drop_mask=None):
+    """rovr/common_layers.py:80-92: LN -> fc1 (E -> E/4) -> exact GELU -> dropout -> fc2. drop_mask
+    (optional, shape of the hidden activation, entries 0 or 1 / (1 - p)) is the nn.Dropout mask."""
     x = layer_norm(sd, prefix + "layer_norm", x)
     h = F.gelu(F.linear(x, sd[prefix + "fc1.weight"], sd[prefix + "fc1.bias"]))
+    if drop_mask is not None:
+        h = h * drop_mask
     return F.linear(h, sd[prefix + "fc2.weight"], sd[prefix + "fc2.bias"])
 
 

@@ -121,6 +121,8 @@ SIGNATURES = {
     "rovr_maxpool_f32_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "rovr_flatten_f32": (_i, [_p, _i, _p, _ll, _i, _i, _i, _p]),
     "rovr_unflatten_f32": (_i, [_p, _ll, _p, _i, _i, _i, _i, _i, _p]),
+    "rovr_dropout": (_i, [_p, _p, _ll, _i, _f, _p, _i, _p]),
+    "rovr_dropout_advance": (_i, [_p, _p]),
     "rovr_lpips_pack": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _i, _p]),
     "rovr_lpips_head_blocks": (_i, [_i, _ll]),
     "rovr_lpips_head": (_i, [_p, _i, _ll, _i, _p, _p, _p, _i, _p]),

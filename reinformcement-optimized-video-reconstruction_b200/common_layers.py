@@ -14,8 +14,13 @@ Each block is one torch.autograd.Function over the B200 kernels:
 and the backward pass is scheduled by hand. The residual of the attention blocks is taken on the
 NORMALISED input, as the reference does (x = LN(x); x = x + MHA(x), :62-63).
 
-Dropout: the reference passes `dropout` to nn.MultiheadAttention / nn.Dropout. Only p == 0 or
-eval mode is implemented (no dropout mask is ever drawn on this path); training with p > 0 raises.
+Dropout (training mode, p > 0): nn.MultiheadAttention drops attention probabilities (:58,70) and
+FeedForwardBlock drops the GELU output (:87,91). Masks come from a counter-based hash of
+(seed, step counter, call site, element index) kept in a device int64[2] per block: nothing is
+stored — backward recomputes the mask — and a CUDA-graph replay draws a fresh mask because the
+counter increment is captured with the step. The seed is drawn from torch's CPU generator at first
+use (torch.manual_seed makes runs reproducible); the masks are NOT torch's own Philox stream, so
+parity tests feed the module's mask (`ops.dropout` on ones) to the oracle.
 """
 import math
 
@@ -44,8 +49,9 @@ def _heads_view(buf, b, n_tok, heads, d, col0):
     return buf.as_strided((b, heads, n_tok, d), (n_tok * W, d, W, 1), buf.storage_offset() + col0)
 
 
-def _attention_core_fwd(q_buf, q_col, kv_buf, k_col, v_col, b, S, T, heads, d):
-    """softmax(Q K^T / sqrt(d)) V per (batch, head). Returns (O [b*S, E] bf16, P [b, h, S, t_pad] bf16)."""
+def _attention_core_fwd(q_buf, q_col, kv_buf, k_col, v_col, b, S, T, heads, d, drop=None):
+    """softmax(Q K^T / sqrt(d)) V per (batch, head). Returns (O [b*S, E] bf16, P [b, h, S, t_pad] bf16).
+    drop = (p, state snapshot, site): attention-probability dropout of nn.MultiheadAttention."""
     dev = q_buf.device
     E = heads * d
     t_pad = ops.pad16(T)
@@ -57,11 +63,13 @@ def _attention_core_fwd(q_buf, q_col, kv_buf, k_col, v_col, b, S, T, heads, d):
     P = ops.softmax_fwd(scores, T, 1.0 / math.sqrt(d))
     Vt = ops.transpose_heads(V, t_pad)                               # [b, h, d, t_pad]
     O = torch.empty((b * S, E), dtype=BF, device=dev)
-    ops.gemm_batched(P, Vt, _heads_view(O, b, S, heads, d, 0))
+    Pd = P if drop is None else ops.dropout(P, *drop)
+    ops.gemm_batched(Pd, Vt, _heads_view(O, b, S, heads, d, 0))
     return O, P
 
 
-def _attention_core_bwd(dO, P, q_buf, q_col, kv_buf, k_col, v_col, dq_buf, dk_buf_view, dv_buf_view, b, S, T, heads, d):
+def _attention_core_bwd(dO, P, q_buf, q_col, kv_buf, k_col, v_col, dq_buf, dk_buf_view, dv_buf_view, b, S, T, heads, d,
+                        drop=None):
     """Gradients of the core: writes dQ / dK / dV (views [b, h, tokens, d] of the projection-gradient buffers)."""
     dev = dO.device
     t_pad, s_pad = ops.pad16(T), ops.pad16(S)
@@ -70,12 +78,15 @@ def _attention_core_bwd(dO, P, q_buf, q_col, kv_buf, k_col, v_col, dq_buf, dk_bu
     V = _heads_view(kv_buf, b, T, heads, d, v_col)
     dOh = _heads_view(dO, b, S, heads, d, 0)
     # dV = P^T dO
-    Pt = ops.transpose_heads(P[..., :T] if t_pad != T else P, s_pad)       # [b, h, T, s_pad]
+    Pd = P if drop is None else ops.dropout(P, *drop)                      # the mask is recomputed, not stored
+    Pt = ops.transpose_heads(Pd[..., :T] if t_pad != T else Pd, s_pad)     # [b, h, T, s_pad]
     dOt = ops.transpose_heads(dOh, s_pad)                                  # [b, h, d, s_pad]
     ops.gemm_batched(Pt, dOt, dv_buf_view)
     # dP = dO V^T ; dS = softmax'(dP)
     dP = torch.empty((b, heads, S, t_pad), dtype=torch.float32, device=dev)
     ops.gemm_batched(dOh, V, dP)
+    if drop is not None:
+        ops.dropout(dP, *drop, out=dP)                                     # d/dP of P * keep / (1 - p)
     dS = ops.softmax_bwd(dP, P, T, 1.0 / math.sqrt(d))
     # dQ = dS K ; dK = dS^T Q
     Kt = ops.transpose_heads(K, t_pad)                                     # [b, h, d, t_pad]
@@ -143,11 +154,13 @@ class _AttentionFn(torch.autograd.Function):
             e2 = emean = erstd = None
             q_buf = kv_buf = ops.gemm_bf16(x2, win, b_in)
             q_col, k_col, v_col = 0, E, 2 * E
-        O, P = _attention_core_fwd(q_buf, q_col, kv_buf, k_col, v_col, b, S, T, heads, d)
+        drop = _draw_dropout(blk, blk.attention.dropout, 0)
+        O, P = _attention_core_fwd(q_buf, q_col, kv_buf, k_col, v_col, b, S, T, heads, d, drop)
         y = ops.gemm_bf16(O, pk.fwd("out", w_out), b_out, out_dtype=torch.float32)
         ops.copy2d_f32(xn32.view(b * S, E), y, accumulate=True)            # residual on the normalised x
         ctx.blk, ctx.cross, ctx.dims = blk, cross, (b, S, T, E, heads, d)
         ctx.cols = (q_col, k_col, v_col)
+        ctx.drop = drop
         ctx.save_for_backward(x, enc, ln_w, lne_w, w_in, w_out, mean, rstd, emean, erstd, x2, e2, q_buf, kv_buf, O, P)
         return y.view(b, S, E)
 
@@ -174,7 +187,7 @@ class _AttentionFn(torch.autograd.Function):
             dq_v = _heads_view(dq_buf, b, S, heads, d, 0)
             dk_v = _heads_view(dq_buf, b, S, heads, d, E)
             dv_v = _heads_view(dq_buf, b, S, heads, d, 2 * E)
-        _attention_core_bwd(dO, P, q_buf, q_col, kv_buf, k_col, v_col, dq_v, dk_v, dv_v, b, S, T, heads, d)
+        _attention_core_bwd(dO, P, q_buf, q_col, kv_buf, k_col, v_col, dq_v, dk_v, dv_v, b, S, T, heads, d, ctx.drop)
         gw_in = torch.empty_like(w_in)
         gb_in = torch.empty(3 * E, dtype=torch.float32, device=dev)
         genc = glne_w = glne_b = None
@@ -211,8 +224,11 @@ class _FeedForwardFn(torch.autograd.Function):
         x2 = xn16.view(-1, E)
         h = ops.gemm_bf16(x2, pk.fwd("fc1", w1), b1)
         a = ops.gelu_fwd(h)
+        drop = _draw_dropout(blk, blk.dropout.p, 1)
+        if drop is not None:
+            a = ops.dropout(a, *drop)                                      # nn.Dropout after the GELU (:91)
         y = ops.gemm_bf16(a, pk.fwd("fc2", w2), b2, out_dtype=torch.float32)
-        ctx.blk = blk
+        ctx.blk, ctx.drop = blk, drop
         ctx.save_for_backward(x, ln_w, w1, w2, mean, rstd, x2, h, a)
         return y.view(shape)
 
@@ -224,6 +240,8 @@ class _FeedForwardFn(torch.autograd.Function):
         g16 = ops.cast_bf16(g.contiguous().float().view(-1, E))
         gw2, gb2 = _linear_grads(g16, a, w2)
         da = ops.gemm_bf16(g16, pk.bwd("fc2", w2))
+        if ctx.drop is not None:
+            ops.dropout(da, *ctx.drop, out=da)
         dh = ops.gelu_bwd(da, h)
         gw1, gb1 = _linear_grads(dh, x2, w1)
         dxn = ops.gemm_bf16(dh, pk.bwd("fc1", w1), out_dtype=torch.float32)
@@ -263,9 +281,19 @@ class _PosEncFn(torch.autograd.Function):
         return g, None, gw1.view(-1, 1), gb1, gw2, gb2
 
 
-def _dropout_guard(module, p):
-    if module.training and p > 0:
-        raise NotImplementedError("dropout > 0 in training mode is not implemented on the B200 attention path")
+def _draw_dropout(blk, p, site):
+    """None when dropout is inactive (eval mode or p == 0); else (p, snapshot of the block's {seed, counter}
+    state, site) — and the live counter moves on, so the next forward draws another mask."""
+    if not blk.training or p <= 0:
+        return None
+    st = getattr(blk, "_dropout_state", None)
+    if st is None or st.device != next(blk.parameters()).device:
+        seed = int(torch.empty((), dtype=torch.int64).random_())          # torch's CPU generator: torch.manual_seed applies
+        st = torch.tensor([seed, 0], dtype=torch.int64, device=next(blk.parameters()).device)
+        blk._dropout_state = st
+    snap = st.clone()
+    ops.dropout_advance(st)
+    return (float(p), snap, site)
 
 
 class ImagePositionalEncoding(nn.Module):
@@ -317,7 +345,6 @@ class SelfAttentionBlock(nn.Module):
 
     def forward(self, x):
         _need_cuda(x, "SelfAttentionBlock")
-        _dropout_guard(self, self.attention.dropout)
         a = self.attention
         return _AttentionFn.apply(self, x.float(), None, self.layer_norm.weight, self.layer_norm.bias, None, None,
                                   a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias)
@@ -334,7 +361,6 @@ class CrossAttentionBlock(nn.Module):
 
     def forward(self, x, encoder_output):
         _need_cuda(x, "CrossAttentionBlock")
-        _dropout_guard(self, self.attention.dropout)
         a = self.attention
         return _AttentionFn.apply(self, x.float(), encoder_output.float(), self.layer_norm.weight,
                                   self.layer_norm.bias, self.layer_norm_encoder_output.weight,
@@ -355,7 +381,6 @@ class FeedForwardBlock(nn.Module):
 
     def forward(self, x):
         _need_cuda(x, "FeedForwardBlock")
-        _dropout_guard(self, self.dropout.p)
         return _FeedForwardFn.apply(self, x.float(), self.layer_norm.weight, self.layer_norm.bias, self.fc1.weight,
                                     self.fc1.bias, self.fc2.weight, self.fc2.bias)
 

@@ -148,4 +148,30 @@ __global__ void posenc_grad_kernel(const float* __restrict__ g, long long rows, 
   }
 }
 
+// ---- dropout (nn.Dropout / the attention-probability dropout of nn.MultiheadAttention) -------------------
+// rovr/common_layers.py:58,70 (MultiheadAttention(dropout=p)) and :87,91 (nn.Dropout after GELU).
+// The keep mask is a pure function of (seed, step counter, call site, element index): nothing is stored,
+// the backward pass recomputes it. `state` = device int64 [2] = {seed, counter} (a snapshot taken by the
+// forward; the live counter is advanced by dropout_advance_kernel, which a CUDA graph captures too, so
+// every replay draws a new mask). out = x * keep / (1 - p).
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long ctr, int site, unsigned long long i,
+                                             uint32_t threshold) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (ctr * 64ull + static_cast<unsigned long long>(site) + 1ull);
+  z ^= i * 0xD1342543DE82EF95ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;     // splitmix64 finaliser
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<uint32_t>(z >> 32) >= threshold;
+}
+template <typename T>
+__global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ out, long long n, uint32_t threshold, float inv_keep,
+                               const long long* __restrict__ state, int site) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long seed = static_cast<unsigned long long>(state[0]), ctr = static_cast<unsigned long long>(state[1]);
+  const float v = dropout_keep(seed, ctr, site, static_cast<unsigned long long>(i), threshold) ? static_cast<float>(x[i]) * inv_keep : 0.f;
+  out[i] = static_cast<T>(v);
+}
+__global__ void dropout_advance_kernel(long long* state) { state[1] += 1; }
+
 }  // namespace rovr

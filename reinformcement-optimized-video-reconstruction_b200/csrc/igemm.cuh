@@ -695,54 +695,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         f1 += bv[2 * j + 1];
                       }
                       pk[j] = p.relu ? pack_bf16x2_relu(f0, f1) : pack_bf16x2(f0, f1);
-                      if constexpr (kPlainEpi && kPool) {   // keep the fp32 values: they break bf16 ties of the pool below
-                        v[c2][2 * j] = __float_as_uint(f0);
-                        v[c2][2 * j + 1] = __float_as_uint(f1);
-                      }
-                    }
-                    [[maybe_unused]] uint32_t mx[8];
-                    if constexpr (kPlainEpi && kPool) {
-                      // 2x2 max-pool of this lane's window (partners: lanes l ^ 1 and l ^ 8) on the packed bf16 values
-                      uint32_t cand = 0;   // bit 2j / 2j+1: this lane's low / high half equals the window maximum
-#pragma unroll
-                      for (int j = 0; j < 8; ++j) {
-                        __nv_bfloat162 a, b;
-                        uint32_t o = __shfl_xor_sync(0xffffffffu, pk[j], 1);
-                        memcpy(&a, &pk[j], 4);
-                        memcpy(&b, &o, 4);
-                        a = __hmax2(a, b);
-                        memcpy(&mx[j], &a, 4);
-                        o = __shfl_xor_sync(0xffffffffu, mx[j], 8);
-                        memcpy(&b, &o, 4);
-                        a = __hmax2(a, b);
-                        memcpy(&mx[j], &a, 4);
-                        cand |= (((pk[j] ^ mx[j]) & 0xffffu) == 0u ? 1u : 0u) << (2 * j);
-                        cand |= (((pk[j] ^ mx[j]) >> 16) == 0u ? 2u : 0u) << (2 * j);
-                      }
-                      // bf16 TIES. Rounding to bf16 is monotonic, so the only windows whose arg-max differs from the
-                      // one an fp32 pipeline picks are those whose top values round to the SAME bf16 (~1 % of the
-                      // windows; the backward kernel re-derives the arg-max from the stored activation as "first
-                      // maximum"). Such ties are resolved here on the fp32 accumulators, and every tied element that
-                      // loses is stored ONE bf16 ulp lower, so that the stored tensor has a unique maximum = the fp32
-                      // winner (the pooled value is unchanged). tie = channels with >= 2 candidates in the window.
-                      const uint32_t c1 = __shfl_xor_sync(0xffffffffu, cand, 1);
-                      const uint32_t and1 = cand & c1, or1 = cand | c1;
-                      const uint32_t tie = and1 | __shfl_xor_sync(0xffffffffu, and1, 8) | (or1 & __shfl_xor_sync(0xffffffffu, or1, 8));
-#pragma unroll
-                      for (int j = 0; j < 8; ++j) {
-                        if (__any_sync(0xffffffffu, (tie >> (2 * j)) & 3u)) {   // warp-uniform: a tie somewhere in this register
-#pragma unroll
-                          for (int hh = 0; hh < 2; ++hh) {
-                            const bool cnd = (cand >> (2 * j + hh)) & 1u;
-                            const float fv = __uint_as_float(v[c2][2 * j + hh]);
-                            const float key = cnd ? fv : -INFINITY;
-                            float km = fmaxf(key, __shfl_xor_sync(0xffffffffu, key, 1));
-                            km = fmaxf(km, __shfl_xor_sync(0xffffffffu, km, 8));
-                            // (equal fp32 values stay tied: the first one wins in the backward, as in ATen)
-                            if (cnd && key < km && ((pk[j] >> (16 * hh)) & 0x7fffu) != 0u && fv > 0.f) pk[j] -= 1u << (16 * hh);
-                          }
-                        }
-                      }
                     }
                     if (blk_mask) {
                       const uint32_t mw[8] = {mreg[2 * ch].x, mreg[2 * ch].y, mreg[2 * ch].z, mreg[2 * ch].w,
@@ -766,9 +718,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                       }
                     }
                     if constexpr (kPlainEpi && kPool) {
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) {
+                        __nv_bfloat162 a, b;
+                        uint32_t o = __shfl_xor_sync(0xffffffffu, pk[j], 1);
+                        memcpy(&a, &pk[j], 4);
+                        memcpy(&b, &o, 4);
+                        a = __hmax2(a, b);
+                        memcpy(&pk[j], &a, 4);
+                        o = __shfl_xor_sync(0xffffffffu, pk[j], 8);
+                        memcpy(&b, &o, 4);
+                        a = __hmax2(a, b);
+                        memcpy(&pk[j], &a, 4);
+                      }
                       if ((lane & 9) == 0) {
-                        *reinterpret_cast<uint4*>(pstg + swz_off(pm, ch * 2, epi_rowb)) = make_uint4(mx[0], mx[1], mx[2], mx[3]);
-                        *reinterpret_cast<uint4*>(pstg + swz_off(pm, ch * 2 + 1, epi_rowb)) = make_uint4(mx[4], mx[5], mx[6], mx[7]);
+                        *reinterpret_cast<uint4*>(pstg + swz_off(pm, ch * 2, epi_rowb)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(pstg + swz_off(pm, ch * 2 + 1, epi_rowb)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                       }
                     }
                     if (blk_cs && !blk_mask && !valid) {   // rows outside the image must not reach the column sums

@@ -1182,3 +1182,22 @@ def lpips_unpack_grad(gx16, gval, shift, scale, normalize):
     _launch("rovr_lpips_unpack_grad", _ptr(gx16), _ptr(gval), _ptr(out), Nn, H, W, _f3(shift), _f3(scale),
             int(normalize), _stream())
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# dropout with a recomputable counter-based mask
+# ---------------------------------------------------------------------------------------------
+def dropout(x, p, state, site, out=None):
+    """out = x * keep / (1 - p); keep = f(state {seed, counter} on the device, site, element index).
+    x: contiguous bf16 or fp32. The same (state, site) gives the same mask (backward recomputes it)."""
+    assert x.is_contiguous() and x.dtype in (torch.bfloat16, torch.float32)
+    assert state.dtype == torch.int64 and state.numel() == 2 and state.is_cuda
+    if out is None:
+        out = torch.empty_like(x)
+    _launch("rovr_dropout", _ptr(x), _ptr(out), x.numel(), int(x.dtype == torch.float32), ctypes.c_float(p), _ptr(state),
+            int(site), _stream())
+    return out
+
+
+def dropout_advance(state):
+    _launch("rovr_dropout_advance", _ptr(state), _stream())

@@ -116,34 +116,9 @@ def test_conv3x3_fprop_fused_pool(B, H, W, Cin, Cout):
     y2 = torch.empty((B, H, W, Cout), dtype=BF, device=dev)
     ops.conv3x3_fprop(x, wk, b, y2, relu=True)
     torch.cuda.synchronize()
-    # the pooled tile is max_pool2d of the convolution output, and of the stored output
-    assert torch.equal(_nchw(pooled), F.max_pool2d(_nchw(y2), 2)), "pooled tile differs from max_pool2d of the conv output"
-    assert torch.equal(_nchw(pooled), F.max_pool2d(_nchw(y.contiguous()), 2))
+    assert torch.equal(y, y2), "fused pooling changed the convolution output"
+    assert torch.equal(_nchw(pooled), F.max_pool2d(_nchw(y2), 2)), "pooled tile differs from max_pool2d of the stored output"
     assert (ybuf[..., :8] == 7.0).all() and (ybuf[..., 8 + Cout:] == 7.0).all()
-    # bf16-tie breaking: the stored output equals the plain convolution except for elements that TIE with their
-    # window's maximum in bf16 but are smaller in fp32 — those are stored one bf16 ulp lower, so that the
-    # backward pass's "first maximum of the stored activation" is the arg-max an fp32 pipeline picks
-    diff = y.contiguous() != y2
-    frac = diff.float().mean().item()
-    assert frac < 0.05, frac
-    if diff.any():
-        lo = y.contiguous()[diff].view(torch.int16).int()
-        hi = y2[diff].view(torch.int16).int()
-        assert ((hi - lo) == 1).all(), "a nudged element must be exactly one bf16 ulp below the conv output"
-        assert (y2[diff] > 0).all()
-    ref = F.relu(F.conv2d(_nchw(x.float()), w.to(BF).float(), b, padding=1))          # fp32 conv of the same bf16 operands
-
-    def argmax_map(t):           # index of the FIRST maximum in every 2x2 window (ATen's rule)
-        win = F.unfold(t.reshape(-1, 1, t.shape[2], t.shape[3]), 2, stride=2)        # [B*C, 4, n]
-        return win.argmax(1)
-
-    live = F.max_pool2d(ref, 2) > 0                                                    # all-zero windows carry no gradient
-    am_ref = argmax_map(ref).reshape(live.shape[0], live.shape[1], -1).reshape(live.shape)
-    agree = lambda t: ((argmax_map(_nchw(t.contiguous()).float()).reshape(live.shape) == am_ref) | ~live).float().mean().item()
-    a_fused, a_plain = agree(y), agree(y2)
-    print(f"fused pool {B}x{H}x{W}x{Cin}->{Cout}: nudged {frac:.4f} of the elements; arg-max agreement with the fp32 conv: "
-          f"{a_fused:.5f} (stored, tie-broken) vs {a_plain:.5f} (plain bf16 rounding)")
-    assert a_fused >= a_plain and a_fused > 0.998
 
 
 @pytest.mark.parametrize("B,H,W,Cin", [(2, 16, 16, 128), (1, 32, 24, 64), (3, 20, 12, 128), (5, 8, 8, 128), (1, 64, 64, 128)])
