@@ -598,25 +598,29 @@ def lpips_state_dict(seed=0):
     return sd
 
 
-def lpips_vgg_features(sd, x):
-    """The five tapped activations of torchvision VGG16 `features` for an already-scaled input."""
+def lpips_vgg_features(sd, x, bf16=False):
+    """The five tapped activations of torchvision VGG16 `features` for an already-scaled input.
+    bf16=True emulates the storage points of the B200 path (fp32 arithmetic; the packed input, the conv
+    weights, every post-ReLU activation and every activation gradient rounded to bf16)."""
+    rt, wq = _storage(bf16)
+    x = rt(x)
     feats = []
     for k, convs in enumerate(VGG16_SLICES):
         if k > 0:
             x = F.max_pool2d(x, 2, 2)
         for idx, _, _ in convs:
-            x = F.relu(F.conv2d(x, sd[f"net.slice{k + 1}.{idx}.weight"], sd[f"net.slice{k + 1}.{idx}.bias"], padding=1))
+            x = rt(F.relu(F.conv2d(x, wq(sd[f"net.slice{k + 1}.{idx}.weight"]), sd[f"net.slice{k + 1}.{idx}.bias"], padding=1)))
         feats.append(x)
     return feats
 
 
-def lpips_vgg(sd, in0, in1, normalize=False):
+def lpips_vgg(sd, in0, in1, normalize=False, bf16=False):
     """lpips.LPIPS(net='vgg').forward(in0, in1, normalize=normalize) -> [N, 1, 1, 1]."""
     if normalize:
         in0, in1 = 2 * in0 - 1, 2 * in1 - 1
     shift, scale = sd["scaling_layer.shift"], sd["scaling_layer.scale"]
-    f0s = lpips_vgg_features(sd, (in0 - shift) / scale)
-    f1s = lpips_vgg_features(sd, (in1 - shift) / scale)
+    f0s = lpips_vgg_features(sd, (in0 - shift) / scale, bf16)
+    f1s = lpips_vgg_features(sd, (in1 - shift) / scale, bf16)
     val = 0.0
     for k, (f0, f1) in enumerate(zip(f0s, f1s)):
         n0 = f0 / (torch.sqrt(torch.sum(f0 ** 2, dim=1, keepdim=True)) + 1e-10)
