@@ -557,6 +557,27 @@ def resnet_extractor_forward(resnet_seq, linear_w, linear_b, x):
     return fmap
 
 
+def video_processor_forward(resnet_seq, linear_w, linear_b, x):
+    """`VideoProcessor` (rovr/rovr.py:61,107; rovr/imitation_learning.py:58,78) — the file is ABSENT from the
+    reference: PARITY UNPINNED AND UN-ORACLED by it. Restated from its call sites as the 32-pixel-tile sibling
+    of rovr/resnet_extractor.py:25-47: per frame ToPILImage -> Resize((224,224)) -> ToTensor, eval-mode ResNet-50
+    trunk at batch 1, Linear(2048, 1024) -> flattened_frames[b, S, 1024]; each vector as a 1x32x32 tile pasted at
+    (s // 5 * 32, s % 5 * 32) of a zero [b, 1, 160, 160] map. Returns (encoded_frames, flattened_frames)."""
+    import torchvision.transforms as transforms
+    prep = transforms.Compose([transforms.ToPILImage(), transforms.Resize((224, 224)), transforms.ToTensor()])
+    b, s_len = x.shape[0], x.shape[1]
+    enc = torch.zeros((b, 1, 160, 160))
+    flat = []
+    for bi in range(b):
+        for s in range(s_len):
+            feat = resnet_seq(prep(x[bi, s]).unsqueeze(0))
+            vec = F.linear(feat.view(-1), linear_w, linear_b)
+            flat.append(vec)
+            r, c = s // 5 * 32, s % 5 * 32
+            enc[bi, :, r:r + 32, c:c + 32] = vec.view(1, 32, 32)
+    return enc, torch.stack(flat).view(b, s_len, -1)
+
+
 # ------------------------------------------------------------------------------------------------
 # LPIPS (net='vgg') perceptual loss — SURVEY §8f-1. Call sites: rovr/train_local_net_unet.py:91,109
 # (`lpips.LPIPS(net='vgg')(y_hat, target).mean()`, normalize=False) and rovr/rovr.py:54,84,255

@@ -31,22 +31,23 @@ BF = torch.bfloat16
 
 
 class _MosaicPaste(torch.autograd.Function):
-    """feature rows [b*S, 768] -> feature_map [b, 3, 80, 80] (zeros elsewhere), rovr/resnet_extractor.py:28-38."""
+    """feature rows [b*S, ch*tile*tile] -> feature_map [b, ch, 5*tile, 5*tile] (zeros elsewhere),
+    rovr/resnet_extractor.py:28-38 (ch = 3, tile = 16; video_processor.VideoProcessor: ch = 1, tile = 32)."""
 
     @staticmethod
-    def forward(ctx, feat, b, S):
+    def forward(ctx, feat, b, S, ch=3, tile=16):
         feat = feat.contiguous()
-        fmap = torch.zeros((b, 3, 80, 80), dtype=torch.float32, device=feat.device)
-        ops.mosaic_paste(feat, fmap, slots_per_mosaic=S)
-        ctx.S = S
+        fmap = torch.zeros((b, ch, 5 * tile, 5 * tile), dtype=torch.float32, device=feat.device)
+        ops.mosaic_paste(feat, fmap, slots_per_mosaic=S, tile=tile)
+        ctx.S, ctx.tile = S, tile
         ctx.n = feat.shape
         return fmap
 
     @staticmethod
     def backward(ctx, g):
         gfeat = torch.empty(ctx.n, dtype=torch.float32, device=g.device)
-        ops.mosaic_paste(gfeat, g.contiguous().float(), slots_per_mosaic=ctx.S, gather=True)
-        return gfeat, None, None
+        ops.mosaic_paste(gfeat, g.contiguous().float(), slots_per_mosaic=ctx.S, tile=ctx.tile, gather=True)
+        return gfeat, None, None, None, None
 
 
 class ResnetFeatureExtractor(torch.nn.Module):

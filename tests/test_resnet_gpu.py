@@ -181,3 +181,40 @@ def test_resnet_built_like_the_reference(monkeypatch):
     m2 = M.ResnetFeatureExtractor().to(_dev())
     with pytest.raises(NotImplementedError):
         m2(x)
+
+
+def test_video_processor_restatement_and_il_step():
+    """video_processor.VideoProcessor (ABSENT from the reference: restated from its call sites, parity
+    unpinned) against the oracle's restatement, then one imitation-learning forward of
+    rovr/imitation_learning.py:72-87 end to end on the drop-ins: frames -> VideoProcessor -> PolicyNetwork2UNet."""
+    import copy
+    from video_processor import VideoProcessor
+    from policy_net_2 import PolicyNetwork2UNet
+    dev = _dev()
+    warnings.filterwarnings("ignore")
+    torch.manual_seed(3)
+    vp = VideoProcessor()
+    O.resnet_randomise_bn(vp.resnet, 61)
+    ref_seq = copy.deepcopy(vp.resnet).eval()
+    lw, lb = vp.linear.weight.detach().clone(), vp.linear.bias.detach().clone()
+    vp = vp.to(dev)
+    g = torch.Generator().manual_seed(8)
+    frames = torch.rand((1, 20, 3, 64, 80), generator=g)
+    enc, flat = vp(frames.to(dev))
+    assert enc.shape == (1, 1, 160, 160) and flat.shape == (1, 20, 1024)
+    with torch.no_grad():
+        enc_ref, flat_ref = O.video_processor_forward(ref_seq, lw, lb, frames)
+    assert _rel(flat, flat_ref) < 2e-2 and _rel(enc, enc_ref) < 2e-2
+    assert float(enc[0, 0, 128:, :].abs().sum()) == 0.0                       # tiles 20..24 stay empty
+    assert torch.equal(enc[0, 0, 32:64, 64:96].reshape(-1), flat[0, 7])       # frame 7 -> tile (1, 2)
+    # rovr/rovr.py:200: overwrite one tile with the encoding of a reconstructed frame
+    enc2 = vp.insert_encoded_frame_batch(torch.tensor(3).view(-1, 1), frames[0, 5:6].to(dev), enc.detach().clone())
+    assert _rel(enc2[0, 0, 0:32, 96:128].reshape(-1), flat[0, 5]) < 1e-3
+    # gradients reach the projection only
+    (flat ** 2).sum().backward()
+    assert vp.linear.weight.grad is not None and all(p.grad is None for p in vp.resnet.parameters())
+    # imitation_learning.py:82-87
+    pn2 = PolicyNetwork2UNet().to(dev).train()
+    encoded = torch.stack([enc.detach()] * 20, dim=0).squeeze(1)             # [20, 1, 160, 160]
+    out = pn2(encoded, flat.detach().transpose(0, 1), torch.arange(20, device=dev).view(20, 1, 1), extra=True)
+    assert out.shape == (20, 20) and torch.isfinite(out).all()
