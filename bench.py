@@ -307,7 +307,9 @@ def run_cuda(args, rank, local_rank, world):
         if graphed is not None:
             def e2e_graph_loop(steps):
                 rb = ScalarReadback(dev, lag=1)
-                for xd, cd, td in DeviceFeeder(((xh, ch, th) for _ in range(steps)), dev):
+                # uint8 frames land in double-buffered device staging; the step converts them (ToTensor) straight
+                # into the graph's static fp32 inputs
+                for xd, cd, td in DeviceFeeder(((xh, ch, th) for _ in range(steps)), dev, to_float=False):
                     rb.exchange(graphed(xd, cd, td))
                 return rb.drain()
             e2e_graph_loop(2)

@@ -462,13 +462,18 @@ class GraphedTrainingStep:
         return all(p.grad is not None and any(lo <= p.grad.data_ptr() < hi for lo, hi in spans)
                    for p in self.P.values() if p.requires_grad)
 
+    def _load(self, dst, src):
+        if src is None:
+            return
+        if src.dtype == torch.uint8:      # frames as decoded (feeder.DeviceFeeder(to_float=False)): ToTensor straight
+            ops.u8_to_f32(src.contiguous(), out=dst)      # into the graph's static input, no fp32 staging copy
+        else:
+            dst.copy_(src, non_blocking=True)
+
     def __call__(self, x=None, context=None, target=None):
-        if x is not None:
-            self.x.copy_(x, non_blocking=True)
-        if context is not None:
-            self.context.copy_(context, non_blocking=True)
-        if target is not None:
-            self.target.copy_(target, non_blocking=True)
+        self._load(self.x, x)
+        self._load(self.context, context)
+        self._load(self.target, target)
         self.graph.replay()
         if self._reduce_after is not None:
             self._reduce_after(self.buckets)                      # NCCL all-reduce (AVG) of the two buckets

@@ -106,3 +106,27 @@ def test_graphed_step_survives_larger_eager_call():
         if n in g0:
             assert torch.equal(p.grad, g0[n]), n
     del junk
+
+
+def test_uint8_frames_feed_equals_host_totensor():
+    """Frames shipped as uint8 (as decoded, rovr/video_ds.py:107-114) and converted on the GPU give exactly
+    the step that host-side ToTensor (uint8 / 255 -> fp32, shipped as fp32) gives — through the feeder's
+    device-side conversion and through GraphedTrainingStep's direct uint8 inputs."""
+    import rovr_oracle as O
+    from feeder import DeviceFeeder
+    from local_net import GraphedTrainingStep, LocalNetworkUNetNorm
+    dev = torch.device("cuda:0")
+    net = LocalNetworkUNetNorm()
+    net.load_state_dict(O.localnet_state_dict(0), strict=True)
+    net = net.to(dev)
+    u8 = [(v * 255.0).round().to(torch.uint8).pin_memory() for v in O.synthetic_localnet_batch(2, 64, 64, seed=51)]
+    f32 = [v.float() / 255.0 for v in u8]                                    # torchvision ToTensor on the host
+    _, want = net.forward_with_mse(*[v.to(dev) for v in f32])
+    (xd, cd, td), = list(DeviceFeeder([tuple(u8)], dev))                     # converted behind the H2D copy
+    assert xd.dtype == torch.float32 and torch.equal(xd.cpu(), f32[0])
+    _, got = net.forward_with_mse(xd, cd, td)
+    assert torch.equal(got, want)
+    step = GraphedTrainingStep(net, *[v.to(dev) for v in f32])
+    (xu, cu, tu), = list(DeviceFeeder([tuple(u8)], dev, to_float=False))
+    assert xu.dtype == torch.uint8
+    assert torch.equal(step(xu, cu, tu), want.detach())
