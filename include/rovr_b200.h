@@ -42,10 +42,11 @@ int rovr_pack_nchw_to_nhwc(const float* s0, int c0, const float* s1, int c1, con
                            void* dst, int B, int H, int W, int cpad, void* stream);
 int rovr_unpack_nhwc_to_nchw(const void* src, int ld, float* dst, int B, int H, int W, int C,
                              void* stream);
-/* torchvision ToTensor on the device: dst[i] = src[i] * scale (uint8 -> fp32, scale = 1/255). The reference
+/* torchvision ToTensor on the device: dst[i] = src[i] / denom (uint8 -> fp32, denom = 255; IEEE division,
+ * bit-identical to the host's .div(255)). The reference
  * decodes frames to uint8 and converts on the host (rovr/video_ds.py:107-121); feeding the uint8 frames and
  * converting here cuts the host -> device bytes of a step 4x. */
-int rovr_u8_to_f32(const void* src, float* dst, long long n, float scale, void* stream);
+int rovr_u8_to_f32(const void* src, float* dst, long long n, float denom, void* stream);
 
 /* ---- weight repacking (fp32 parameter -> bf16 K-major GEMM operand) ------------------------- */
 /* Conv2d 3x3 weight [Cout][Cin][3][3] -> [Cout][9][cin_pad] */

@@ -47,10 +47,11 @@ __global__ void pack_nchw_to_nhwc_kernel(PackSrc src, __nv_bfloat16* __restrict_
   }
 }
 
-// torchvision ToTensor on the device: uint8 -> fp32 * scale (1/255), 16 values per thread. Video frames are
+// torchvision ToTensor on the device: uint8 -> fp32 / denom (255; a true IEEE division, so that the result is
+// bit-identical to the host's `.div(255)`), 16 values per thread. Video frames are
 // decoded to uint8 (rovr/video_ds.py:107-114: cv2.imread / resize, then the ToTensor transform on the host);
 // shipping the uint8 frames and converting here cuts the host -> device bytes of a step 4x.
-__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long long n, float scale) {
+__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long long n, float denom) {
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 16;
   if (i + 16 <= n) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + i));
@@ -58,10 +59,10 @@ __global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restr
     float4* o = reinterpret_cast<float4*>(dst + i);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      o[j] = make_float4((w[j] & 0xffu) * scale, ((w[j] >> 8) & 0xffu) * scale, ((w[j] >> 16) & 0xffu) * scale,
-                         (w[j] >> 24) * scale);
+      o[j] = make_float4(__fdiv_rn(static_cast<float>(w[j] & 0xffu), denom), __fdiv_rn(static_cast<float>((w[j] >> 8) & 0xffu), denom),
+                         __fdiv_rn(static_cast<float>((w[j] >> 16) & 0xffu), denom), __fdiv_rn(static_cast<float>(w[j] >> 24), denom));
   } else {
-    for (long long k = i; k < n; ++k) dst[k] = src[k] * scale;
+    for (long long k = i; k < n; ++k) dst[k] = __fdiv_rn(static_cast<float>(src[k]), denom);
   }
 }
 

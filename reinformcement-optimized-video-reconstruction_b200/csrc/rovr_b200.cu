@@ -290,13 +290,13 @@ extern "C" int rovr_unpack_nhwc_to_nchw(const void* src, int ld, float* dst, int
   return launch_check("unpack_nhwc_to_nchw");
 }
 
-extern "C" int rovr_u8_to_f32(const void* src, float* dst, long long n, float scale, void* stream) {
+extern "C" int rovr_u8_to_f32(const void* src, float* dst, long long n, float denom, void* stream) {
   if (int rc = ensure_device()) return rc;
   ROVR_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0,
                "u8_to_f32: pointers must be 16-byte aligned");
   const long long threads = (n + 15) / 16;
   u8_to_f32_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint8_t*>(src), dst, n, scale);
+      static_cast<const uint8_t*>(src), dst, n, denom);
   return launch_check("u8_to_f32");
 }
 

@@ -126,14 +126,14 @@ def pack_nchw(srcs, cpad, out=None):
     return out
 
 
-def u8_to_f32(src, out=None, scale=1.0 / 255.0):
-    """ToTensor on the device: uint8 tensor (any shape, contiguous) -> fp32 * scale."""
+def u8_to_f32(src, out=None, denom=255.0):
+    """ToTensor on the device: uint8 tensor (any shape, contiguous) -> fp32 / denom (bit-identical to .div(255))."""
     if src.dtype != torch.uint8 or not src.is_cuda or not src.is_contiguous():
         raise ValueError("u8_to_f32: expected a contiguous CUDA uint8 tensor")
     if out is None:
         out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
     assert out.numel() == src.numel() and out.is_contiguous() and out.dtype == torch.float32
-    _launch("rovr_u8_to_f32", _ptr(src), _ptr(out), src.numel(), ctypes.c_float(scale), _stream())
+    _launch("rovr_u8_to_f32", _ptr(src), _ptr(out), src.numel(), ctypes.c_float(denom), _stream())
     return out
 
 
