@@ -659,7 +659,7 @@ def build_workload(name, dev, rank, world, args):
         vid_h = (fr.view(K, S_, 3, H, W) * 255).round().to(torch.uint8).pin_memory()
         org_h = (tg.view(K, S_, 3, H, W) * 255).round().to(torch.uint8).pin_memory()
         vid, org = vid_h.to(dev).float().div_(255), org_h.to(dev).float().div_(255)
-        rl = ROVRStep(actor, critic, local, lp, vp, averager=avgs)
+        rl = ROVRStep(actor, critic, local, lp, vp, averager=avgs, graphed=not args.no_graph)
 
         def e2e(n):
             rb = ScalarReadback(dev, lag=1)
@@ -673,8 +673,9 @@ def build_workload(name, dev, rank, world, args):
                                         "clip(s) per GPU of 20 frames 256x256; rollout = VideoProcessor encode (ResNet-50, 20 frames) + "
                                         "20 time-steps of [PolicyNetwork2UNet actor b=1 per clip, LocalNet forward, LPIPS-VGG reward, "
                                         "re-encode of the reconstructed frame], then PPO on PolicyNetwork2UNet per clip (5 updates of "
-                                        "critic fwd+bwd and logprob fwd+bwd at b=20, Adam); eager launches; gradients averaged over "
-                                        "ranks inside PPO", "clips_per_gpu": K})
+                                        "critic fwd+bwd and logprob fwd+bwd at b=20, Adam); " +
+                                        ("eager launches" if args.no_graph else "one CUDA graph per time-step (replayed 20x) and two "
+                                         "per PPO update") + "; gradients averaged over ranks inside PPO", "clips_per_gpu": K})
     raise ValueError(name)
 
 

@@ -173,3 +173,32 @@ def test_batched_clips_keep_each_trajectory(monkeypatch):
         (single,), _ = step.rollout(vid[k:k + 1].to(dev), org[k:k + 1].to(dev))
         assert torch.equal(single[1], infos2[k][1]), f"clip {k}: batching changed the selected frames"
         assert torch.allclose(single[3], infos2[k][3], rtol=1e-3, atol=1e-5)
+
+
+def test_graphed_rollout_matches_eager():
+    """graphed=True: one CUDA graph per time-step (replayed 20 times with a device-side step counter) and two per
+    PPO update give the eager trajectory — same device RNG stream, so the selected frames are identical."""
+    from rovr_step import ROVRStep
+    dev = _dev()
+    (actor, critic, local, lp, vp), parts = _build(dev)
+    vid, org = _clips(1, 9)
+    eager = ROVRStep(actor, critic, local, lp, vp, n_updates_per_ppo=1)
+    graphed = ROVRStep(actor, critic, local, lp, vp, n_updates_per_ppo=1, graphed=True)
+    # capture first (warm-up + capture consume random numbers and update BatchNorm running statistics — neither
+    # enters the train-mode forward values), then run both from the same generator state
+    graphed.rollout_graphed(vid.to(dev), org.to(dev))
+    torch.manual_seed(1234)
+    (e_info,), e_rec = eager.rollout(vid.to(dev), org.to(dev))
+    torch.manual_seed(1234)
+    (g_info,), g_rec = graphed.rollout_graphed(vid.to(dev), org.to(dev))
+    assert torch.equal(e_info[1], g_info[1]), (e_info[1].tolist(), g_info[1].tolist())
+    assert torch.allclose(e_info[3], g_info[3], rtol=1e-4, atol=1e-6)
+    assert torch.allclose(e_info[2], g_info[2], rtol=1e-4, atol=1e-6)
+    assert torch.allclose(e_info[0][0], g_info[0][0], rtol=1e-4, atol=1e-6) and torch.equal(e_info[0][2], g_info[0][2])
+    assert torch.allclose(e_rec, g_rec, rtol=1e-4, atol=1e-6)
+    # a PPO update through the graphs changes both networks and returns finite losses
+    w0 = actor.final_fc[4].weight.detach().clone()
+    c0 = critic.final_fc[4].weight.detach().clone()
+    losses = graphed.ppo(g_info, dev)
+    assert len(losses) == 1 and all(torch.isfinite(v) for v in losses[0])
+    assert not torch.equal(actor.final_fc[4].weight, w0) and not torch.equal(critic.final_fc[4].weight, c0)
