@@ -775,9 +775,9 @@ def main():
     if world != args.gpus and world == 1 and args.gpus > 1:
         # launched without torchrun: re-exec under torch.distributed.run on this node
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
-               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 400), os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
-               "--workload", args.workload, "--clips", str(args.clips)]
+               "--workload", args.workload, "--clips", str(args.clips)] + (["--no-graph"] if args.no_graph else [])
         sys.exit(subprocess.call(cmd))
     if args.workload != "localnet":
         run_workload(args, rank, local_rank, world)
