@@ -668,7 +668,7 @@ def build_workload(name, dev, rank, world, args):
                 rb.exchange(losses[-1][-1][1])
             rb.drain()
         return dict(step=lambda: rl.train(vid, org), e2e=e2e, units=K * S_, gflop_per_unit=0.0,
-                    h2d=vid_h.numel() + org_h.numel(), d2h=4, close=lambda: None, launches=None,
+                    h2d=vid_h.numel() + org_h.numel(), d2h=4, close=lambda: None, launches=None, replayed=rl,
                     config={"workload": f"one RL iteration of rovr/rovr.py:68-337 restated on the drop-ins (rovr_step.ROVRStep): {K} "
                                         "clip(s) per GPU of 20 frames 256x256; rollout = VideoProcessor encode (ResNet-50, 20 frames) + "
                                         "20 time-steps of [PolicyNetwork2UNet actor b=1 per clip, LocalNet forward, LPIPS-VGG reward, "
@@ -717,9 +717,12 @@ def run_workload(args, rank, local_rank, world):
     for _ in range(max(args.warmup, 3)):
         wl["step"]()
     n0 = _native.lib.rovr_launch_count()
+    r0 = wl["replayed"].replayed_launches if wl.get("replayed") is not None else 0
     ms_total = timed(lambda: [wl["step"]() for _ in range(args.steps)])
-    # kernels launched by this library in the timed region: counted (eager workloads) or replayed from a graph
+    # kernels launched by this library in the timed region: counted (eager launches) plus replayed from graphs
     launches_total = (wl["launches"] * args.steps) if wl["launches"] else (_native.lib.rovr_launch_count() - n0)
+    if wl.get("replayed") is not None:
+        launches_total += wl["replayed"].replayed_launches - r0
     clocks = sampler.stop() if rank == 0 else {}
     wl["e2e"](2)
     ms_e2e = timed(lambda: wl["e2e"](args.steps))

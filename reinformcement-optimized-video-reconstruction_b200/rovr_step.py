@@ -40,6 +40,8 @@ class ROVRStep:
         self.num_updates_per_ppo = n_updates_per_ppo
         self.averagers = averager            # optional (actor, critic) data_parallel.GradientAverager pair
         self.graphed = graphed
+        self.replayed_launches = 0           # kernels of librovr_b200 launched through graph replays (bench.py reports them)
+        self.launches_per_time_step = 0
         self._ts_graph = None                # (key, graph, state) of the captured time-step
         self._ppo_graphs = None
 
@@ -142,9 +144,12 @@ class ROVRStep:
                 self._time_step(st)
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
+            import _native
+            n0 = _native.lib.rovr_launch_count()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self._time_step(st)
+            self.launches_per_time_step = int(_native.lib.rovr_launch_count() - n0)   # kernels of this library per replay
             self._ts_graph = (key, graph, st)
         _, graph, st = self._ts_graph
         st["video"].copy_(video)
@@ -158,6 +163,7 @@ class ROVRStep:
         st["j"].zero_()
         for _ in range(S):
             graph.replay()
+        self.replayed_launches += S * self.launches_per_time_step
         rtg = torch.flip(torch.cumsum(torch.flip(st["rewards"], [1]), 1), [1])
         steps = torch.arange(S, dtype=torch.int64, device=dev).unsqueeze(-1)
         out = [((st["obs_enc"][k].clone(), st["flattened"][k].clone(), steps), st["acs"][k].clone(), st["logp"][k].clone(),
@@ -201,6 +207,7 @@ class ROVRStep:
                 self.averagers[1].average()
             self.critic_optimizer.step()
             a_loss = ga(*obs, acs, log_prob, A_k)
+            self.replayed_launches += gc.launches + ga.launches
             if self.averagers is not None:
                 self.averagers[0].average()
             self.actor_optimizer.step()
