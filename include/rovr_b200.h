@@ -47,6 +47,11 @@ int rovr_unpack_nhwc_to_nchw(const void* src, int ld, float* dst, int B, int H, 
  * decodes frames to uint8 and converts on the host (rovr/video_ds.py:107-121); feeding the uint8 frames and
  * converting here cuts the host -> device bytes of a step 4x. */
 int rovr_u8_to_f32(const void* src, float* dst, long long n, float denom, void* stream);
+/* the dataset's mask corruption on the device (rovr/video_ds.py:62-87, the deterministic box of every difficulty):
+ * image i (NCHW fp32, clip-frame index frame_index[i], device int64) gets a zeroed box_w x box_h box at
+ * x0 = (n % 8) * W / 8, y0 = (n / 8) * H / 3, clipped; out = clean * mask; mask (optional) as in the dataset. */
+int rovr_corrupt_frames(const float* clean, const long long* frame_index, float* out, float* mask, int N, int C,
+                        int H, int W, int box_w, int box_h, void* stream);
 
 /* ---- weight repacking (fp32 parameter -> bf16 K-major GEMM operand) ------------------------- */
 /* Conv2d 3x3 weight [Cout][Cin][3][3] -> [Cout][9][cin_pad] */

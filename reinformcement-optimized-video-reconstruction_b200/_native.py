@@ -33,6 +33,7 @@ SIGNATURES = {
     "rovr_pack_nchw_to_nhwc": (_i, [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p]),
     "rovr_unpack_nhwc_to_nchw": (_i, [_p, _i, _p, _i, _i, _i, _i, _p]),
     "rovr_u8_to_f32": (_i, [_p, _p, _ll, _f, _p]),
+    "rovr_corrupt_frames": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "rovr_repack_conv3x3_fprop": (_i, [_p, _p, _i, _i, _i, _p]),
     "rovr_repack_conv3x3_dgrad": (_i, [_p, _p, _i, _i, _i, _p]),
     "rovr_repack_convT2x2_fprop": (_i, [_p, _p, _i, _i, _p]),

@@ -66,6 +66,25 @@ __global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restr
   }
 }
 
+// The dataset's mask corruption on the device (rovr/video_ds.py:62-87, difficulty < 2 branch): frame n of a clip
+// gets a zeroed box_w x box_h box at x0 = (n % 8) * W / 8, y0 = (n / 8) * H / 3, clipped to the frame;
+// out = clean * mask, mask (optional) = 1 outside the box. frame_index[i] is the clip-frame index n of image i.
+__global__ void corrupt_frames_kernel(const float* __restrict__ clean, const long long* __restrict__ frame_index,
+                                      float* __restrict__ out, float* __restrict__ mask, int N, int C, int H, int W,
+                                      int box_w, int box_h) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(N) * C * H * W;
+  if (i >= total) return;
+  const int x = static_cast<int>(i % W);
+  const int y = static_cast<int>((i / W) % H);
+  const int n = static_cast<int>(i / (static_cast<long long>(C) * H * W));
+  const long long f = frame_index[n];
+  const int x0 = static_cast<int>(f % 8) * W / 8, y0 = static_cast<int>(f / 8) * H / 3;
+  const bool inside = x >= x0 && x < min(W, x0 + box_w) && y >= y0 && y < min(H, y0 + box_h);
+  out[i] = inside ? 0.f : clean[i];
+  if (mask != nullptr) mask[i] = inside ? 0.f : 1.f;
+}
+
 // NHWC bf16 (ld) -> NCHW fp32, used to hand results back at the module boundary.
 __global__ void unpack_nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int ld,
                                            float* __restrict__ dst, int B, int HW, int C) {

@@ -300,6 +300,16 @@ extern "C" int rovr_u8_to_f32(const void* src, float* dst, long long n, float de
   return launch_check("u8_to_f32");
 }
 
+extern "C" int rovr_corrupt_frames(const float* clean, const long long* frame_index, float* out, float* mask, int N,
+                                   int C, int H, int W, int box_w, int box_h, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  ROVR_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && box_w > 0 && box_h > 0, "corrupt_frames: empty problem");
+  const long long n = 1ll * N * C * H * W;
+  corrupt_frames_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      clean, frame_index, out, mask, N, C, H, W, box_w, box_h);
+  return launch_check("corrupt_frames");
+}
+
 static int repack(const float* w, void* wk, int d0, int d1, int d2, long long s0, long long s1,
                   long long s2, int v0, int v2, void* stream, long long off = 0) {
   w += off;

@@ -137,6 +137,19 @@ def u8_to_f32(src, out=None, denom=255.0):
     return out
 
 
+def corrupt_frames(clean, frame_index, box_w=150, box_h=100, want_mask=False):
+    """rovr/video_ds.py:62-87 on the device: (clean * mask[, mask]) for NCHW fp32 images whose clip-frame indices are
+    `frame_index` (int64 [N], on the device)."""
+    _f32(clean, "clean")
+    N_, C, H, W = clean.shape
+    fi = _idx(frame_index, "frame_index")
+    assert fi.numel() == N_
+    out = torch.empty_like(clean)
+    mask = torch.empty_like(clean) if want_mask else None
+    _launch("rovr_corrupt_frames", _ptr(clean), _ptr(fi), _ptr(out), _ptr(mask), N_, C, H, W, int(box_w), int(box_h), _stream())
+    return (out, mask) if want_mask else out
+
+
 def unpack_nhwc(x, C=None):
     B, H, W, Cx, ld = _act(x)
     C = Cx if C is None else C

@@ -406,3 +406,34 @@ def test_colsum(npix_shape, C):
     ops.colsum(x, out)
     torch.cuda.synchronize()
     _report("colsum", out, x.float().sum(dim=(0, 1, 2)), 1e-4)
+
+
+def test_corrupt_frames_matches_dataset_logic():
+    """rovr/video_ds.py:62-87 (the deterministic zeroed box; frame_index already halved as in :63) restated in numpy
+    vs the device kernel, at the dataset's 256x256 and at a non-square size."""
+    import numpy as np
+    import ops
+    dev = _dev()
+
+    def corrupt_frame(frame, frame_index):            # frame HWC, as in the reference
+        h, w, _ = frame.shape
+        mask = np.ones_like(frame)
+        section_idx, position_idx = frame_index // 8, frame_index % 8
+        start_y = section_idx * h // 3
+        end_y = start_y + 100
+        start_x = position_idx * w // 8
+        end_x = start_x + 150
+        start_x, end_x = max(0, start_x), min(w, end_x)
+        start_y, end_y = max(0, start_y), min(h, end_y)
+        mask[start_y:end_y, start_x:end_x, :] = 0
+        return frame * mask, mask
+
+    for H, W in ((256, 256), (120, 200)):
+        g = torch.Generator().manual_seed(H)
+        clean = torch.rand((25, 3, H, W), generator=g)
+        idx = torch.arange(25)
+        out, mask = ops.corrupt_frames(clean.to(dev), idx.to(dev), want_mask=True)
+        for n in range(25):
+            ref, m = corrupt_frame(clean[n].permute(1, 2, 0).numpy(), n)
+            assert np.array_equal(out[n].permute(1, 2, 0).cpu().numpy(), ref), (H, W, n)
+            assert np.array_equal(mask[n].permute(1, 2, 0).cpu().numpy(), m)
