@@ -352,9 +352,11 @@ int rovr_colsum_rows(const void* g, long long ld, long long M, int C, float* out
  * operand), 3: [h m h] (gradient operand), 2: [h m]. src is addressed through element strides (batch, row,
  * column, channel), so NHWC views and NCHW tensors both work; with src2 != NULL channels c_split .. C are
  * read from src2 (same strides): torch.cat([image, context], 1) of rovr/policy_net_1.py:88 without the
- * copy. kh = kw = sh = sw = 1: no pooling.
+ * copy. relu_mask != NULL (same strides as src, no pooling / second source): values are taken as 0 where the
+ * mask is <= 0 — the ReLU backward of the producing layer folded into the gradient split.
+ * kh = kw = sh = sw = 1: no pooling.
  * Replaces F.max_pool2d + the operand conversion in front of every convolution of the trunks. */
-int rovr_split_stack(const float* src, const float* src2, int c_split, long long s_b, long long s_y,
+int rovr_split_stack(const float* src, const float* src2, int c_split, const float* relu_mask, long long s_b, long long s_y,
                      long long s_x, long long s_c, int B, int H, int W, int C, int kh, int kw, int sh, int sw,
                      void* dst, int dst_ld, int cb, int c_off, int cw, int nterms, void* stream);
 /* weight side of the same products: w fp32 [d0][d1][inner] -> out fp32 with dim stack_dim (0 / 1) replaced
@@ -416,6 +418,14 @@ int rovr_lpips_pack(const float* in0, const float* in1, void* dst, int N, int H,
 int rovr_lpips_head_blocks(int N, long long hw);
 int rovr_lpips_head(const void* feats, int N, long long hw, int C, const float* lin_w, void* grad, float* partial,
                     int nblocks, void* stream);
+/* fp32 variants for LPIPS(precision="fp32x") (VGG16 on the emulated-fp32 path of csrc/fp32x.cuh): packed input
+ * [2N][H][W][4] fp32, fp32 features / feature gradients, gradient w.r.t. the packed input [N][H][W][ld] fp32 */
+int rovr_lpips_pack_f32(const float* in0, const float* in1, float* dst, int N, int H, int W, const float* shift3,
+                        const float* scale3, int normalize, void* stream);
+int rovr_lpips_head_f32(const float* feats, int N, long long hw, int C, const float* lin_w, float* grad,
+                        float* partial, int nblocks, void* stream);
+int rovr_lpips_unpack_grad_f32(const float* gx, int ld, const float* gval, float* gout, int N, int H, int W,
+                               const float* shift3, const float* scale3, int normalize, void* stream);
 /* val[n] = sum over taps of (sum of partial blocks) / hw; partials / nblocks / hws are HOST arrays of ntaps entries */
 int rovr_lpips_finalize(const float* const* partials, const int* nblocks, const long long* hws, int ntaps, int N,
                         float* val, void* stream);

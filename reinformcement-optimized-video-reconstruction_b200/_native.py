@@ -108,7 +108,7 @@ SIGNATURES = {
     "rovr_colsum_rows_workspace": (_sz, [_i]),
     "rovr_colsum_rows": (_i, [_p, _ll, _ll, _i, _p, _p, _sz, _p]),
     "rovr_colsum": (_i, [_p, _i, _ll, _i, _p, _p, _sz, _p]),
-    "rovr_split_stack": (_i, [_p, _p, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p]),
+    "rovr_split_stack": (_i, [_p, _p, _i, _p, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p]),
     "rovr_split_weights": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "rovr_blocksum4": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "rovr_conv3x3_f32out": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
@@ -126,6 +126,9 @@ SIGNATURES = {
     "rovr_dropout_advance": (_i, [_p, _p]),
     "rovr_lpips_pack": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _i, _p]),
     "rovr_lpips_head_blocks": (_i, [_i, _ll]),
+    "rovr_lpips_pack_f32": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _i, _p]),
+    "rovr_lpips_head_f32": (_i, [_p, _i, _ll, _i, _p, _p, _p, _i, _p]),
+    "rovr_lpips_unpack_grad_f32": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _p, _i, _p]),
     "rovr_lpips_head": (_i, [_p, _i, _ll, _i, _p, _p, _p, _i, _p]),
     "rovr_lpips_finalize": (_i, [_p, _p, _p, _i, _i, _p, _p]),
     "rovr_lpips_unpack_grad": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _i, _p]),

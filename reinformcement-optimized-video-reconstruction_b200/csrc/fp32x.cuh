@@ -56,6 +56,8 @@ struct SplitSrc {
   const float* p;
   const float* p2;            // optional second tensor with the same strides: channels c_split .. C come from it
   int c_split;                //   (torch.cat([image, context], 1) of rovr/policy_net_1.py:88 without the copy)
+  const float* relu_mask;     // optional tensor with the same strides: the value is taken as 0 where mask <= 0 (the
+                              //   ReLU backward of the producing layer folded into the gradient split; no pooling then)
   long long sb, sy, sx, sc;   // element strides of (batch, row, column, channel): NHWC views and NCHW tensors alike
 };
 
@@ -83,6 +85,7 @@ __global__ void split_stack_kernel(SplitSrc s, int B, int H, int W, int C, int k
       const float* base = (c < s.c_split ? s.p + c * s.sc : s.p2 + (c - s.c_split) * s.sc) + b * s.sb +
                           static_cast<long long>(oy) * sh * s.sy + static_cast<long long>(ox) * sw_ * s.sx;
       m = __ldg(base);
+      if (s.relu_mask != nullptr && !(__ldg(s.relu_mask + (base - s.p)) > 0.f)) m = 0.f;
       for (int dy = 0; dy < kh; ++dy)
         for (int dx = 0; dx < kw; ++dx) {
           if (dy == 0 && dx == 0) continue;

@@ -47,12 +47,99 @@ __global__ void lpips_unpack_grad_kernel(const __nv_bfloat16* __restrict__ gx16,
   o[2 * hw] = bf16_lo(u.y) * sc.inv_scale[2] * g;
 }
 
+// fp32 variants for the emulated-fp32 mode (LPIPS(precision="fp32x")): dst [2N][H][W][4] fp32 (3 valid channels)
+__global__ void lpips_pack_f32_kernel(const float* __restrict__ in0, const float* __restrict__ in1, int N, long long hw,
+                                      LpipsScale sc, float* __restrict__ dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= 2ll * N * hw) return;
+  const long long n = i / hw, p = i - n * hw;
+  const float* src = (n < N ? in0 + n * 3 * hw : in1 + (n - N) * 3 * hw) + p;
+  float v[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) v[c] = ((sc.pre_mul * __ldg(src + c * hw) + sc.pre_add) - sc.shift[c]) * sc.inv_scale[c];
+  reinterpret_cast<float4*>(dst)[i] = make_float4(v[0], v[1], v[2], 0.f);
+}
+// gx [N][H][W][ld] fp32 (gradient w.r.t. the packed input, first 3 channels) -> gout NCHW
+__global__ void lpips_unpack_grad_f32_kernel(const float* __restrict__ gx, int ld, int N, long long hw, LpipsScale sc,
+                                             const float* __restrict__ gval, float* __restrict__ gout) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(N) * hw) return;
+  const long long n = i / hw, p = i - n * hw;
+  const float g = gval[n] * sc.pre_mul;
+  float* o = gout + n * 3 * hw + p;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o[c * hw] = gx[i * ld + c] * sc.inv_scale[c] * g;
+}
+
 constexpr int LP_WARPS = 8;
 
 // One tap. F: [2N][hw][C] bf16 (post-ReLU features; images n and N + n are compared), w: [C] lin weights.
 // partial[n * gridDim.x + blockIdx.x] = sum over this block's pixels of sum_c w_c (a_c - b_c)^2 with
 // a = f0 / (|f0| + 1e-10), b = f1 / (|f1| + 1e-10). G (optional, [N][hw][C] bf16) = inv_hw * d(that)/d f0,
 // masked by f0 > 0 (the ReLU the features came through). One warp per pixel, CPL channels per lane.
+// fp32 features (emulated-fp32 mode): same arithmetic, scalar loads / stores (lane l owns channels l, l + 32, ...)
+template <int CPL>
+__global__ void __launch_bounds__(LP_WARPS * 32)
+lpips_head_f32_kernel(const float* __restrict__ F, int N, long long hw, const float* __restrict__ w, float inv_hw,
+                      float* __restrict__ G, float* __restrict__ partial) {
+  constexpr int C = CPL * 32;
+  __shared__ float sacc[LP_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.y;
+  const float* f0p = F + static_cast<long long>(n) * hw * C + lane;
+  const float* f1p = F + static_cast<long long>(N + n) * hw * C + lane;
+  float wv[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) wv[j] = __ldg(w + lane + 32 * j);
+  float acc = 0.f;
+  for (long long p = static_cast<long long>(blockIdx.x) * LP_WARPS + warp; p < hw; p += static_cast<long long>(gridDim.x) * LP_WARPS) {
+    float a[CPL], b[CPL];
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      a[j] = __ldg(f0p + p * C + 32 * j);
+      b[j] = __ldg(f1p + p * C + 32 * j);
+      s0 = fmaf(a[j], a[j], s0);
+      s1 = fmaf(b[j], b[j], s1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    const float n0 = sqrtf(s0), n1 = sqrtf(s1);
+    const float i0 = 1.f / (n0 + 1e-10f), i1 = 1.f / (n1 + 1e-10f);
+    float v = 0.f, dot = 0.f, u[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const float d = a[j] * i0 - b[j] * i1;
+      v = fmaf(wv[j] * d, d, v);
+      u[j] = 2.f * wv[j] * d;
+      dot = fmaf(u[j], a[j], dot);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v += __shfl_xor_sync(0xffffffffu, v, o);
+      dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    }
+    acc += v;
+    if (G != nullptr) {
+      const float coef = n0 > 0.f ? dot * i0 * i0 / n0 : 0.f;
+      float* gp = G + (static_cast<long long>(n) * hw + p) * C + lane;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) gp[32 * j] = a[j] > 0.f ? inv_hw * (u[j] * i0 - coef * a[j]) : 0.f;
+    }
+  }
+  if (lane == 0) sacc[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < LP_WARPS; ++k) s += sacc[k];
+    partial[static_cast<long long>(n) * gridDim.x + blockIdx.x] = s;
+  }
+}
+
 template <int CPL>
 __global__ void __launch_bounds__(LP_WARPS * 32)
 lpips_head_kernel(const __nv_bfloat16* __restrict__ F, int N, long long hw, const float* __restrict__ w, float inv_hw,

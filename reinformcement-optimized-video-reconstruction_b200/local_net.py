@@ -396,8 +396,11 @@ class GraphedTrainingStep:
             g_out = None
             if lpips_fn is not None:
                 import lpips_vgg
-                self.lpips, saved = lpips_vgg._forward_impl(lpips_fn, y, self.target, normalize, True)
-                g_out = lpips_vgg._backward_impl(lpips_fn, saved, self._g_lpips)
+                f32 = lpips_fn.precision == "fp32x"
+                fwd = lpips_vgg._forward_impl_f32 if f32 else lpips_vgg._forward_impl
+                bwd = lpips_vgg._backward_impl_f32 if f32 else lpips_vgg._backward_impl
+                self.lpips, saved = fwd(lpips_fn, y, self.target, normalize, True)
+                g_out = bwd(lpips_fn, saved, self._g_lpips)
             _backward_impl(net, acts, Pd, self.target, g_out, self._g_loss, buckets=(dec_flat, enc_flat, G))
             return y, loss
 

@@ -105,10 +105,79 @@ def _backward_impl(mod, saved, gval):
     return ops.lpips_unpack_grad(g, gval.contiguous(), mod._shift_host, mod._scale_host, normalize)
 
 
+# ---- precision="fp32x": the same network on the emulated-fp32 tensor-core path (csrc/fp32x.cuh) ---------------
+# fp32 NHWC activations; every convolution is the 6-term split-bf16 product (forward) / 3-term (data gradient)
+# stacked along the channel dimension, fp32 epilogue. Removes the ReLU-sign noise of bf16 operands from the pixel
+# gradient d lpips / d in0 at ~6x the convolution cost.
+def _pad16(c):
+    return (c + 15) // 16 * 16
+
+
+def _forward_impl_f32(mod, in0, in1, normalize, want_grad):
+    N, _, H, W = in0.shape
+    dev = in0.device
+    pk = mod._packed
+    x = ops.lpips_pack_f32(in0, in1, mod._shift_host, mod._scale_host, normalize)        # [2N, H, W, 4] fp32
+    acts, feats = [], []
+    pool = None
+    for k, convs in enumerate(_SLICES):
+        for j, (idx, cin, cout) in enumerate(convs):
+            conv = getattr(getattr(mod.net, f"slice{k + 1}"), str(idx))
+            cbi = ops.pad8(cin)
+            wk = pk.get((k, idx, "f6"), conv.weight, lambda t: ops.repack_conv3x3(ops.split_weights(t, 1, 6, cbi), False))
+            xs = ops.split_stack(x, 6, cbi, pool=pool)                   # MaxPool2d(2, 2) of the previous slice fused in
+            pool = None
+            B2, h, w, _ = xs.shape
+            y = torch.empty((B2, h, w, cout), dtype=torch.float32, device=dev)
+            ops.conv3x3_f32out(xs, wk, conv.bias, y, relu=True)
+            acts.append((x, y))
+            x = y
+        feats.append(x)
+        pool = (2, 2, 2, 2)
+    partials, grads = [], []
+    for k, f in enumerate(feats):
+        lin_w = getattr(mod, f"lin{k}").model[1].weight
+        p_, g_ = ops.lpips_head_f32(f, lin_w.detach().reshape(-1).contiguous(), want_grad)
+        partials.append(p_)
+        grads.append(g_)
+    val = ops.lpips_finalize(partials, [f.shape[1] * f.shape[2] for f in feats], N)
+    saved = (acts, feats, grads, N, normalize) if want_grad else None
+    return val, saved
+
+
+def _backward_impl_f32(mod, saved, gval):
+    acts, feats, grads, N, normalize = saved
+    pk = mod._packed
+    dev = gval.device
+    g = grads[4]                  # d / d relu5_3, already masked by the feature's own ReLU
+    mask = None                   # ReLU mask still to be applied to g (folded into its split)
+    ci = len(acts)
+    for k in range(4, -1, -1):
+        convs = _SLICES[k]
+        for j in range(len(convs) - 1, -1, -1):
+            idx, cin, cout = convs[j]
+            ci -= 1
+            conv = getattr(getattr(mod.net, f"slice{k + 1}"), str(idx))
+            cbo = _pad16(cout)
+            wd = pk.get((k, idx, "d3"), conv.weight, lambda t: ops.repack_conv3x3(ops.split_weights(t, 0, 3, cbo), True))
+            ds = ops.split_stack(g, 3, cbo, relu_mask=mask)
+            xin = acts[ci][0]
+            dx = torch.empty((N, ds.shape[1], ds.shape[2], _pad16(cin)), dtype=torch.float32, device=dev)
+            ops.conv3x3_f32out(ds, wd, None, dx)
+            g = dx
+            mask = xin[:N] if j > 0 else None          # ReLU of the producing convolution (same slice)
+        if k > 0:
+            f = feats[k - 1][:N]                       # g is the gradient w.r.t. the pooled tensor
+            g = ops.maxpool_f32_bwd(f, g, torch.empty(f.shape, dtype=torch.float32, device=dev), 2, gskip=grads[k - 1])
+            mask = f                                   # relu{k}'s mask, applied when g is split for the next dgrad
+    return ops.lpips_unpack_grad_f32(g, gval.contiguous(), mod._shift_host, mod._scale_host, normalize)
+
+
 class _LPIPSFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, in0, in1, normalize):
-        val, saved = _forward_impl(mod, in0, in1, normalize, ctx.needs_input_grad[1])
+        fwd = _forward_impl_f32 if mod.precision == "fp32x" else _forward_impl
+        val, saved = fwd(mod, in0, in1, normalize, ctx.needs_input_grad[1])
         ctx.mod, ctx.saved = mod, saved
         return val.view(-1, 1, 1, 1)
 
@@ -116,7 +185,8 @@ class _LPIPSFunction(torch.autograd.Function):
     def backward(ctx, gval):
         if ctx.saved is None:
             return None, None, None, None
-        gin0 = _backward_impl(ctx.mod, ctx.saved, gval.reshape(-1).float())
+        bwd = _backward_impl_f32 if ctx.mod.precision == "fp32x" else _backward_impl
+        gin0 = bwd(ctx.mod, ctx.saved, gval.reshape(-1).float())
         ctx.saved = None
         return None, gin0, None, None
 
@@ -158,8 +228,13 @@ class LPIPS(nn.Module):
     """lpips.LPIPS(net='vgg') (v0.1): forward(in0, in1, retPerLayer=False, normalize=False) -> [N, 1, 1, 1]."""
 
     def __init__(self, pretrained=False, net="vgg", version="0.1", lpips=True, spatial=False, pnet_rand=False,
-                 pnet_tune=False, use_dropout=True, model_path=None, eval_mode=True, verbose=False):
+                 pnet_tune=False, use_dropout=True, model_path=None, eval_mode=True, verbose=False, precision="bf16"):
+        """precision (not in the package): "bf16" = bf16 tensor-core convolutions (fast; values 3e-4, parameter-level
+        gradients 2e-2 from fp32), "fp32x" = emulated fp32 on the tensor cores (pixel gradient also fp32-class)."""
         super().__init__()
+        if precision not in ("bf16", "fp32x"):
+            raise ValueError(precision)
+        self.precision = precision
         if net not in ("vgg", "vgg16") or not lpips or spatial or pnet_tune:
             raise NotImplementedError("only LPIPS(net='vgg', lpips=True, spatial=False) — the configuration the "
                                       "reference uses (rovr/train_local_net_unet.py:91, rovr/rovr.py:54)")

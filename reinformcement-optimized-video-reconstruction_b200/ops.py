@@ -965,7 +965,7 @@ def pad8(c):
     return (c + 7) // 8 * 8
 
 
-def split_stack(src, nterms, cb, layout="nhwc", pool=None, out=None, src2=None):
+def split_stack(src, nterms, cb, layout="nhwc", pool=None, out=None, src2=None, relu_mask=None):
     """Stacked bf16 pieces of an fp32 tensor: out[b, y, x, t*cb + c] = piece_t(maxpool(src)[b, y, x, c]),
     zero for c >= C. src: NHWC fp32 view (layout "nhwc") or NCHW fp32 tensor ("nchw"; src2 = a second
     NCHW tensor of the same shape concatenated behind it along C). pool: None or (kh, kw, sh, sw).
@@ -988,7 +988,10 @@ def split_stack(src, nterms, cb, layout="nhwc", pool=None, out=None, src2=None):
     assert cb >= C and cb % 2 == 0
     if out is None:
         out = torch.empty((B, Ho, Wo, nterms * cb), dtype=torch.bfloat16, device=src.device)
-    _launch("rovr_split_stack", _ptr(src), _ptr(src2), c_split, sb, sy, sx, sc, B, H, W, C, kh, kw, sh, sw, _ptr(out), out.stride(2), cb, 0,
+    if relu_mask is not None:       # same view geometry as src: value taken as 0 where mask <= 0
+        assert layout == "nhwc" and pool is None and relu_mask.shape == src.shape and relu_mask.stride() == src.stride()
+        assert relu_mask.dtype == torch.float32
+    _launch("rovr_split_stack", _ptr(src), _ptr(src2), c_split, _ptr(relu_mask), sb, sy, sx, sc, B, H, W, C, kh, kw, sh, sw, _ptr(out), out.stride(2), cb, 0,
             cb, nterms, _stream())
     return out
 
@@ -1214,3 +1217,34 @@ def dropout(x, p, state, site, out=None):
 
 def dropout_advance(state):
     _launch("rovr_dropout_advance", _ptr(state), _stream())
+
+
+def lpips_pack_f32(in0, in1, shift, scale, normalize):
+    """fp32 variant: [2N, H, W, 4] fp32 (3 valid channels)."""
+    _f32(in0, "in0")
+    _f32(in1, "in1")
+    N_, C, H, W = in0.shape
+    assert C == 3 and in1.shape == in0.shape
+    out = torch.empty((2 * N_, H, W, 4), dtype=torch.float32, device=in0.device)
+    _launch("rovr_lpips_pack_f32", _ptr(in0), _ptr(in1), _ptr(out), N_, H, W, _f3(shift), _f3(scale), int(normalize), _stream())
+    return out
+
+
+def lpips_head_f32(feats, lin_w, want_grad):
+    B2, h, w, C, ld = _actf(feats, "feats")
+    assert ld == C and B2 % 2 == 0 and feats.is_contiguous()
+    N_ = B2 // 2
+    nb = N_lib_head_blocks(N_, h * w)
+    partial = torch.empty((N_, nb), dtype=torch.float32, device=feats.device)
+    grad = torch.empty((N_, h, w, C), dtype=torch.float32, device=feats.device) if want_grad else None
+    _launch("rovr_lpips_head_f32", _ptr(feats), N_, h * w, C, _ptr(lin_w), _ptr(grad), _ptr(partial), nb, _stream())
+    return partial, grad
+
+
+def lpips_unpack_grad_f32(gx, gval, shift, scale, normalize):
+    Nn, H, W, C, ld = _actf(gx, "gx")
+    _f32(gval, "gval")
+    out = torch.empty((Nn, 3, H, W), dtype=torch.float32, device=gx.device)
+    _launch("rovr_lpips_unpack_grad_f32", _ptr(gx), ld, _ptr(gval), _ptr(out), Nn, H, W, _f3(shift), _f3(scale),
+            int(normalize), _stream())
+    return out

@@ -193,3 +193,29 @@ def test_graphed_step_with_lpips_matches_eager():
             if n in g:
                 assert torch.equal(p.grad, g[n]), (gamma, n)
     assert not torch.equal(g1["conv7.weight"], g2["conv7.weight"])
+
+
+@pytest.mark.parametrize("shape,normalize", [((2, 64, 48), True), ((2, 128, 128), False)])
+def test_lpips_fp32x_mode_pixel_gradient(shape, normalize):
+    """LPIPS(precision="fp32x"): VGG16 on the emulated-fp32 tensor-core path — the value AND the raw pixel gradient
+    d lpips / d in0 within the north_star tolerance of the fp32 oracle (the bf16 mode cannot: ReLU-sign noise)."""
+    from lpips_vgg import LPIPS
+    dev = _dev()
+    sd = O.lpips_state_dict(0)
+    m = LPIPS(net="vgg", precision="fp32x")
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev)
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+    n, h, w = shape
+    g = torch.Generator().manual_seed(h + w)
+    in0 = torch.rand((n, 3, h, w), generator=g).to(dev)
+    in1 = torch.rand((n, 3, h, w), generator=g).to(dev)
+    x0 = in0.clone().requires_grad_(True)
+    val = m(x0, in1, normalize=normalize)
+    val.mean().backward()
+    xr = in0.clone().requires_grad_(True)
+    ref = O.lpips_vgg(sdd, xr, in1, normalize)
+    ref.mean().backward()
+    print(f"lpips fp32x {shape}: value rel {_rel(val, ref):.3e}, pixel gradient rel {_rel(x0.grad, xr.grad):.3e}")
+    assert _rel(val, ref) < 1e-3
+    assert _rel(x0.grad, xr.grad) < TOL
