@@ -392,10 +392,10 @@ def run_cuda(args, rank, local_rank, world):
                                    "synthetic masked clips, random-init weights",
                        "global_batch": B_PER_GPU * world, "parallelism": f"dp{world}",
                        "launch": (("one CUDA graph per step (GraphedTrainingStep)" +
-                                   ((" with the NCCL all-reduces of the 2 gradient buckets captured inside it on a forked "
-                                     "stream (decoder bucket overlapped with the encoder backward)"
+                                   ((" with the NCCL all-reduces of the 3 gradient buckets captured inside it on a forked "
+                                     "stream (decoder and conv4 buckets overlapped with the rest of backward)"
                                      if graphed.allreduce_mode == "captured-overlapped" else
-                                     " + NCCL all-reduce of 2 gradient buckets after each replay") if world > 1 else ""))
+                                     " + NCCL all-reduce of 3 gradient buckets after each replay") if world > 1 else ""))
                                   if graphed is not None else "eager launches, bucketed all-reduce overlapped with backward"),
                        "eager_ms_per_step_with_per_kernel_events": ms_eager / args.steps,
                        "l2": "each step streams ~2.5 GB of activations/gradients (>> 126 MB L2); no explicit flush",

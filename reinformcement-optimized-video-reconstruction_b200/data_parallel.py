@@ -6,11 +6,12 @@ The reference has no distributed code at all (`parallel_and_de
 `.to(device)`, rovr/train_local_net_unet.py:73-75), so this is new work specified by §8e:
 
   * LocalNet's backward produces its gradients decoder-first. `local_net._LocalNetFunction`
-    writes them into two flat fp32 buckets (decoder: conv8..upconv1 = 2 237 507 elements, ready
-    first; encoder: conv4..conv1 = 1 554 432) and calls `_bucket_ready(i, flat)` the moment a
-    bucket is complete. `GradientBuckets` then launches the all-reduce of that bucket on a side
-    stream (NCCL over NVLink/NVSwitch) while the encoder half of backward is still running, and
-    makes the main stream wait for both before autograd accumulates into `.grad`.
+    writes them into three flat fp32 buckets (decoder: conv8..upconv1 = 2 237 507 elements, ready
+    first; conv4 = 1 180 160, ready one kernel later; conv3..conv1 = 374 272) and calls
+    `_bucket_ready(i, flat)` the moment a bucket is complete. `GradientBuckets` then launches the
+    all-reduce of that bucket on a side stream (NCCL over NVLink/NVSwitch) while the rest of
+    backward is still running — only the 1.5 MB tail bucket is exposed at the end — and makes the
+    main stream wait for all of them before autograd accumulates into `.grad`.
   * No other collective exists on the path (no all-gather / all-to-all): frames are independent.
   * Policy nets use train-mode BatchNorm; they are sharded by whole clip so each replica sees
     exactly the per-clip batch of the reference (§8e caveat) and only gradients are reduced.

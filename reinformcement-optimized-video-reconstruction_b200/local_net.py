@@ -41,6 +41,11 @@ _GRAD_ORDER = ["conv8", "conv7", "upconv3", "conv6", "upconv2", "conv5", "upconv
                "conv4", "conv3", "conv2", "conv1"]
 _DECODER = _GRAD_ORDER[:7]
 _ENCODER = _GRAD_ORDER[7:]
+# all-reduce buckets, in the order their gradients become final: the decoder (8.95 MB, ready after upconv1's
+# weight gradient), conv4 alone (4.72 MB, ready one kernel later) and the thin rest of the encoder (1.50 MB): only
+# the last, smallest bucket's all-reduce is exposed at the end of the step (round 1 had two buckets and the whole
+# 6.2 MB encoder one at the end)
+_BUCKETS = [_DECODER, ["conv4"], ["conv3", "conv2", "conv1"]]
 
 
 class _PackedWeights:
@@ -143,9 +148,8 @@ def _forward_impl(net, x, context, target, P, with_dgrad):
 
 
 def _backward_impl(net, a, P, target, g_out, g_loss, buckets=None):
-    """The backward launch sequence. Writes every parameter gradient into two flat fp32 buckets
-    (decoder, encoder — `buckets` = (dec_flat, enc_flat, views) to reuse static ones) and returns
-    {parameter name: gradient view}."""
+    """The backward launch sequence. Writes every parameter gradient into three flat fp32 buckets
+    (`_BUCKETS`; `buckets` = ([flat, ...], views) to reuse static ones) and returns {parameter name: gradient view}."""
     dev = a["out"].device
     bf = torch.bfloat16
     pk = net._packed
@@ -157,12 +161,10 @@ def _backward_impl(net, a, P, target, g_out, g_loss, buckets=None):
         return pk.get(name, P[name + ".weight"], kind, True)
 
     if buckets is None:
-        dec_flat, G = _flat_bucket(P, _DECODER, dev)
-        enc_flat, Ge = _flat_bucket(P, _ENCODER, dev)
-        G.update(Ge)
+        flats, G = _make_buckets(P, dev)
     else:
-        dec_flat, enc_flat, G = buckets
-    net._last_buckets = (dec_flat, enc_flat)
+        flats, G = buckets
+    net._last_buckets = tuple(flats)
 
     def el(t):
         return torch.empty_like(t)
@@ -202,9 +204,10 @@ def _backward_impl(net, a, P, target, g_out, g_loss, buckets=None):
     ops.convT2x2_wgrad(gu1, a["x4"], G["upconv1.weight"])
     g4 = el(a["x4"])
     ops.convT2x2_dgrad(gu1, wd("upconv1", "up"), g4, mask=a["x4"], colsum=G["conv4.bias"])
-    net._bucket_ready(0, dec_flat)
+    net._bucket_ready(0, flats[0])
     # ---- conv4 ----
     ops.conv3x3_wgrad(g4, a["p3"], G["conv4.weight"])
+    net._bucket_ready(1, flats[1])
     gp3 = el(a["p3"])
     ops.conv3x3_dgrad(g4, wd("conv4"), gp3)
     g3 = torch.empty((B, H // 4, W // 4, 256), dtype=bf, device=dev)
@@ -226,9 +229,18 @@ def _backward_impl(net, a, P, target, g_out, g_loss, buckets=None):
                     colsum=G["conv1.bias"])
     # ---- conv1 (input needs no gradient: no dgrad, as in the reference's autograd graph) ----
     ops.conv3x3_wgrad(g1, a["in16"], G["conv1.weight"])
-    net._bucket_ready(1, enc_flat)
+    net._bucket_ready(2, flats[2])
     net._buckets_wait()
     return G
+
+
+def _make_buckets(P, dev):
+    flats, G = [], {}
+    for names in _BUCKETS:
+        flat, views = _flat_bucket(P, names, dev)
+        flats.append(flat)
+        G.update(views)
+    return flats, G
 
 
 class _LocalNetFunction(torch.autograd.Function):
@@ -357,9 +369,9 @@ class GraphedTrainingStep:
     default: a training loop's optimizer changes the fp32 masters every step, one launch);
     with False they are packed once before capture — only valid while the weights never change.
 
-    With data_parallel.GradientBuckets installed the two NCCL all-reduces are captured INSIDE the
-    graph on a forked stream: the decoder bucket is reduced while the encoder half of backward is
-    still running, the encoder bucket at the end (`allreduce_mode == "captured-overlapped"`). If the
+    With data_parallel.GradientBuckets installed the three NCCL all-reduces are captured INSIDE the
+    graph on a forked stream: the decoder and conv4 buckets are reduced while the rest of backward is
+    still running, only the 1.5 MB tail bucket at the end (`allreduce_mode == "captured-overlapped"`). If the
     collective cannot be captured (backend without graph support) the buckets are all-reduced right
     after each replay instead (`"after-replay"`).
     """
@@ -377,10 +389,8 @@ class GraphedTrainingStep:
         named = dict(net.named_parameters())
         self.P = {n: named[n] for n in net._live_names}
         Pd = {n: p.detach() for n, p in self.P.items()}
-        dec_flat, G = _flat_bucket(Pd, _DECODER, dev)
-        enc_flat, Ge = _flat_bucket(Pd, _ENCODER, dev)
-        G.update(Ge)
-        self.buckets = (dec_flat, enc_flat)
+        flats, G = _make_buckets(Pd, dev)
+        self.buckets = tuple(flats)
         self.grad_views = G
         self._g_loss = torch.ones((), dtype=torch.float32, device=dev)        # d total / d mse  (= gamma)
         self._g_lpips = torch.zeros(x.shape[0], dtype=torch.float32, device=dev)  # d total / d lpips[n] (= (1-gamma)/N)
@@ -401,7 +411,7 @@ class GraphedTrainingStep:
                 bwd = lpips_vgg._backward_impl_f32 if f32 else lpips_vgg._backward_impl
                 self.lpips, saved = fwd(lpips_fn, y, self.target, normalize, True)
                 g_out = bwd(lpips_fn, saved, self._g_lpips)
-            _backward_impl(net, acts, Pd, self.target, g_out, self._g_loss, buckets=(dec_flat, enc_flat, G))
+            _backward_impl(net, acts, Pd, self.target, g_out, self._g_loss, buckets=(flats, G))
             return y, loss
 
         import _native
@@ -479,6 +489,6 @@ class GraphedTrainingStep:
         self._load(self.target, target)
         self.graph.replay()
         if self._reduce_after is not None:
-            self._reduce_after(self.buckets)                      # NCCL all-reduce (AVG) of the two buckets
+            self._reduce_after(self.buckets)                      # NCCL all-reduce (AVG) of the buckets
         self._bind_grads()      # the reference loop's zero_grad() sets .grad to None: re-attach the static views
         return self.loss

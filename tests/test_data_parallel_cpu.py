@@ -41,7 +41,7 @@ def _worker(rank, world, port, q):
     dec.fill_(float(rank + 1))
     enc.copy_(torch.arange(enc.numel(), dtype=torch.float32) * (rank + 1))
     net._bucket_ready(0, dec)   # decoder bucket is complete first
-    net._bucket_ready(1, enc)
+    net._bucket_ready(2, enc)
     net._buckets_wait()
     mean_scale = sum(r + 1 for r in range(world)) / world
     ok_dec = torch.allclose(dec, torch.full_like(dec, mean_scale))
@@ -54,7 +54,11 @@ def _worker(rank, world, port, q):
     net._grad_bucket_reduce((dec, enc))
     ok_dec = ok_dec and torch.allclose(dec, torch.full_like(dec, mean_scale))
     ok_enc = ok_enc and torch.allclose(enc, torch.full_like(enc, 2.0 * mean_scale))
+    from local_net import _BUCKETS, _make_buckets
+    flats, views = _make_buckets(P, torch.device("cpu"))
+    sizes = [f.numel() for f in flats]
     lo, hi = shard_range(50, rank, world)
+    assert sizes == [2237507, 512 * 256 * 9 + 512, 1554432 - (512 * 256 * 9 + 512)] and len(views) == 22, sizes
     q.put((rank, same_after_broadcast, ok_dec, ok_enc, ok_view, dec.numel(), enc.numel(), gb.launched, lo, hi))
     dist.destroy_process_group()
 

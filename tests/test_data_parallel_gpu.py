@@ -121,7 +121,7 @@ def test_two_gpu_gradients_equal_single_gpu():
         assert p.exitcode == 0, "a rank did not exit cleanly (process-group teardown hung?)"
     for r in res:
         assert r["same_truth"], "broadcast_parameters left the replicas different (stale bf16 operand cache?)"
-        assert r["eager_launched"] == 2
+        assert r["eager_launched"] == 3
         assert r["loss_rel"] < 1e-5
         # identical per-frame arithmetic; only the split-K / cross-rank summation order differs
         assert r["eager"] < 1e-4, r
