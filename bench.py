@@ -513,6 +513,7 @@ def build_workload(name, dev, rank, world, args):
             out = net(enc, flat, target, extra=True)
             loss = sum(bce(out, pos_t[i]) * 1.5 for i in range(pos_t.shape[0])) - sum(bce(out, neg_t[i]) for i in range(neg_t.shape[0]))
             loss.backward()
+            reduce_()                                    # N > 1: the gradient all-reduces are captured in the graph
             return loss.detach()
         gstep = GraphedFunction(fn, (enc_h.to(dev), flat_h.to(dev)), modules=[net])
         clips = max(1, args.clips)
@@ -520,17 +521,14 @@ def build_workload(name, dev, rank, world, args):
         def step():
             for _ in range(clips):                       # clips are independent optimizer steps in the reference
                 gstep(None, None)
-                reduce_()
 
         def e2e(n):
             rb = ScalarReadback(dev, lag=1)
             for encd, flatd in DeviceFeeder(((enc_h, flat_h) for _ in range(n * clips)), dev):
-                loss = gstep(encd, flatd)
-                reduce_()
-                rb.exchange(loss)
+                rb.exchange(gstep(encd, flatd))
             rb.drain()
         return dict(step=step, e2e=e2e, units=b * clips, gflop_per_unit=0.503, h2d=(enc_h.numel() + flat_h.numel()) * 4 * clips,
-                    d2h=4 * clips, close=lambda: None, launches=gstep.launches * clips,
+                    d2h=4 * clips, close=gstep.close, launches=gstep.launches * clips,
                     config={"workload": f"imitation-learning step of rovr/imitation_learning.py:83-100 on PolicyNetwork2UNet: "
                                         f"{clips} clip(s) per GPU per step, each clip = 20 samples of [1,160,160] + [1024] "
                                         "(one forward + BCE loss + backward per clip, per-clip BatchNorm statistics as in the "
@@ -550,22 +548,20 @@ def build_workload(name, dev, rank, world, args):
         def fn(img, ctx):
             lp = net.logprob(img, ctx, act)
             lp.sum().backward()
+            reduce_()
             return lp.detach().sum()
         gstep = GraphedFunction(fn, (img_h.to(dev), ctx_h.to(dev)), modules=[net])
 
         def step():
             gstep(None, None)
-            reduce_()
 
         def e2e(n):
             rb = ScalarReadback(dev, lag=1)
             for i_d, c_d in DeviceFeeder(((img_h, ctx_h) for _ in range(n)), dev):
-                v = gstep(i_d, c_d)
-                reduce_()
-                rb.exchange(v)
+                rb.exchange(gstep(i_d, c_d))
             rb.drain()
         return dict(step=step, e2e=e2e, units=b, gflop_per_unit=2.960, h2d=(img_h.numel() + ctx_h.numel()) * 4, d2h=4,
-                    close=lambda: None, launches=gstep.launches,
+                    close=gstep.close, launches=gstep.launches,
                     config={"workload": "PolicyNetwork1UNet.logprob forward + backward, b=25 mosaics of 80x80 (rovr/rovr.py:312 "
                                         "shape), emulated-fp32 trunk, one CUDA graph replay per step",
                             "precision": net.trunk_precision})
@@ -587,21 +583,19 @@ def build_workload(name, dev, rank, world, args):
             out = net(fr)
             loss = (out ** 2).sum()
             loss.backward()
+            reduce_()
             return loss.detach()
         gstep = GraphedFunction(fn, (fr_h.to(dev),), modules=[net])
 
         def step():
             gstep(None)
-            reduce_()
 
         def e2e(n):
             rb = ScalarReadback(dev, lag=1)
             for (fd,) in DeviceFeeder(((fr_h,) for _ in range(n)), dev):
-                v = gstep(fd)
-                reduce_()
-                rb.exchange(v)
+                rb.exchange(gstep(fd))
             rb.drain()
-        return dict(step=step, e2e=e2e, units=25, gflop_per_unit=8.174, h2d=fr_h.numel() * 4, d2h=4, close=lambda: None,
+        return dict(step=step, e2e=e2e, units=25, gflop_per_unit=8.174, h2d=fr_h.numel() * 4, d2h=4, close=gstep.close,
                     launches=gstep.launches,
                     config={"workload": "ResnetFeatureExtractor forward of one clip (25 frames, 224x224; frozen eval-mode ResNet-50 "
                                         "trunk as with pretrained=True) + Linear(2048,768) forward/backward + mosaic paste"})
@@ -618,22 +612,20 @@ def build_workload(name, dev, rank, world, args):
             out = net(xx)
             loss = (out ** 2).mean()
             loss.backward()
+            reduce_()
             return loss.detach()
         gstep = GraphedFunction(fn, (x_h.to(dev).requires_grad_(True),), modules=[net])
 
         def step():
             gstep(None)
-            reduce_()
 
         def e2e(n):
             rb = ScalarReadback(dev, lag=1)
             for (xd,) in DeviceFeeder(((x_h,) for _ in range(n)), dev):
-                v = gstep(xd)
-                reduce_()
-                rb.exchange(v)
+                rb.exchange(gstep(xd))
             rb.drain()
         return dict(step=step, e2e=e2e, units=Bq, gflop_per_unit=3 * (20.13 + 2.42), h2d=x_h.numel() * 4, d2h=4,
-                    close=lambda: None, launches=gstep.launches,
+                    close=gstep.close, launches=gstep.launches,
                     config={"workload": "EncoderBlock(hidden 3072, 8 heads) forward + backward on B=24 sequences of 256 tokens "
                                         "(rovr/common_layers.py:94-104 at the token shape of :8-9)"})
     if name == "rovr_step":

@@ -12,6 +12,8 @@ and replays it with new inputs copied into the captured buffers.
 
 `modules` have their gradients reset (set_to_none) right before the capture, so the captured backward
 ASSIGNS fresh gradient tensors instead of accumulating into the ones the warm-up left behind.
+`fn` may end with `data_parallel.GradientAverager.average()`: the NCCL all-reduces are then captured
+inside the graph (no per-step launch latency); call `close()` before destroying the process group.
 
 Outputs returned by `fn` are static tensors overwritten by every replay (clone to keep them).
 """
@@ -42,6 +44,14 @@ class GraphedFunction:
         with torch.cuda.graph(self.graph):
             self.outputs = fn(*self.inputs)
         self.launches = int(_native.lib.rovr_launch_count() - n0)
+
+    def close(self):
+        """Destroy the captured graph (required before `dist.destroy_process_group()` if `fn` issued collectives:
+        NCCL does not tear a communicator down while a graph that captured its collectives is alive)."""
+        if getattr(self, "graph", None) is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
 
     def __call__(self, *inputs):
         for dst, src in zip(self.inputs, inputs):

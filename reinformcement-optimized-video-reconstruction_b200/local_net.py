@@ -16,6 +16,8 @@ skip-gradient add and ReLU mask) is one autograd.Function. Inputs / outputs at t
 boundary stay NCHW fp32 like the reference; internals are NHWC bf16 with fp32 accumulation and
 fp32 master weights. There is no fallback path: a CPU tensor or a non-sm_100 device raises.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -46,6 +48,8 @@ _ENCODER = _GRAD_ORDER[7:]
 # the last, smallest bucket's all-reduce is exposed at the end of the step (round 1 had two buckets and the whole
 # 6.2 MB encoder one at the end)
 _BUCKETS = [_DECODER, ["conv4"], ["conv3", "conv2", "conv1"]]
+if os.environ.get("ROVR_DP_BUCKETS") == "2":      # A/B switch: the round-1 layout (decoder, whole encoder)
+    _BUCKETS = [_DECODER, _ENCODER]
 
 
 class _PackedWeights:
@@ -207,7 +211,8 @@ def _backward_impl(net, a, P, target, g_out, g_loss, buckets=None):
     net._bucket_ready(0, flats[0])
     # ---- conv4 ----
     ops.conv3x3_wgrad(g4, a["p3"], G["conv4.weight"])
-    net._bucket_ready(1, flats[1])
+    if len(flats) == 3:
+        net._bucket_ready(1, flats[1])
     gp3 = el(a["p3"])
     ops.conv3x3_dgrad(g4, wd("conv4"), gp3)
     g3 = torch.empty((B, H // 4, W // 4, 256), dtype=bf, device=dev)
@@ -229,7 +234,7 @@ def _backward_impl(net, a, P, target, g_out, g_loss, buckets=None):
                     colsum=G["conv1.bias"])
     # ---- conv1 (input needs no gradient: no dgrad, as in the reference's autograd graph) ----
     ops.conv3x3_wgrad(g1, a["in16"], G["conv1.weight"])
-    net._bucket_ready(2, flats[2])
+    net._bucket_ready(len(flats) - 1, flats[-1])
     net._buckets_wait()
     return G
 
