@@ -383,7 +383,8 @@ def run_cuda(args, rank, local_rank, world):
                 "avg_launch_ms": ig_avg_s * 1e3, "flops_per_launch": ig_flops_per_launch,
                 "peak_source": peaks["source"]}
     total_flops_per_frame = 2.0 * (macs["igemm"] + macs["wgrad"] + macs["tail"])
-    cpu_base = None if args.profile_run else cpu_step_rate(steps=2, warmup=1, budget_s=25.0)[0]
+    # the oracle port on this box's host cores at the stated B = 24 (about 2.5 s per step on 16 threads): 1 warm-up + 3 steps
+    cpu_base = None if args.profile_run else cpu_step_rate(steps=3, warmup=1, sample_b=B_PER_GPU, budget_s=30.0)[0]
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,

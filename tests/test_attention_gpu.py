@@ -201,3 +201,36 @@ def test_encoder_block_realistic_shape_vs_oracle():
         r = _rel(p.grad, leaf[n].grad)
         print(f"encoder768: grad {n:45s} l2-rel {r:.3e}")
         assert r < 2e-2, n
+
+
+def test_encoder_decoder_at_surveyed_width_3072():
+    """The token shape the reference's comments give (rovr/common_layers.py:8-9,28-29): E = 3072, 256 image tokens,
+    128 context tokens; EncoderBlock and DecoderBlock forward + every gradient vs the oracle, which is evaluated by
+    PyTorch fp32 on the GPU (TF32 off, tests/conftest.py) because 28 M parameters x 256 tokens are slow on the host."""
+    import common_layers as CL
+    dev = _dev()
+    E, heads, S, T, B = 3072, 8, 256, 128, 2
+    g = torch.Generator().manual_seed(90)
+    x = torch.randn((B, S, E), generator=g)
+    enc = torch.randn((B, T, E), generator=g)
+    for kind in ("encoder", "decoder"):
+        m = CL.EncoderBlock(E, heads, 0.0) if kind == "encoder" else CL.DecoderBlock(E, heads, 0.0)
+        sd = _block_state_dict(m, 91)
+        m.load_state_dict(sd, strict=True)
+        m = m.to(dev).eval()
+        xd, ed = x.to(dev).requires_grad_(True), enc.to(dev).requires_grad_(True)
+        y = m(xd) if kind == "encoder" else m(xd, ed)
+        (y ** 2).mean().backward()
+        leaf = {k: v.to(dev).clone().requires_grad_(True) for k, v in sd.items()}
+        xr, er = x.to(dev).requires_grad_(True), enc.to(dev).requires_grad_(True)
+        yr = O.encoder_block(leaf, "", xr, heads) if kind == "encoder" else O.decoder_block(leaf, "", xr, er, heads)
+        (yr ** 2).mean().backward()
+        worst = max(_rel(p.grad, leaf[n].grad) for n, p in m.named_parameters())
+        print(f"{kind}3072: y {_rel(y, yr):.3e} gx {_rel(xd.grad, xr.grad):.3e} worst param grad {worst:.3e}")
+        assert _rel(y, yr) < 2e-2 and _rel(xd.grad, xr.grad) < 2e-2
+        if kind == "decoder":
+            assert _rel(ed.grad, er.grad) < 2e-2
+        for n, p in m.named_parameters():
+            assert _rel(p.grad, leaf[n].grad) < 2e-2, (kind, n, _rel(p.grad, leaf[n].grad))
+        del m, leaf
+        torch.cuda.empty_cache()
