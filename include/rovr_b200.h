@@ -367,6 +367,11 @@ int rovr_split_weights(const float* w, float* out, int d0, int d1, int inner, in
 /* weight gradient of a stacked product: dwp fp32 [2*cb0][2*cb1][inner] -> dw[i][j][t] = sum of its four
  * blocks (i < d0, j < d1) */
 int rovr_blocksum4(const float* dwp, float* dw, int d0, int d1, int inner, int cb0, int cb1, void* stream);
+/* Conv2d 3x3, padding 1, stride 2 (torchvision ResNet-50 layer{2,3,4}.0.conv2, rovr/resnet_extractor.py:8,16): x is
+ * [B][H][W][Cin], y is [B][(H-1)/2+1][(W-1)/2+1][Cout]; the operand map samples every other input pixel (TMA element
+ * strides), so nothing is computed at the discarded positions. */
+int rovr_conv3x3_fprop_s2(const void* x, int x_ld, const void* wk, const float* bias, void* y, int y_ld, int B, int H,
+                          int W, int Cin, int Cout, int relu, void* stream);
 /* Conv2d 3x3 pad 1 with fp32 NHWC output (forward; or, with the rovr_repack_conv3x3_dgrad operand and
  * Cin / Cout swapped by the caller, the data gradient) */
 int rovr_conv3x3_f32out(const void* x, int x_ld, const void* wk, const float* bias, float* y, int y_ld,

@@ -111,6 +111,7 @@ SIGNATURES = {
     "rovr_split_stack": (_i, [_p, _p, _i, _p, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p]),
     "rovr_split_weights": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "rovr_blocksum4": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "rovr_conv3x3_fprop_s2": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "rovr_conv3x3_f32out": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "rovr_convT2x2_fprop_f32out": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "rovr_convT2x2_dgrad_f32out": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p]),

@@ -75,6 +75,8 @@ struct IgemmParams {
   long long ostride[4];   // output element stride per dim (direct fp32 epilogue only)
   int ntaps;
   int tap_off[IG_MAX_TAPS][4];
+  int a_mul[4];           // A-operand coordinate of a tile = org[j] * a_mul[j] + tap_off[t][j] (2 for the pixel dims of a
+                          // stride-2 convolution, whose A map samples every other input pixel; 1 otherwise)
   int cin;                // K extent per tap (multiple of bk)
   int bk;                 // K elements per sub-tile: 16 / 32 / 64  (swizzle 32/64/128 B)
   int tps;                // (tap, k-chunk) sub-tiles per pipeline stage
@@ -354,8 +356,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const int kc = it - t * kchunks;
             uint8_t* a_dst = st + static_cast<size_t>(u) * sub_bytes;
             if (elect_one_sync()) {
-              load_a5(&full_bar[s], a_dst, kc * p.bk, org[0] + p.tap_off[t][0], org[1] + p.tap_off[t][1],
-                      org[2] + p.tap_off[t][2], org[3] + p.tap_off[t][3]);
+              load_a5(&full_bar[s], a_dst, kc * p.bk, org[0] * p.a_mul[0] + p.tap_off[t][0],
+                      org[1] * p.a_mul[1] + p.tap_off[t][1], org[2] * p.a_mul[2] + p.tap_off[t][2],
+                      org[3] * p.a_mul[3] + p.tap_off[t][3]);
               if (p.b_batched)   // (never combined with a pair launch)
                 tma_load_5d(&tmB, &full_bar[s], a_dst + a_bytes, t * p.cin + kc * p.bk, nt * p.n_tile, org[1],
                             org[2], org[3]);

@@ -165,12 +165,17 @@ static CUtensorMapSwizzle swizzle_for(int sw_bytes) {
 }
 // rank-5 bf16 map: dims[0] is the contiguous (channel) dim; strides_elems[i] is the stride of
 // dim i+1 in elements.
+// elem_strides (optional): traversal stride per dim — the box then covers box[i] global elements and delivers
+// every elem_strides[i]-th of them (a stride-2 convolution reads every other input pixel this way).
 static int make_map5(CUtensorMap* m, const void* base, const long long dims[5],
-                     const long long strides_elems[4], const int box[5], int sw_bytes) {
+                     const long long strides_elems[4], const int box[5], int sw_bytes,
+                     const int* elem_strides = nullptr) {
   cuuint64_t gd[5];
   cuuint64_t gs[4];
   cuuint32_t bx[5];
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  if (elem_strides != nullptr)
+    for (int i = 0; i < 5; ++i) es[i] = static_cast<cuuint32_t>(elem_strides[i]);
   for (int i = 0; i < 5; ++i) {
     gd[i] = static_cast<cuuint64_t>(dims[i]);
     bx[i] = static_cast<cuuint32_t>(box[i]);

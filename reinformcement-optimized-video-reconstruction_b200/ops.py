@@ -240,6 +240,17 @@ def conv3x3_fprop(x, wk, bias, y, relu=True, pooled=None):
     return y
 
 
+def conv3x3_fprop_s2(x, wk, bias, y, relu=True):
+    """3x3, padding 1, stride 2: y [B, (H-1)//2+1, (W-1)//2+1, Cout] = [relu](conv(x) + bias)."""
+    B, H, W, Cin, x_ld = _act(x, "x")
+    By, Hy, Wy, Cout, y_ld = _act(y, "y")
+    assert (By, Hy, Wy) == (B, (H - 1) // 2 + 1, (W - 1) // 2 + 1) and wk.shape == (Cout, 9 * Cin), (x.shape, y.shape, wk.shape)
+    _f32(bias, "bias")
+    _launch("rovr_conv3x3_fprop_s2", _ptr(x), x_ld, _ptr(wk), _ptr(bias), _ptr(y), y_ld, B, H, W, Cin, Cout, int(relu),
+            _stream())
+    return y
+
+
 def conv3x3_fprop_tail(x, wk, bias, y, w8, b8, target=None):
     """y = relu(conv3x3(x) + bias) (Cout = 64) and, from the same epilogue, out = sigmoid(conv8_1x1(y))
     (NCHW fp32) [+ mean((out - target)^2)]. Returns (out, loss | None)."""

@@ -111,11 +111,11 @@ class ResnetFeatureExtractor(torch.nn.Module):
     def _c3(self, x, conv, bn, relu):
         B, H, W, C = x.shape
         wk, bias = self._conv_bn(conv, bn, "c3")
+        if conv.stride[0] == 2:     # native stride 2: the TMA operand map samples every other input pixel
+            y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, conv.out_channels), dtype=BF, device=x.device)
+            return ops.conv3x3_fprop_s2(x, wk, bias, y, relu=relu)
         y = torch.empty((B, H, W, conv.out_channels), dtype=BF, device=x.device)
-        ops.conv3x3_fprop(x, wk, bias, y, relu=relu)
-        if conv.stride[0] > 1:      # stride-2 3x3 pad-1 = the stride-1 result sampled at even positions
-            y = ops.subsample(y, conv.stride[0])
-        return y
+        return ops.conv3x3_fprop(x, wk, bias, y, relu=relu)
 
     def _trunk(self, frames):
         """frames: NCHW fp32 [n,3,224,224] already ToTensor-quantised -> pooled features [n,2048] fp32."""

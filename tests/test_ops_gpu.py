@@ -437,3 +437,26 @@ def test_corrupt_frames_matches_dataset_logic():
             ref, m = corrupt_frame(clean[n].permute(1, 2, 0).numpy(), n)
             assert np.array_equal(out[n].permute(1, 2, 0).cpu().numpy(), ref), (H, W, n)
             assert np.array_equal(mask[n].permute(1, 2, 0).cpu().numpy(), m)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 56, 56, 128, 128), (3, 28, 28, 256, 256), (5, 14, 14, 512, 512), (1, 15, 9, 64, 32),
+                                            (2, 6, 6, 32, 64)])
+def test_conv3x3_stride2(B, H, W, Cin, Cout):
+    """3x3 / padding 1 / stride 2 (ResNet-50's down-sampling convolutions) through TMA element strides, vs F.conv2d
+    on the same bf16-rounded operands — and identical to the stride-1 kernel sampled at the even positions."""
+    import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 31 + H + Cin + Cout)
+    x = _rand_act((B, H, W, Cin), g, dev)
+    w = (torch.randn((Cout, Cin, 3, 3), generator=g) * (1.0 / (3 * Cin ** 0.5))).to(dev)
+    b = torch.randn((Cout,), generator=g).to(dev) * 0.1
+    wk = ops.repack_conv3x3(w)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.full((B, Ho, Wo, Cout), 9.0, dtype=BF, device=dev)
+    ops.conv3x3_fprop_s2(x, wk, b, y, relu=True)
+    ref = F.relu(F.conv2d(_nchw(x.float()), w.to(BF).float(), b, stride=2, padding=1))
+    assert ref.shape == (B, Cout, Ho, Wo)
+    _report("conv3x3_s2", _nchw(y), ref, 1e-2)
+    y1 = torch.empty((B, H, W, Cout), dtype=BF, device=dev)
+    ops.conv3x3_fprop(x, wk, b, y1, relu=True)
+    assert torch.equal(y, y1[:, ::2, ::2].contiguous()), "stride-2 kernel differs from the sub-sampled stride-1 kernel"
