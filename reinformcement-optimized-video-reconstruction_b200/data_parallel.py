@@ -117,19 +117,24 @@ class GradientAverager:
     def average(self):
         if self.world == 1:
             return
-        shared, loose = {}, []
+        groups, loose = {}, []
         for p in self.module.parameters():
             g = p.grad
             if g is None:
                 continue
             st = g.untyped_storage()
-            if st.nbytes() > g.numel() * g.element_size() and g.dtype == torch.float32:
-                shared.setdefault(st.data_ptr(), (st, g))
+            if st.nbytes() > g.numel() * g.element_size() and g.dtype == torch.float32 and g.is_contiguous():
+                groups.setdefault(st.data_ptr(), [st, []])[1].append(g)
             else:
                 loose.append(g)
-        for st, g in shared.values():          # a whole arena: one collective, in place
-            flat = torch.empty(0, dtype=torch.float32, device=g.device).set_(st)
-            self._allreduce(flat)
+        for st, grads in groups.values():
+            # an arena = a storage that these gradients tile completely (nothing else lives in it): one collective
+            # over the whole storage, in place. Anything else (a gradient that is a view of some larger tensor)
+            # goes the flatten / copy-back way so that no foreign data is ever averaged.
+            if sum(g.numel() * 4 for g in grads) == st.nbytes():
+                self._allreduce(torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(st))
+            else:
+                loose.extend(grads)
         if loose:
             flat = torch.cat([g.reshape(-1) for g in loose])
             self._allreduce(flat)

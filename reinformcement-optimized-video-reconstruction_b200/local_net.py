@@ -366,7 +366,7 @@ class GraphedTrainingStep:
             optimizer.step()                         # net.<param>.grad are this step's gradients
 
     The launch sequence is captured WITHOUT the autograd engine (`_forward_impl` / `_backward_impl`
-    called directly): every gradient is written into two static flat fp32 buckets and each replay
+    called directly): every gradient is written into three static flat fp32 buckets and each replay
     re-binds `param.grad` to its view of them, so the step survives `zero_grad(set_to_none=True)`
     (which drops `.grad`) and the gradients provably alias the buckets that are all-reduced.
 
@@ -489,6 +489,8 @@ class GraphedTrainingStep:
             dst.copy_(src, non_blocking=True)
 
     def __call__(self, x=None, context=None, target=None):
+        if self.graph is None:
+            raise RuntimeError("GraphedTrainingStep.close() has been called")
         self._load(self.x, x)
         self._load(self.context, context)
         self._load(self.target, target)
