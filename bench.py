@@ -261,7 +261,9 @@ def run_cuda(args, rank, local_rank, world):
     graphed = None
     if not args.no_graph:
         from local_net import GraphedTrainingStep
-        graphed = GraphedTrainingStep(net, x, c, t)
+        # two sets of static inputs / outputs (the step captured twice): the feeder lands batch i+1 in the other set
+        # while batch i is computed, so no staging kernel sits between two replays on the compute stream
+        graphed = GraphedTrainingStep(net, x, c, t, input_sets=2)
         for _ in range(3):
             graphed()
         for _ in range(2):      # torch.cuda.graph() empties the allocator cache: refill it before timing eager steps
@@ -306,18 +308,20 @@ def run_cuda(args, rank, local_rank, world):
         e2e_graph = None
         if graphed is not None:
             def e2e_graph_loop(steps):
-                rb = ScalarReadback(dev, lag=1)
-                # uint8 frames land in double-buffered device staging; the step converts them (ToTensor) straight
-                # into the graph's static fp32 inputs
-                for xd, cd, td in DeviceFeeder(((xh, ch, th) for _ in range(steps)), dev, to_float=False):
-                    rb.exchange(graphed(xd, cd, td))
+                # uint8 frames: H2D + ToTensor (uint8 -> fp32 / 255) on the feeder's stream, straight into the static
+                # inputs of the graph set that consumes them; the loss of every step is read back on a side stream
+                rb = ScalarReadback(dev, lag=1, side_stream=True)
+                feed = DeviceFeeder(((xh, ch, th) for _ in range(steps)), dev, slots=graphed.input_slots)
+                for k, _ in enumerate(feed):
+                    rb.exchange(graphed.replay(k % 2))
                 return rb.drain()
             e2e_graph_loop(2)
             ms_g = timed(lambda: e2e_graph_loop(args.steps), 1)
             e2e_graph = {"value": frames / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g / args.steps,
-                         "api": "step = GraphedTrainingStep(net, ...); rb = ScalarReadback(lag=1); for batch in "
-                                "DeviceFeeder(pinned_host_uint8_batches): rb.exchange(step(*batch))  # host uint8 frames (as decoded) "
-                                "copied H2D every step and converted to fp32/255 on the GPU (ToTensor), all 19 weight tensors re-packed to bf16 inside the graph every step (as after an "
+                         "api": "step = GraphedTrainingStep(net, ..., input_sets=2); rb = ScalarReadback(lag=1, side_stream=True); "
+                                "for k, _ in enumerate(DeviceFeeder(pinned_host_uint8_batches, slots=step.input_slots)): "
+                                "rb.exchange(step.replay(k % 2))  # host uint8 frames (as decoded) "
+                                "copied H2D every step and converted to fp32/255 on the GPU (ToTensor) into the static inputs, all 19 weight tensors re-packed to bf16 inside the graph every step (as after an "
                                 "optimizer update), every step's loss read back on the host"}
 
     if rank != 0:

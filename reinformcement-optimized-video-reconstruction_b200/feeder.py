@@ -13,8 +13,11 @@ import torch
 
 
 class DeviceFeeder:
-    def __init__(self, batches, device, depth=2, to_float=True):
+    def __init__(self, batches, device, depth=2, to_float=True, slots=None):
         """batches: iterable of tuples of equally-shaped host tensors (pinned memory recommended).
+        slots (optional): `depth` tuples of pre-allocated device tensors to land the batches in instead of the
+        feeder's own buffers — e.g. `GraphedTrainingStep(..., input_sets=2).input_slots`, so that a batch arrives
+        directly in the static inputs of the graph that will consume it.
         uint8 tensors (frames as decoded by cv2, rovr/video_ds.py:107-114) are shipped as uint8 — a quarter
         of the fp32 bytes — and converted to fp32 / 255 on the device (torchvision's ToTensor) by a kernel
         behind the copy on the feeder's stream, unless to_float=False."""
@@ -24,7 +27,8 @@ class DeviceFeeder:
         self.to_float = to_float
         self.staging = [None] * depth     # uint8 landing buffers of the slots that convert
         self.stream = torch.cuda.Stream(device=device)
-        self.slots = [None] * depth       # static device buffers
+        self.slots = [None] * depth if slots is None else [tuple(sl) for sl in slots]      # static device buffers
+        assert len(self.slots) == depth
         self.count = 0
         self._next = None
         self._preload()
@@ -41,6 +45,7 @@ class DeviceFeeder:
         if self.slots[k] is None:
             self.slots[k] = tuple(torch.empty(t.shape, dtype=torch.float32 if c else t.dtype, device=self.device)
                                   for t, c in zip(host, conv))
+        if self.staging[k] is None:
             self.staging[k] = tuple(torch.empty(t.shape, dtype=torch.uint8, device=self.device) if c else None
                                     for t, c in zip(host, conv))
         # slot k was last read by the step issued `depth` batches ago, whose kernels are already
@@ -80,10 +85,16 @@ class ScalarReadback:
     already queued. Every step's value is still read, in order.
     """
 
-    def __init__(self, device, lag=1):
+    def __init__(self, device, lag=1, side_stream=False):
+        """side_stream=True issues the 4-byte copies on a stream of their own (behind an event of the producing
+        stream) so that nothing sits between two graph replays on the compute stream. Only valid if the scalar
+        stays untouched until it has been read — e.g. the per-set loss of GraphedTrainingStep(input_sets=2) with
+        lag <= 1; a scalar that the very next step overwrites needs the default (same-stream) copy."""
         self.host = torch.empty(lag + 1, dtype=torch.float32).pin_memory()
         self.events = [torch.cuda.Event() for _ in range(lag + 1)]
         self.device = device
+        self.side = torch.cuda.Stream(device=device) if side_stream else None
+        self.ready = [torch.cuda.Event() for _ in range(lag + 1)]
         self.head = 0      # next slot to write
         self.tail = 0      # oldest unread slot
         self.lag = lag
@@ -94,8 +105,15 @@ class ScalarReadback:
     def push(self, scalar):
         assert len(self) <= self.lag, "pop() before pushing more than lag + 1 values"
         k = self.head % (self.lag + 1)
-        self.host[k:k + 1].copy_(scalar.detach().reshape(1), non_blocking=True)
-        self.events[k].record(torch.cuda.current_stream(self.device))
+        if self.side is None:
+            self.host[k:k + 1].copy_(scalar.detach().reshape(1), non_blocking=True)
+            self.events[k].record(torch.cuda.current_stream(self.device))
+        else:
+            self.ready[k].record(torch.cuda.current_stream(self.device))
+            self.side.wait_event(self.ready[k])
+            with torch.cuda.stream(self.side):
+                self.host[k:k + 1].copy_(scalar.detach().reshape(1), non_blocking=True)
+                self.events[k].record(self.side)
         self.head += 1
 
     def pop(self):

@@ -130,3 +130,40 @@ def test_uint8_frames_feed_equals_host_totensor():
     (xu, cu, tu), = list(DeviceFeeder([tuple(u8)], dev, to_float=False))
     assert xu.dtype == torch.uint8
     assert torch.equal(step(xu, cu, tu), want.detach())
+
+
+def test_double_buffered_graph_inputs_and_side_stream_readback():
+    """GraphedTrainingStep(input_sets=2) + DeviceFeeder(slots=...) + ScalarReadback(side_stream=True): six different
+    uint8 batches give, in order, exactly the losses and the final gradients of six eager steps."""
+    import rovr_oracle as O
+    from feeder import DeviceFeeder, ScalarReadback
+    from local_net import GraphedTrainingStep, LocalNetworkUNetNorm
+    dev = torch.device("cuda:0")
+    net = LocalNetworkUNetNorm()
+    net.load_state_dict(O.localnet_state_dict(0), strict=True)
+    net = net.to(dev)
+    host = [tuple((v * 255.0).round().to(torch.uint8).pin_memory() for v in O.synthetic_localnet_batch(2, 64, 64, seed=60 + i))
+            for i in range(6)]
+    want, grads = [], None
+    for xb, cb, tb in host:
+        net.zero_grad(set_to_none=True)
+        _, loss = net.forward_with_mse(*[v.to(dev).float().div(255) for v in (xb, cb, tb)])
+        loss.backward()
+        want.append(float(loss))
+        grads = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    assert len(set(want)) == 6
+    step = GraphedTrainingStep(net, *[v.to(dev).float().div(255) for v in host[0]], input_sets=2)
+    assert len(step.input_slots) == 2 and step.input_slots[0][0].data_ptr() != step.input_slots[1][0].data_ptr()
+    for rep in range(2):                                   # twice: the slots / graphs are reused across loops
+        rb = ScalarReadback(dev, lag=1, side_stream=True)
+        got = []
+        for k, _ in enumerate(DeviceFeeder(iter(host), dev, slots=step.input_slots)):
+            v = rb.exchange(step.replay(k % 2))
+            if v is not None:
+                got.append(v)
+        got.append(rb.drain())
+        assert got == want, (rep, got, want)
+        torch.cuda.synchronize()
+        for n, p in net.named_parameters():
+            if n in grads:
+                assert torch.equal(p.grad, grads[n]), n
