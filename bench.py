@@ -216,7 +216,7 @@ def run_cuda(args, rank, local_rank, world):
     # exactly what ToTensor produces; the e2e legs ship the uint8 frames and convert on the GPU (feeder.DeviceFeeder).
     xf, cf, tf = synthetic_batch_gpu(dev, 1234 + rank)
     xh, ch, th = [(v * 255.0).round().to(torch.uint8).pin_memory() for v in (xf, cf, tf)]
-    x, c, t = [v.to(dev).float().div_(255.0) for v in (xh, ch, th)]      # == rovr_u8_to_f32 (IEEE division)
+    x, c, t = [(v.float() / 255.0).to(dev) for v in (xh, ch, th)]        # host ToTensor == rovr_u8_to_f32 (IEEE division)
 
     def step_resident():
         net.zero_grad(set_to_none=True)
@@ -655,7 +655,7 @@ def build_workload(name, dev, rank, world, args):
         fr, _, tg = masked_frame_batch(K * S_, H, W, seed=99 + rank)
         vid_h = (fr.view(K, S_, 3, H, W) * 255).round().to(torch.uint8).pin_memory()
         org_h = (tg.view(K, S_, 3, H, W) * 255).round().to(torch.uint8).pin_memory()
-        vid, org = vid_h.to(dev).float().div_(255), org_h.to(dev).float().div_(255)
+        vid, org = (vid_h.float() / 255).to(dev), (org_h.float() / 255).to(dev)
         rl = ROVRStep(actor, critic, local, lp, vp, averager=avgs, graphed=not args.no_graph)
 
         def e2e(n):

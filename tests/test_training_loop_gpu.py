@@ -147,12 +147,13 @@ def test_double_buffered_graph_inputs_and_side_stream_readback():
     want, grads = [], None
     for xb, cb, tb in host:
         net.zero_grad(set_to_none=True)
-        _, loss = net.forward_with_mse(*[v.to(dev).float().div(255) for v in (xb, cb, tb)])
+        # host-side ToTensor (IEEE division; torch's CUDA div-by-scalar multiplies by the reciprocal instead)
+        _, loss = net.forward_with_mse(*[(v.float() / 255).to(dev) for v in (xb, cb, tb)])
         loss.backward()
         want.append(float(loss))
         grads = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
     assert len(set(want)) == 6
-    step = GraphedTrainingStep(net, *[v.to(dev).float().div(255) for v in host[0]], input_sets=2)
+    step = GraphedTrainingStep(net, *[(v.float() / 255).to(dev) for v in host[0]], input_sets=2)
     assert len(step.input_slots) == 2 and step.input_slots[0][0].data_ptr() != step.input_slots[1][0].data_ptr()
     for rep in range(2):                                   # twice: the slots / graphs are reused across loops
         rb = ScalarReadback(dev, lag=1, side_stream=True)
