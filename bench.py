@@ -481,18 +481,18 @@ def build_workload(name, dev, rank, world, args):
             broadcast_parameters(lp)
             GradientBuckets(net)
         from synthetic import masked_frame_batch
-        host = [t.pin_memory() for t in masked_frame_batch(B_PER_GPU, H, W, seed=1234 + rank)]
-        x, c, t = [v.to(dev) for v in host]
+        host = [(t * 255.0).round().to(torch.uint8).pin_memory() for t in masked_frame_batch(B_PER_GPU, H, W, seed=1234 + rank)]
+        x, c, t = [(v.float() / 255.0).to(dev) for v in host]      # uint8 frames on the host, ToTensor on the device
         gamma = 0.1 + 0.9 * (0.9993 ** 1000)           # rovr/train_local_net_unet.py:111 at iteration 1000
-        step = GraphedTrainingStep(net, x, c, t, lpips_fn=lp, gamma=gamma)
+        step = GraphedTrainingStep(net, x, c, t, lpips_fn=lp, gamma=gamma, input_sets=2)
 
         def e2e(n):
-            rb = ScalarReadback(dev, lag=1)
-            for xd, cd, td in DeviceFeeder((tuple(host) for _ in range(n)), dev):
-                rb.exchange(step(xd, cd, td))
+            rb = ScalarReadback(dev, lag=1, side_stream=True)
+            for k, _ in enumerate(DeviceFeeder((tuple(host) for _ in range(n)), dev, slots=step.input_slots)):
+                rb.exchange(step.replay(k % 2))
             rb.drain()
         return dict(step=lambda: step(), e2e=e2e, units=B_PER_GPU, gflop_per_unit=119.81 + _vgg_lpips_gflop_per_frame(),
-                    h2d=sum(v.numel() for v in host) * 4, d2h=4, close=step.close, launches=step.launches_per_step,
+                    h2d=sum(v.numel() for v in host), d2h=4, close=step.close, launches=step.launches_per_step,
                     config={"workload": "LocalNet U-Net training step with the reference's full loss (rovr/train_local_net_unet.py:"
                                         "105-115): B=24 frames/GPU, 256x256, gamma*MSE + (1-gamma)*LPIPS-VGG (random-init VGG16, "
                                         "frozen), forward + backward, one CUDA graph per step",
