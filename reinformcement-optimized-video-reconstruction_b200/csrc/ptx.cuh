@@ -48,8 +48,13 @@ __device__ unsigned int g_rovr_hang_code = 0;
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-inline int pdl_mode() {   // ROVR_PDL=0: plain stream-ordered launches (A/B experiments)
-  static const int v = [] { const char* e = getenv("ROVR_PDL"); return e ? atoi(e) : 1; }();
+// ROVR_PDL=1 enables programmatic stream serialisation; the default is plain stream-ordered launches. Round 1 enabled
+// it for the eager path when that was bound by launch latency (3.55 -> 3.40 ms); with today's step (back-to-back
+// persistent kernels that fill every SM, so a dependent grid has nowhere to start early) an alternating A/B on one
+// B200 measured it 1.5-3 % SLOWER for eager launches and graph replays alike (3.17 / 3.19 / 3.17 vs 3.21 / 3.23 /
+// 3.25 ms eager; 3.17 / 3.19 / 3.20 vs 3.31 / 3.23 / 3.27 ms replay; gpurun_out/r2_pdl_ab.log -> profiles/).
+inline int pdl_mode() {
+  static const int v = [] { const char* e = getenv("ROVR_PDL"); return e ? atoi(e) : 0; }();
   return v;
 }
 // Launch `kernel` behind the previous launch of the stream with programmatic stream serialisation, optionally
