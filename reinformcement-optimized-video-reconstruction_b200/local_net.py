@@ -151,6 +151,20 @@ def _forward_impl(net, x, context, target, P, with_dgrad):
     return out, loss, a
 
 
+_SIDE_STREAMS = {}
+
+
+def _wgrad_side_stream(dev):
+    """ROVR_WGRAD_STREAM=1 (experiment): weight-gradient launches (split-K kernel + its reduction) go to a forked stream,
+    so that their reductions and tails may overlap the data-gradient kernels on the main stream."""
+    if os.environ.get("ROVR_WGRAD_STREAM") != "1":
+        return None
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 def _backward_impl(net, a, P, target, g_out, g_loss, buckets=None):
     """The backward launch sequence. Writes every parameter gradient into three flat fp32 buckets
     (`_BUCKETS`; `buckets` = ([flat, ...], views) to reuse static ones) and returns {parameter name: gradient view}."""
@@ -173,6 +187,19 @@ def _backward_impl(net, a, P, target, g_out, g_loss, buckets=None):
     def el(t):
         return torch.empty_like(t)
 
+    side = _wgrad_side_stream(dev)
+
+    def wgrad(fn, *args):
+        if side is None:
+            return fn(*args)
+        side.wait_stream(torch.cuda.current_stream(dev))      # its operands were produced on the main stream
+        with torch.cuda.stream(side):
+            fn(*args)
+
+    def join():
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)
+
     # ---- tail: conv8 + sigmoid (+L2) ----
     g7 = el(a["y7"])
     use_loss = target is not None and g_loss is not None
@@ -181,37 +208,39 @@ def _backward_impl(net, a, P, target, g_out, g_loss, buckets=None):
                  mse_scale=2.0 / a["out"].numel(),
                  gloss=g_loss.contiguous() if use_loss else None, db7=G["conv7.bias"])
     # ---- conv7 (its bias gradient came out of the tail kernel) ----
-    ops.conv3x3_wgrad(g7, a["cat7"], G["conv7.weight"])
+    wgrad(ops.conv3x3_wgrad, g7, a["cat7"], G["conv7.weight"])
     gcat7 = el(a["cat7"])
     # the ReLU mask is only needed on the up-conv half: the skip half (x1) is masked by pool1's backward
     ops.conv3x3_dgrad(g7, wd("conv7"), gcat7, mask=a["cat7"], mask_cols=64, colsum=G["upconv3.bias"])
     # ---- upconv3 ----
     gu3 = gcat7[..., :64]
-    ops.convT2x2_wgrad(gu3, a["y6"], G["upconv3.weight"])
+    wgrad(ops.convT2x2_wgrad, gu3, a["y6"], G["upconv3.weight"])
     g6 = el(a["y6"])
     ops.convT2x2_dgrad(gu3, wd("upconv3", "up"), g6, mask=a["y6"], colsum=G["conv6.bias"])
     # ---- conv6 ----
-    ops.conv3x3_wgrad(g6, a["cat6"], G["conv6.weight"])
+    wgrad(ops.conv3x3_wgrad, g6, a["cat6"], G["conv6.weight"])
     gcat6 = el(a["cat6"])
     ops.conv3x3_dgrad(g6, wd("conv6"), gcat6, mask=a["cat6"], mask_cols=128, colsum=G["upconv2.bias"])
     # ---- upconv2 ----
     gu2 = gcat6[..., :128]
-    ops.convT2x2_wgrad(gu2, a["y5"], G["upconv2.weight"])
+    wgrad(ops.convT2x2_wgrad, gu2, a["y5"], G["upconv2.weight"])
     g5 = el(a["y5"])
     ops.convT2x2_dgrad(gu2, wd("upconv2", "up"), g5, mask=a["y5"], colsum=G["conv5.bias"])
     # ---- conv5 ----
-    ops.conv3x3_wgrad(g5, a["cat5"], G["conv5.weight"])
+    wgrad(ops.conv3x3_wgrad, g5, a["cat5"], G["conv5.weight"])
     gcat5 = el(a["cat5"])
     ops.conv3x3_dgrad(g5, wd("conv5"), gcat5, mask=a["cat5"], mask_cols=256, colsum=G["upconv1.bias"])
     # ---- upconv1 ----
     gu1 = gcat5[..., :256]
-    ops.convT2x2_wgrad(gu1, a["x4"], G["upconv1.weight"])
+    wgrad(ops.convT2x2_wgrad, gu1, a["x4"], G["upconv1.weight"])
     g4 = el(a["x4"])
     ops.convT2x2_dgrad(gu1, wd("upconv1", "up"), g4, mask=a["x4"], colsum=G["conv4.bias"])
+    join()
     net._bucket_ready(0, flats[0])
     # ---- conv4 ----
-    ops.conv3x3_wgrad(g4, a["p3"], G["conv4.weight"])
+    wgrad(ops.conv3x3_wgrad, g4, a["p3"], G["conv4.weight"])
     if len(flats) == 3:
+        join()
         net._bucket_ready(1, flats[1])
     gp3 = el(a["p3"])
     ops.conv3x3_dgrad(g4, wd("conv4"), gp3)
@@ -219,21 +248,22 @@ def _backward_impl(net, a, P, target, g_out, g_loss, buckets=None):
     ops.maxpool_bwd(a["cat5"][..., 256:], gp3, g3, 2, gskip=gcat5[..., 256:], relu_mask=True,
                     colsum=G["conv3.bias"])             # bias gradient from the same pass over g3
     # ---- conv3 ----
-    ops.conv3x3_wgrad(g3, a["p2"], G["conv3.weight"])
+    wgrad(ops.conv3x3_wgrad, g3, a["p2"], G["conv3.weight"])
     gp2 = el(a["p2"])
     ops.conv3x3_dgrad(g3, wd("conv3"), gp2)
     g2 = torch.empty((B, H // 2, W // 2, 128), dtype=bf, device=dev)
     ops.maxpool_bwd(a["cat6"][..., 128:], gp2, g2, 2, gskip=gcat6[..., 128:], relu_mask=True,
                     colsum=G["conv2.bias"])
     # ---- conv2 ----
-    ops.conv3x3_wgrad(g2, a["p1"], G["conv2.weight"])
+    wgrad(ops.conv3x3_wgrad, g2, a["p1"], G["conv2.weight"])
     gp1 = el(a["p1"])
     ops.conv3x3_dgrad(g2, wd("conv2"), gp1)
     g1 = torch.empty((B, H, W, 64), dtype=bf, device=dev)
     ops.maxpool_bwd(a["cat7"][..., 64:], gp1, g1, 2, gskip=gcat7[..., 64:], relu_mask=True,
                     colsum=G["conv1.bias"])
     # ---- conv1 (input needs no gradient: no dgrad, as in the reference's autograd graph) ----
-    ops.conv3x3_wgrad(g1, a["in16"], G["conv1.weight"])
+    wgrad(ops.conv3x3_wgrad, g1, a["in16"], G["conv1.weight"])
+    join()
     net._bucket_ready(len(flats) - 1, flats[-1])
     net._buckets_wait()
     return G
