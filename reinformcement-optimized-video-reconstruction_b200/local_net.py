@@ -155,9 +155,14 @@ _SIDE_STREAMS = {}
 
 
 def _wgrad_side_stream(dev):
-    """ROVR_WGRAD_STREAM=1 (experiment): weight-gradient launches (split-K kernel + its reduction) go to a forked stream,
-    so that their reductions and tails may overlap the data-gradient kernels on the main stream."""
-    if os.environ.get("ROVR_WGRAD_STREAM") != "1":
+    """Weight-gradient launches (split-K kernel + its reduction) go to a forked stream when the step is launched
+    eagerly: a layer's weight gradient and data gradient are independent, and with two hardware queues the tail of one
+    persistent kernel is filled by the CTAs of the other and the small reductions overlap the next tensor-bound
+    kernel. Measured on one B200 (alternating A/B, profiles/r02_wgrad_stream_ab.log): eager step 3.19 -> 3.08 ms, but a
+    CUDA-graph replay of the same fork / join gets 1 % SLOWER (3.19 -> 3.23), so it is not used under stream capture.
+    ROVR_WGRAD_STREAM=0 / 1 forces it off / on everywhere."""
+    mode = os.environ.get("ROVR_WGRAD_STREAM")
+    if mode == "0" or (mode != "1" and torch.cuda.is_current_stream_capturing()):
         return None
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     if key not in _SIDE_STREAMS:
