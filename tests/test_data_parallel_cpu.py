@@ -160,3 +160,21 @@ def test_synthetic_generator_matches_oracle_copy():
     f, c, t = a
     assert f.shape == (3, 3, 64, 48) and c.shape == (3, 2, 3, 64, 48) and t.shape == (3, 3, 64, 48)
     assert float(f.min()) >= 0 and float(f.max()) <= 1 and (f == 0).any()  # the masked box
+
+
+def test_grad_arena_tiles_one_storage():
+    """_blocks.GradArena (host logic): the gradients of a trunk are views that tile ONE flat fp32 storage completely,
+    which is what lets GradientAverager reduce them with a single in-place collective."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                    "reinformcement-optimized-video-reconstruction_b200"))
+    from _blocks import GradArena
+    P = {"a.weight": torch.zeros(4, 3, 3, 3), "a.bias": torch.zeros(4), "b.weight": torch.zeros(2, 4)}
+    arena = GradArena(P)
+    views = [arena.take(P["a.weight"]), arena.take(P["a.bias"], zero=True), arena.take(P["b.weight"])]
+    assert [tuple(v.shape) for v in views] == [(4, 3, 3, 3), (4,), (2, 4)]
+    assert all(v.untyped_storage().data_ptr() == arena.flat.untyped_storage().data_ptr() for v in views)
+    assert sum(v.numel() for v in views) * 4 == arena.flat.untyped_storage().nbytes()
+    assert float(views[1].abs().sum()) == 0.0
+    views[2].fill_(3.0)
+    assert float(arena.flat[-8:].sum()) == 24.0
