@@ -279,11 +279,14 @@ def run_cuda(args, rank, local_rank, world):
     # every step: (1) eager launches through the autograd Function — weight gradients on a forked stream, bucket
     # all-reduces overlapped with backward; (2) ONE CUDA-graph replay per step. `value` is the faster of the two
     # (named in config.launch); both are kept in config.launch_modes_ms_per_step.
+    # (at N > 1 only the graph mode is timed when available: measured at N = 2, the eager mode is host-bound there —
+    # 3.81 vs 3.28 ms — because every rank also enqueues three NCCL collectives per step from Python)
     n1 = _native.lib.rovr_launch_count()
-    ms_eager_plain = timed(lambda: step_resident(repack=True), args.steps)
+    time_eager = world == 1 or graphed is None
+    ms_eager_plain = timed(lambda: step_resident(repack=True), args.steps) if time_eager else None
     launches_eager = _native.lib.rovr_launch_count() - n1
     ms_graph = timed(graphed, args.steps) if graphed is not None else None
-    use_graph = ms_graph is not None and ms_graph <= ms_eager_plain
+    use_graph = ms_graph is not None and (ms_eager_plain is None or ms_graph <= ms_eager_plain)
     ms_total = ms_graph if use_graph else ms_eager_plain
     launches = graphed.launches_per_step * args.steps if use_graph else launches_eager
     clocks = sampler.stop() if rank == 0 else {}
@@ -416,7 +419,7 @@ def run_cuda(args, rank, local_rank, world):
             "config": {"workload": "LocalNet U-Net fwd+L2+bwd (configs[1]): B=24 frames/GPU, 256x256, "
                                    "synthetic masked clips, random-init weights",
                        "global_batch": B_PER_GPU * world, "parallelism": f"dp{world}",
-                       "launch_modes_ms_per_step": {"eager_forked_wgrad_stream": ms_eager_plain / args.steps,
+                       "launch_modes_ms_per_step": {"eager_forked_wgrad_stream": (ms_eager_plain / args.steps) if ms_eager_plain is not None else None,
                                                     "cuda_graph_replay": (ms_graph / args.steps) if ms_graph is not None else None},
                        "launch": ("eager launches through the autograd Function, weight gradients on a forked stream" +
                                   (", bucketed NCCL all-reduce overlapped with backward" if world > 1 else "")
