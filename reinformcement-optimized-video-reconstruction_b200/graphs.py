@@ -41,7 +41,9 @@ class GraphedFunction:
         import _native
         n0 = _native.lib.rovr_launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # capture on the SAME stream the warm-up ran on: the per-(device, stream) scratch workspace it sized lives in the
+        # ordinary pool and is simply reused — nothing the kernels scribble on is tied to this graph's private pool
+        with torch.cuda.graph(self.graph, stream=side):
             self.outputs = fn(*self.inputs)
         self.launches = int(_native.lib.rovr_launch_count() - n0)
 

@@ -484,7 +484,7 @@ class GraphedTrainingStep:
                 n0 = _native.lib.rovr_launch_count()
                 self.graph = torch.cuda.CUDAGraph()
                 try:
-                    with torch.cuda.graph(self.graph):
+                    with torch.cuda.graph(self.graph, stream=side):     # the warm-up's stream: its scratch workspace is reused
                         self.y, self.loss = run()
                 except Exception as exc:      # noqa: BLE001 — a collective that cannot be captured
                     if not attempt:
@@ -504,7 +504,7 @@ class GraphedTrainingStep:
                 if repack_weights:
                     net._packed._cache.clear()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, stream=side):
                     yk, lk = run(k)
                 self.graphs.append(g)
                 self.ys.append(yk)

@@ -147,7 +147,7 @@ class ROVRStep:
             import _native
             n0 = _native.lib.rovr_launch_count()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=side):
                 self._time_step(st)
             self.launches_per_time_step = int(_native.lib.rovr_launch_count() - n0)   # kernels of this library per replay
             self._ts_graph = (key, graph, st)
