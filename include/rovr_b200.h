@@ -185,6 +185,19 @@ int rovr_bn_train_bwd(const void* dy, int dy_ld, const void* y, int y_ld, const 
                       const float* mean, const float* rstd, float* dgamma, float* dbeta, int relu,
                       void* ws, size_t ws_bytes, void* stream);
 
+/* Train-mode BatchNorm with PER-FRAME statistics over `frames` groups of `pix` pixels (frame-major NHWC; x is the
+ * convolution output, bf16 or — x_f32 != 0, x_ld in floats — fp32, so that the statistics and the centring see the
+ * unrounded values; y is always bf16):
+ * the reference encodes one frame per call (rovr/resnet_extractor.py:42-47, `.unsqueeze(0)`), so a trunk left in
+ * training mode (the default constructor, rovr/resnet_extractor.py:6-8) normalises each frame with its own
+ * statistics and updates running_mean / running_var once per frame, in frame order; num_batches_tracked += frames.
+ * mean / rstd: fp32 [frames][C]. x == y is allowed for a bf16 x. ws >= rovr_bn_frames_workspace(C, frames, pix). */
+size_t rovr_bn_frames_workspace(int C, int frames, long long pix);
+int rovr_bn_train_fwd_frames(const void* x, int x_f32, int x_ld, void* y, int y_ld, int frames, long long pix, int C,
+                             int c_valid, const float* gamma, const float* beta, float eps, float momentum,
+                             float* running_mean, float* running_var, long long* num_batches_tracked,
+                             float* mean, float* rstd, int relu, void* ws, size_t ws_bytes, void* stream);
+
 /* eval mode (module.eval()): running statistics, buffers untouched. rstd (fp32 [C]) is produced for the
  * backward pass, whose statistics are constants: dx = gamma * rstd * dy * (y > 0). */
 int rovr_bn_eval_fwd(const void* x, int x_ld, void* y, int y_ld, long long npix, int C, int c_valid,
@@ -372,6 +385,9 @@ int rovr_blocksum4(const float* dwp, float* dw, int d0, int d1, int inner, int c
  * strides), so nothing is computed at the discarded positions. */
 int rovr_conv3x3_fprop_s2(const void* x, int x_ld, const void* wk, const float* bias, void* y, int y_ld, int B, int H,
                           int W, int Cin, int Cout, int relu, void* stream);
+/* the same with an fp32 NHWC output (y_ld in floats): the train-mode trunk's BatchNorm reads the unrounded values */
+int rovr_conv3x3_fprop_s2_f32out(const void* x, int x_ld, const void* wk, const float* bias, float* y, int y_ld, int B,
+                                 int H, int W, int Cin, int Cout, int relu, void* stream);
 /* Conv2d 3x3 pad 1 with fp32 NHWC output (forward; or, with the rovr_repack_conv3x3_dgrad operand and
  * Cin / Cout swapped by the caller, the data gradient) */
 int rovr_conv3x3_f32out(const void* x, int x_ld, const void* wk, const float* bias, float* y, int y_ld,

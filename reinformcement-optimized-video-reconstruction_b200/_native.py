@@ -65,6 +65,9 @@ SIGNATURES = {
     "rovr_bn_train_fwd": (_i, [_p, _i, _p, _i, _ll, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
     "rovr_bn_train_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _i, _ll, _i, _i, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
     "rovr_bn_eval_fwd": (_i, [_p, _i, _p, _i, _ll, _i, _i, _p, _p, _f, _p, _p, _p, _i, _p]),
+    "rovr_bn_frames_workspace": (_sz, [_i, _i, _ll]),
+    "rovr_bn_train_fwd_frames": (_i, [_p, _i, _i, _p, _i, _i, _ll, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i, _p, _sz,
+                                      _p]),
     "rovr_bn_eval_bwd": (_i, [_p, _i, _p, _i, _p, _i, _p, _i, _ll, _i, _i, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
     "rovr_layernorm_fwd": (_i, [_p, _ll, _i, _f, _p, _p, _p, _p, _p, _p, _p]),
     "rovr_layernorm_workspace": (_sz, [_i]),
@@ -112,6 +115,7 @@ SIGNATURES = {
     "rovr_split_weights": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "rovr_blocksum4": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "rovr_conv3x3_fprop_s2": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "rovr_conv3x3_fprop_s2_f32out": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "rovr_conv3x3_f32out": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "rovr_convT2x2_fprop_f32out": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "rovr_convT2x2_dgrad_f32out": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p]),

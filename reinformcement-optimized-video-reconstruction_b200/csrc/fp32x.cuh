@@ -151,6 +151,8 @@ __global__ void blocksum4_kernel(const float* __restrict__ dwp, float* __restric
 __global__ void bn_stats_partial_f32_kernel(const float* __restrict__ x, int ld, long long npix, int C,
                                             float* __restrict__ partial) {
   extern __shared__ float ssum[];  // [blockDim.x * 4]
+  x += static_cast<long long>(blockIdx.y) * npix * ld;        // gridDim.y > 1: one statistics group per frame
+  partial += static_cast<long long>(blockIdx.y) * gridDim.x * 2 * C;
   const int c2 = C >> 1;
   const int pl = threadIdx.x / c2;
   const int cp = threadIdx.x - pl * c2;

@@ -15,9 +15,12 @@ namespace rovr {
 
 // ---- BatchNorm statistics: stage 1, [grid][2*C] partial (sum, sum of squares) ------------------
 // blockDim = 256 (or C/2 if larger): thread t owns channel pair (t % (C/2)) of pixel lane t / (C/2).
+// gridDim.y > 1: one statistics group per FRAME of npix pixels (partial is [frame][gridDim.x][2 * C]).
 __global__ void bn_stats_partial_kernel(const __nv_bfloat16* __restrict__ x, int ld, long long npix,
                                         int C, float* __restrict__ partial) {
   extern __shared__ float ssum[];  // [blockDim.x * 4]
+  x += static_cast<long long>(blockIdx.y) * npix * ld;
+  partial += static_cast<long long>(blockIdx.y) * gridDim.x * 2 * C;
   const int c2 = C >> 1;
   const int pl = threadIdx.x / c2;
   const int cp = threadIdx.x - pl * c2;
@@ -77,6 +80,44 @@ __global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int 
   }
 }
 
+// Per-frame statistics: the reference encodes every frame on its own (rovr/resnet_extractor.py:42-47,
+// `.unsqueeze(0)` -> a batch of ONE), so a train-mode trunk (the default `pretrained=False` constructor,
+// rovr/resnet_extractor.py:6-8) normalises each frame with its own mean / variance and updates the running
+// buffers once per frame, in frame order. One thread per channel walks the frames in that order.
+// mean / rstd: [frames][C].
+__global__ void bn_frames_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, long long pix,
+                                          int frames, float eps, float momentum, float* __restrict__ mean,
+                                          float* __restrict__ rstd, float* __restrict__ running_mean,
+                                          float* __restrict__ running_var,
+                                          long long* __restrict__ num_batches_tracked, int c_valid) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += frames;
+  if (c >= C) return;
+  const bool track = c < c_valid && running_mean != nullptr;
+  float rm = track ? running_mean[c] : 0.f, rv = track ? running_var[c] : 0.f;
+  const double n = static_cast<double>(pix);
+  for (int f = 0; f < frames; ++f) {
+    const float* pf = partial + static_cast<long long>(f) * nblocks * 2 * C;
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+      s += static_cast<double>(pf[static_cast<long long>(b) * 2 * C + c]);
+      q += static_cast<double>(pf[static_cast<long long>(b) * 2 * C + C + c]);
+    }
+    const double m = s / n;
+    double var = q / n - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[static_cast<long long>(f) * C + c] = static_cast<float>(m);
+    rstd[static_cast<long long>(f) * C + c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const double unbiased = pix > 1 ? var * n / (n - 1.0) : var;
+    rm = (1.f - momentum) * rm + momentum * static_cast<float>(m);
+    rv = (1.f - momentum) * rv + momentum * static_cast<float>(unbiased);
+  }
+  if (track) {
+    running_mean[c] = rm;
+    running_var[c] = rv;
+  }
+}
+
 // eval mode: rstd[c] = 1 / sqrt(running_var[c] + eps) (mean is running_mean itself)
 __global__ void bn_eval_rstd_kernel(const float* __restrict__ running_var, float eps, float* __restrict__ rstd,
                                     int c_valid, int C) {
@@ -85,16 +126,21 @@ __global__ void bn_eval_rstd_kernel(const float* __restrict__ running_var, float
 }
 
 // y = [relu](gamma * (x - mean) * rstd + beta); channels >= c_valid (zero padding) are written as 0.
+// frame_pix > 0: mean / rstd are [frames][C], pixel px belongs to frame px / frame_pix.
 __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld,
                                 __nv_bfloat16* __restrict__ y, int y_ld, long long npix, int C,
                                 const float* __restrict__ mean, const float* __restrict__ rstd,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                int c_valid, int relu) {
+                                int c_valid, int relu, long long frame_pix) {
   const int c8 = C >> 3;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= npix * c8) return;
   const int cb = static_cast<int>(i % c8) * 8;
   const long long px = i / c8;
+  if (frame_pix > 0) {
+    mean += (px / frame_pix) * C;
+    rstd += (px / frame_pix) * C;
+  }
   const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + px * x_ld + cb));
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
   uint32_t o[4];
@@ -114,6 +160,37 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld,
     o[j] = pack_bf16x2(v[0], v[1]);
   }
   *reinterpret_cast<uint4*>(y + px * y_ld + cb) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// the same from an fp32 convolution output (x_ld in floats, a multiple of 4) to the bf16 activation
+__global__ void bn_apply_f32in_kernel(const float* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y, int y_ld,
+                                      long long npix, int C, const float* __restrict__ mean,
+                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, int c_valid, int relu, long long frame_pix) {
+  const int c8 = C >> 3;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= npix * c8) return;
+  const int cb = static_cast<int>(i % c8) * 8;
+  const long long px = i / c8;
+  if (frame_pix > 0) {
+    mean += (px / frame_pix) * C;
+    rstd += (px / frame_pix) * C;
+  }
+  const float4 a = __ldg(reinterpret_cast<const float4*>(x + px * x_ld + cb));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(x + px * x_ld + cb + 4));
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = cb + e;
+    float r = 0.f;
+    if (c < c_valid) {
+      r = (v[e] - mean[c]) * rstd[c] * gamma[c] + beta[c];
+      if (relu) r = fmaxf(r, 0.f);
+    }
+    v[e] = r;
+  }
+  *reinterpret_cast<uint4*>(y + px * y_ld + cb) =
+      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
 
 // ---- BatchNorm backward ---------------------------------------------------------------------

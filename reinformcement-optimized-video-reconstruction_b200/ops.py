@@ -251,6 +251,17 @@ def conv3x3_fprop_s2(x, wk, bias, y, relu=True):
     return y
 
 
+def conv3x3_fprop_s2_f32out(x, wk, bias, y, relu=False):
+    """conv3x3_fprop_s2 with an fp32 NHWC output."""
+    B, H, W, Cin, x_ld = _act(x, "x")
+    By, Hy, Wy, Cout, y_ld = _actf(y, "y")
+    assert (By, Hy, Wy) == (B, (H - 1) // 2 + 1, (W - 1) // 2 + 1) and wk.shape == (Cout, 9 * Cin), (x.shape, y.shape, wk.shape)
+    _f32(bias, "bias")
+    _launch("rovr_conv3x3_fprop_s2_f32out", _ptr(x), x_ld, _ptr(wk), _ptr(bias), _ptr(y), y_ld, B, H, W, Cin, Cout,
+            int(relu), _stream())
+    return y
+
+
 def conv3x3_fprop_tail(x, wk, bias, y, w8, b8, target=None):
     """y = relu(conv3x3(x) + bias) (Cout = 64) and, from the same epilogue, out = sigmoid(conv8_1x1(y))
     (NCHW fp32) [+ mean((out - target)^2)]. Returns (out, loss | None)."""
@@ -513,6 +524,23 @@ def bn_train_fwd(x, y, gamma, beta, c_valid, eps, momentum, running_mean, runnin
     ws = workspace(N.lib.rovr_bn_workspace(C), x.device)
     _launch("rovr_bn_train_fwd", _ptr(x), x_ld, _ptr(y), y_ld, B * H * W, C, c_valid, _ptr(gamma), _ptr(beta),
             ctypes.c_float(eps), ctypes.c_float(momentum), _ptr(running_mean), _ptr(running_var), _ptr(nbt),
+            _ptr(mean), _ptr(rstd), int(relu), _ptr(ws), ws.numel(), _stream())
+    return mean, rstd
+
+
+def bn_train_fwd_frames(x, y, gamma, beta, eps, momentum, running_mean, running_var, nbt, relu=True):
+    """Train-mode BatchNorm (+ReLU) with one statistics group per FRAME: the reference's trunk at batch 1 per frame
+    (rovr/resnet_extractor.py:42-47). x: the convolution output, NHWC [frames, H, W, C], bf16 (y may then be x) or
+    fp32; y: bf16. Running buffers are updated once per frame in frame order. Returns (mean, rstd) fp32 [frames, C]."""
+    x_f32 = x.dtype == torch.float32
+    B, H, W, C, x_ld = _actf(x, "x") if x_f32 else _act(x, "x")
+    By, Hy, Wy, Cy, y_ld = _act(y, "y")
+    assert (By, Hy, Wy, Cy) == (B, H, W, C)
+    mean = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    rstd = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    ws = workspace(N.lib.rovr_bn_frames_workspace(C, B, H * W), x.device)
+    _launch("rovr_bn_train_fwd_frames", _ptr(x), int(x_f32), x_ld, _ptr(y), y_ld, B, H * W, C, C, _ptr(gamma),
+            _ptr(beta), ctypes.c_float(eps), ctypes.c_float(momentum), _ptr(running_mean), _ptr(running_var), _ptr(nbt),
             _ptr(mean), _ptr(rstd), int(relu), _ptr(ws), ws.numel(), _stream())
     return mean, rstd
 

@@ -70,6 +70,7 @@ class ResnetFeatureExtractor(torch.nn.Module):
             transforms.ToTensor(),
         ])
         self._folded = {}
+        self._bn_train = False
 
     # -- folded / packed trunk weights --------------------------------------------------------------
     def _conv_bn(self, conv, bn, kind):
@@ -87,44 +88,85 @@ class ResnetFeatureExtractor(torch.nn.Module):
         self._folded[key] = (ver, wk, bias)
         return wk, bias
 
+    def _conv_raw(self, conv, kind):
+        """Train-mode trunk: the convolution's own weights (no BatchNorm folded in, no bias), packed."""
+        key = ("raw", id(conv))
+        ver = (conv.weight.data_ptr(), conv.weight._version)
+        hit = self._folded.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1], None
+        wf = conv.weight.detach().float().contiguous()
+        wk = ops.repack_conv3x3(wf, False) if kind == "c3" else ops.repack_linear(wf.reshape(wf.shape[0], -1), False)
+        self._folded[key] = (ver, wk, None)
+        return wk, None
+
+    def _weights(self, conv, bn, kind):
+        return self._conv_raw(conv, kind) if self._bn_train else self._conv_bn(conv, bn, kind)
+
+    def _bn(self, z, bn, relu):
+        """Train-mode trunk only: z is the fp32 convolution output (the statistics and the centring must see the
+        unrounded values: |mean| is a multiple of the standard deviation behind a ReLU, so a bf16 z would cost that
+        multiple in relative accuracy at every one of the 53 layers); returns the bf16 activation
+        BatchNorm(z) [+ReLU] with per-frame batch statistics."""
+        if not self._bn_train:
+            return z
+        if bn.momentum is None or not bn.track_running_stats:
+            raise NotImplementedError("ResnetFeatureExtractor (B200): train-mode BatchNorm needs momentum and "
+                                      "track_running_stats, as torchvision's resnet50 has them")
+        y = torch.empty(z.shape, dtype=BF, device=z.device)
+        ops.bn_train_fwd_frames(z, y, bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum, bn.running_mean,
+                                bn.running_var, bn.num_batches_tracked, relu=relu)
+        return y
+
     def _check_trunk_mode(self):
+        """Returns True for a train-mode trunk (the default constructor, rovr/resnet_extractor.py:6-8), False for the
+        frozen eval-mode one (pretrained=True, :11-14 — what rovr.py:31 and imitation_learning.py:39 build)."""
         # decided from the BatchNorm layers themselves: `self.resnet` is a fresh nn.Sequential built AFTER the
         # reference's `.eval()` (rovr/resnet_extractor.py:11-16), so its own `training` flag is True even
         # though every child is in eval mode
-        if any(m.training for m in self.resnet.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)):
-            raise NotImplementedError(
-                "ResnetFeatureExtractor (B200): the trunk must be in eval mode (frozen, as with pretrained=True, "
-                "rovr/resnet_extractor.py:11-14); a train-mode trunk is outside the ROVR hot path")
+        modes = {m.training for m in self.resnet.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)}
+        if len(modes) > 1:
+            raise NotImplementedError("ResnetFeatureExtractor (B200): the trunk's BatchNorm layers must all be in the "
+                                      "same mode")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.resnet.parameters()):
             raise NotImplementedError(
                 "ResnetFeatureExtractor (B200): the trunk is forward-only; freeze it (requires_grad=False) as the "
                 "reference does for pretrained=True, or call under torch.no_grad()")
+        return True in modes
 
     def _c1(self, x, conv, bn, relu):
         if conv.stride[0] > 1:
             x = ops.subsample(x, conv.stride[0])
         B, H, W, C = x.shape
-        wk, bias = self._conv_bn(conv, bn, "c1")
-        y = ops.gemm_bf16(x.reshape(-1, C), wk, bias, relu=relu)
-        return y.view(B, H, W, conv.out_channels)
+        wk, bias = self._weights(conv, bn, "c1")
+        y = ops.gemm_bf16(x.reshape(-1, C), wk, bias, relu=relu and not self._bn_train,
+                          out_dtype=torch.float32 if self._bn_train else BF)
+        return self._bn(y.view(B, H, W, conv.out_channels), bn, relu)
 
     def _c3(self, x, conv, bn, relu):
         B, H, W, C = x.shape
-        wk, bias = self._conv_bn(conv, bn, "c3")
-        if conv.stride[0] == 2:     # native stride 2: the TMA operand map samples every other input pixel
-            y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, conv.out_channels), dtype=BF, device=x.device)
-            return ops.conv3x3_fprop_s2(x, wk, bias, y, relu=relu)
-        y = torch.empty((B, H, W, conv.out_channels), dtype=BF, device=x.device)
-        return ops.conv3x3_fprop(x, wk, bias, y, relu=relu)
+        wk, bias = self._weights(conv, bn, "c3")
+        s2 = conv.stride[0] == 2    # native stride 2: the TMA operand map samples every other input pixel
+        shape = (B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, conv.out_channels) if s2 else (B, H, W, conv.out_channels)
+        if self._bn_train:
+            z = torch.empty(shape, dtype=torch.float32, device=x.device)
+            (ops.conv3x3_fprop_s2_f32out if s2 else ops.conv3x3_f32out)(x, wk, None, z, relu=False)
+            return self._bn(z, bn, relu)
+        y = torch.empty(shape, dtype=BF, device=x.device)
+        return (ops.conv3x3_fprop_s2 if s2 else ops.conv3x3_fprop)(x, wk, bias, y, relu=relu)
 
-    def _trunk(self, frames):
-        """frames: NCHW fp32 [n,3,224,224] already ToTensor-quantised -> pooled features [n,2048] fp32."""
+    def _trunk(self, frames, bn_train=False):
+        """frames: NCHW fp32 [n,3,224,224] already ToTensor-quantised -> pooled features [n,2048] fp32.
+        bn_train: every BatchNorm uses (and records) per-frame batch statistics — the reference's trunk in
+        training mode at its batch of one frame per call — instead of being folded into the convolution."""
+        self._bn_train = bool(bn_train)
         r = self.resnet
         conv1, bn1, layers = r[0], r[1], (r[4], r[5], r[6], r[7])
         n = frames.shape[0]
         cols, Ho, Wo = ops.stem_im2col(frames, 160, quantise=False)
-        wk, bias = self._conv_bn(conv1, bn1, "stem")
-        x = ops.gemm_bf16(cols, wk, bias, relu=True).view(n, Ho, Wo, 64)
+        wk, bias = self._weights(conv1, bn1, "stem")
+        x = self._bn(ops.gemm_bf16(cols, wk, bias, relu=not self._bn_train,
+                                   out_dtype=torch.float32 if self._bn_train else BF).view(n, Ho, Wo, 64), bn1, True)
         x = ops.maxpool_pad_fwd(x, 3, 2, 1)
         for layer in layers:
             for blk in layer:
@@ -145,9 +187,9 @@ class ResnetFeatureExtractor(torch.nn.Module):
         """frames [n,3,h,w] in [0,1] -> [n,768] features (grad flows into `linear` only)."""
         if not frames.is_cuda:
             raise RuntimeError("ResnetFeatureExtractor (B200) needs CUDA tensors: there is no CPU path")
-        self._check_trunk_mode()
+        bn_train = self._check_trunk_mode()
         with torch.no_grad():
-            pooled = self._trunk(self._preprocess_gpu(frames))
+            pooled = self._trunk(self._preprocess_gpu(frames), bn_train)
         return LinearF32.apply(pooled, self.linear.weight, self.linear.bias)
 
     # -- reference API --------------------------------------------------------------------------------

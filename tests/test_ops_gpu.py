@@ -462,3 +462,38 @@ def test_conv3x3_stride2(B, H, W, Cin, Cout):
     # the stride-1 kernel sampled at the even positions (its halo mode accumulates the taps in another order: not
     # bit-identical, but within one bf16 rounding)
     _report("conv3x3_s2 vs sub-sampled stride 1", _nchw(y), _nchw(y1[:, ::2, ::2].contiguous()).float(), 1e-2)
+    # fp32 output of the same kernel (train-mode ResNet trunk): the same accumulators, unrounded
+    yf = torch.full((B, Ho, Wo, Cout), 9.0, dtype=torch.float32, device=dev)
+    ops.conv3x3_fprop_s2_f32out(x, wk, b, yf, relu=True)
+    assert torch.equal(yf.to(BF), y)
+    _report("conv3x3_s2 fp32 out", _nchw(yf), ref, 2e-5)
+
+
+@pytest.mark.parametrize("frames,H,W,C,f32", [(6, 56, 56, 64, True), (6, 7, 7, 2048, True), (3, 14, 14, 1024, False), (1, 28, 28, 512, True),
+                                              (40, 9, 5, 256, True)])
+def test_bn_train_fwd_frames(frames, H, W, C, f32):
+    """Train-mode BatchNorm with per-frame statistics (the reference's trunk at batch 1 per frame,
+    rovr/resnet_extractor.py:42-47) vs a loop of F.batch_norm calls, one frame at a time, on the same buffers."""
+    import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(frames * 7 + C)
+    x = (torch.randn((frames, H, W, C), generator=g) * (0.5 + torch.rand((C,), generator=g)) + 2.0 * torch.rand((C,), generator=g))
+    x = x.to(dev) if f32 else x.to(BF).to(dev)
+    gamma = (0.5 + torch.rand((C,), generator=g)).to(dev)
+    beta = (torch.rand((C,), generator=g) - 0.5).to(dev)
+    rm, rv = torch.rand((C,), generator=g).to(dev), (1.0 + torch.rand((C,), generator=g)).to(dev)
+    nbt = torch.tensor(3, dtype=torch.int64, device=dev)
+    rm0, rv0 = rm.clone(), rv.clone()
+    y = torch.empty((frames, H, W, C), dtype=BF, device=dev)
+    mean, rstd = ops.bn_train_fwd_frames(x, y, gamma, beta, 1e-5, 0.1, rm, rv, nbt, relu=True)
+    refs = []
+    for f in range(frames):
+        xf = x[f:f + 1].float().permute(0, 3, 1, 2)
+        refs.append(F.relu(F.batch_norm(xf, rm0, rv0, gamma, beta, training=True, momentum=0.1, eps=1e-5)))
+    ref = torch.cat(refs)
+    assert int(nbt) == 3 + frames
+    _report("bn frames y", _nchw(y), ref, 5e-3)
+    _report("bn frames running_mean", rm, rm0, 1e-5)
+    _report("bn frames running_var", rv, rv0, 1e-4)
+    want_mean = x.float().mean(dim=(1, 2))
+    _report("bn frames mean", mean, want_mean, 1e-5)

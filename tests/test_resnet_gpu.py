@@ -148,9 +148,8 @@ def test_resnet_encode_insert_extract(golden_dir):
     assert _rel(enc[0, :, 16:32, 32:48], fmap[0, :, 0:16, 0:16]) < 1e-3
     patches = m.extract_patch([[0, 1]], fmap)
     assert patches.shape == (1, 2, 3, 16, 16) and torch.equal(patches[0, 1], fmap[0, :, 0:16, 16:32])
-    with pytest.raises(NotImplementedError):
-        m.resnet.train()
-        m(x)
+    m.resnet.train()                                    # frozen but train-mode trunk: batch statistics, forward-only
+    assert torch.isfinite(m(x)).all() and _rel(m(x).detach(), fmap) > 1e-3
     with pytest.raises(RuntimeError):
         m.resnet.eval()
         m(x.cpu())
@@ -177,10 +176,58 @@ def test_resnet_built_like_the_reference(monkeypatch):
     assert m.linear.weight.grad is not None and all(p.grad is None for p in m.resnet.parameters())
     tile = m.encode(x[0, 0])
     assert tile.shape == (3, 16, 16)
-    # a default-constructed (train-mode, trainable) trunk is outside the hot path and says so
+    # a default-constructed (train-mode, TRAINABLE) trunk is forward-only: with autograd on it says so ...
     m2 = M.ResnetFeatureExtractor().to(_dev())
     with pytest.raises(NotImplementedError):
         m2(x)
+    # ... and under no_grad it runs with batch statistics (test_resnet_train_mode_trunk_vs_oracle checks the numbers)
+    with torch.no_grad():
+        assert torch.isfinite(m2(x)).all()
+
+
+def test_resnet_train_mode_trunk_vs_oracle():
+    """The default constructor (`pretrained=False`, rovr/resnet_extractor.py:6-8) leaves the trunk in TRAINING mode,
+    and the reference encodes one frame per call (:42-47), so every BatchNorm normalises each frame with that frame's
+    own statistics and updates its running buffers once per frame, in frame order. The drop-in batches the frames and
+    must reproduce exactly that: feature map, running_mean / running_var and num_batches_tracked against the oracle
+    (the reference's own loop over the same torchvision modules on the CPU)."""
+    import copy
+    import resnet_extractor as M
+    dev = _dev()
+    warnings.filterwarnings("ignore")
+    torch.manual_seed(11)
+    m = M.ResnetFeatureExtractor()
+    O.resnet_randomise_bn(m.resnet, 29)                 # non-trivial affine and running statistics
+    ref_seq = copy.deepcopy(m.resnet).train()
+    lw, lb = m.linear.weight.detach().clone(), m.linear.bias.detach().clone()
+    m = m.to(dev)
+    x = torch.rand((2, 3, 3, 96, 128), generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        want = O.resnet_extractor_forward(ref_seq, lw, lb, x)
+        got = m(x.to(dev))
+    err = ((got.cpu() - want).norm() / want.norm()).item()
+    print(f"train-mode trunk: feature map l2-rel {err:.3e}")
+    assert err < 5e-2, err
+    ref_bns = [b for b in ref_seq.modules() if isinstance(b, torch.nn.BatchNorm2d)]
+    got_bns = [b for b in m.resnet.modules() if isinstance(b, torch.nn.BatchNorm2d)]
+    assert len(ref_bns) == len(got_bns) == 53
+    worst_m = worst_v = 0.0
+    for rb, gb in zip(ref_bns, got_bns):
+        assert int(gb.num_batches_tracked) == int(rb.num_batches_tracked) == 6
+        worst_m = max(worst_m, ((gb.running_mean.cpu() - rb.running_mean).norm() / rb.running_mean.norm()).item())
+        worst_v = max(worst_v, ((gb.running_var.cpu() - rb.running_var).norm() / rb.running_var.norm()).item())
+    print(f"train-mode trunk: running_mean worst l2-rel {worst_m:.3e}, running_var {worst_v:.3e}")
+    assert worst_m < 5e-2 and worst_v < 5e-2, (worst_m, worst_v)
+    # the per-frame statistics make the result independent of how frames are batched: one frame alone (the
+    # reference's own call shape) gives the same tile as the same frame inside the batch of six
+    m_one = M.ResnetFeatureExtractor().to(dev)
+    m_one.load_state_dict(m.state_dict())
+    with torch.no_grad():
+        tile = m_one.encode(x[1, 2].to(dev))
+        again = m(x.to(dev))
+    d = ((tile - again[1, :, 0:16, 32:48]).norm() / tile.norm()).item()
+    print(f"train-mode trunk: one frame alone vs inside the batch l2-rel {d:.3e}")
+    assert d < 1e-5, d
 
 
 def test_video_processor_restatement_and_il_step():
