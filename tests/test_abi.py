@@ -59,3 +59,22 @@ def test_host_selftest_index_arithmetic():
     umulhi + add + shift) agrees with integer division — checked on the host, no GPU involved."""
     import _native
     assert _native.lib.rovr_host_selftest() == 0
+
+
+def test_workspace_sizes_are_host_arithmetic():
+    """The `rovr_*_workspace` functions are pure host arithmetic (no device needed): the per-frame BatchNorm
+    workspace is frames x blocks x 2C floats with 1..16 blocks per frame, never grows when the same pixels are
+    spread over more frames than blocks are useful for, and rejects nonsense shapes with 0."""
+    import _native
+    lib = _native.lib
+    for C in (64, 256, 2048):
+        assert lib.rovr_bn_workspace(C) >= 2 * C * 4
+        for frames, pix in ((1, 49), (6, 3136), (25, 12544), (500, 49), (4000, 196)):
+            n = lib.rovr_bn_frames_workspace(C, frames, pix)
+            blocks, rem = divmod(n, frames * 2 * C * 4)
+            assert rem == 0 and 1 <= blocks <= 16, (C, frames, pix, n)
+        # many frames: one or two blocks per frame are enough to fill the machine
+        assert lib.rovr_bn_frames_workspace(C, 4000, 196) == 4000 * 2 * C * 4
+    assert lib.rovr_bn_frames_workspace(0, 4, 49) == 0
+    assert lib.rovr_bn_frames_workspace(64, 0, 49) == 0
+    assert lib.rovr_bn_frames_workspace(64, 4, 0) == 0
