@@ -273,7 +273,17 @@ def run_cuda(args, rank, local_rank, world):
     prof = []
     n0 = _native.lib.rovr_launch_count()
     esteps = min(args.steps, 20)      # the per-kernel-event pass is bounded (a --steps 1000 run would hold 10^5 events)
-    ms_eager = timed(step_resident, esteps, profile=prof) * (args.steps / esteps)
+    # every kernel is timed ALONE in this pass: the forked weight-gradient stream of the eager mode is switched off, or the
+    # events around a data-gradient launch would also span the weight-gradient kernel sharing the SMs with it
+    fork_env = os.environ.get("ROVR_WGRAD_STREAM")
+    os.environ["ROVR_WGRAD_STREAM"] = "0"
+    try:
+        ms_eager = timed(step_resident, esteps, profile=prof) * (args.steps / esteps)
+    finally:
+        if fork_env is None:
+            del os.environ["ROVR_WGRAD_STREAM"]
+        else:
+            os.environ["ROVR_WGRAD_STREAM"] = fork_env
     launches = (_native.lib.rovr_launch_count() - n0) * (args.steps / esteps)
     # Two launch modes of the same kernel sequence are timed over the K steps, both re-packing all 19 weight tensors
     # every step: (1) eager launches through the autograd Function — weight gradients on a forked stream, bucket
