@@ -174,6 +174,11 @@ class ROVRStep:
         from graphs import GraphedFunction
         obs, acs, log_prob, rtgs = info
         actor, critic = self.actor2, self.critic2
+        key = tuple(tuple(t.shape) for t in (*obs, acs, log_prob, rtgs))
+        if self._ppo_graphs is not None and self._ppo_graphs[2] != key:      # another clip length: capture again
+            for g in self._ppo_graphs[:2]:
+                g.close()
+            self._ppo_graphs = None
         if self._ppo_graphs is None:
             s_obs = tuple(t.clone() for t in obs)
             s_acs, s_lp, s_rtg = acs.clone(), log_prob.clone(), rtgs.clone()
@@ -193,8 +198,8 @@ class ROVRStep:
                 return loss.detach()
             gc = GraphedFunction(critic_fn, (*s_obs, s_rtg), modules=[critic])
             ga = GraphedFunction(actor_fn, (*s_obs, s_acs, s_lp, s_A), modules=[actor])
-            self._ppo_graphs = (gc, ga)
-        gc, ga = self._ppo_graphs
+            self._ppo_graphs = (gc, ga, key)
+        gc, ga = self._ppo_graphs[:2]
         with torch.no_grad():
             V = critic(*obs, device)
         A_k = rtgs - V.detach()
