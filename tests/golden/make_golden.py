@@ -304,6 +304,33 @@ def gen_resnet():
     print("resnet.npz", len(out), "arrays")
 
 
+def resnet_train_inputs():
+    return torch.rand((1, 3, 3, 48, 64), generator=torch.Generator().manual_seed(63))
+
+
+def gen_resnet_train():
+    """The reference's DEFAULT constructor (`pretrained=False`, rovr/resnet_extractor.py:6-8): nothing puts the trunk
+    in eval mode, so every BatchNorm runs on batch statistics — of ONE frame, since `encode` is called per frame
+    (:31-33, :42-47) — and its running buffers advance once per frame. Pins that behaviour: feature map, the running
+    statistics of the first and the last BatchNorm and `num_batches_tracked` after one forward of a 3-frame clip."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    from resnet_extractor import ResnetFeatureExtractor
+    torch.manual_seed(0)
+    m = quiet(ResnetFeatureExtractor)                       # default arguments: train-mode, trainable trunk
+    O.resnet_randomise_bn(m.resnet, 29)
+    assert all(b.training for b in m.resnet.modules() if isinstance(b, torch.nn.BatchNorm2d))
+    with torch.no_grad():
+        y = m(resnet_train_inputs())
+    bns = [b for b in m.resnet.modules() if isinstance(b, torch.nn.BatchNorm2d)]
+    out = {"y": y.numpy(), "nbt": np.array([int(b.num_batches_tracked) for b in bns])}
+    for tag, b in (("first", bns[0]), ("last", bns[-1])):
+        out[f"{tag}/running_mean"] = b.running_mean.numpy().copy()
+        out[f"{tag}/running_var"] = b.running_var.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "resnet_train.npz"), **out)
+    print("resnet_train.npz", len(out), "arrays")
+
+
 def gen_lpips():
     """LPIPS(net='vgg'): the `lpips` package is not in this image (parity unpinned against it); what IS
     pinned is the VGG16 trunk — torchvision.models.vgg16().features run as torchvision wrote it, with the
@@ -359,6 +386,6 @@ def gen_lpips():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["localnet", "pn1", "pn2", "common", "action_lstm", "resnet", "lpips"]
+    which = sys.argv[1:] or ["localnet", "pn1", "pn2", "common", "action_lstm", "resnet", "resnet_train", "lpips"]
     for w in which:
         globals()["gen_" + w]()

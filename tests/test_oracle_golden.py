@@ -315,6 +315,41 @@ def test_resnet_extractor_matches_reference(golden_dir):
     assert keys == list(G["keys"])
 
 
+def test_resnet_train_mode_oracle_matches_reference(golden_dir):
+    """The reference's default constructor leaves the trunk in training mode and encodes one frame per call
+    (rovr/resnet_extractor.py:6-8,31-33,42-47): per-frame batch statistics, running buffers advanced once per frame.
+    The oracle's loop on a train-mode trunk must reproduce tests/golden/resnet_train.npz (made by the imported
+    reference class): feature map, first / last BatchNorm running statistics, num_batches_tracked."""
+    import warnings
+    import torchvision.models as models
+    warnings.filterwarnings("ignore")
+    G = _load(golden_dir, "resnet_train.npz")
+    torch.manual_seed(0)
+    net = models.resnet50(pretrained=False)
+    linear = torch.nn.Linear(2048, 768)
+    seq = torch.nn.Sequential(*(list(net.children())[:-1]))
+    O.resnet_randomise_bn(seq, 29)
+    seq.train()
+    x = torch.rand((1, 3, 3, 48, 64), generator=torch.Generator().manual_seed(63))
+    with torch.no_grad():
+        y = O.resnet_extractor_forward(seq, linear.weight, linear.bias, x)
+    assert np.allclose(y.numpy(), G["y"], rtol=1e-4, atol=1e-5)
+    bns = [b for b in seq.modules() if isinstance(b, torch.nn.BatchNorm2d)]
+    assert [int(b.num_batches_tracked) for b in bns] == list(G["nbt"]) == [3] * 53
+    for tag, b in (("first", bns[0]), ("last", bns[-1])):
+        assert np.allclose(b.running_mean.numpy(), G[f"{tag}/running_mean"], rtol=1e-4, atol=1e-6)
+        assert np.allclose(b.running_var.numpy(), G[f"{tag}/running_var"], rtol=1e-4, atol=1e-6)
+    # and the statistics really are per frame: the same frames in ONE batch of three give another result
+    seq2 = torch.nn.Sequential(*(list(models.resnet50(pretrained=False).children())[:-1]))
+    seq2.load_state_dict({k: v for k, v in seq.state_dict().items()})
+    import torchvision.transforms as T
+    prep = T.Compose([T.ToPILImage(), T.Resize((224, 224)), T.ToTensor()])
+    with torch.no_grad():
+        batched = seq2.train()(torch.stack([prep(f) for f in x[0]]))
+        tiles = torch.nn.functional.linear(batched.flatten(1), linear.weight, linear.bias).view(3, 3, 16, 16)
+    assert not np.allclose(tiles[1].numpy(), G["y"][0, :, 0:16, 16:32], rtol=1e-2, atol=1e-3)
+
+
 def test_lpips_oracle_matches_torchvision_golden(golden_dir):
     """oracle.lpips_vgg vs tests/golden/lpips.npz (torchvision's own VGG16 `features` + the published LPIPS
     head written out literally by make_golden.py). The `lpips` package itself is absent: parity unpinned

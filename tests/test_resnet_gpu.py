@@ -207,6 +207,8 @@ def test_resnet_train_mode_trunk_vs_oracle():
         got = m(x.to(dev))
     err = ((got.cpu() - want).norm() / want.norm()).item()
     print(f"train-mode trunk: feature map l2-rel {err:.3e}")
+    # 5e-2, not 2e-2: scripts/exp/resnet_train_bf16_noise.py (pure PyTorch, CPU) measures 4.45e-2 for ANY bf16-operand
+    # evaluation of this loop — 53 per-frame re-normalisations amplify the operand rounding
     assert err < 5e-2, err
     ref_bns = [b for b in ref_seq.modules() if isinstance(b, torch.nn.BatchNorm2d)]
     got_bns = [b for b in m.resnet.modules() if isinstance(b, torch.nn.BatchNorm2d)]
@@ -228,6 +230,36 @@ def test_resnet_train_mode_trunk_vs_oracle():
     d = ((tile - again[1, :, 0:16, 32:48]).norm() / tile.norm()).item()
     print(f"train-mode trunk: one frame alone vs inside the batch l2-rel {d:.3e}")
     assert d < 1e-5, d
+
+
+def test_resnet_train_mode_trunk_vs_reference_golden(golden_dir):
+    """tests/golden/resnet_train.npz was written by the UNMODIFIED reference class built with its default arguments
+    (train-mode trunk, one frame per call): the drop-in, which batches the three frames, must land on the same feature
+    map, running statistics and num_batches_tracked."""
+    import numpy as np
+    import resnet_extractor as M
+    dev = _dev()
+    warnings.filterwarnings("ignore")
+    G = np.load(os.path.join(golden_dir, "resnet_train.npz"))
+    torch.manual_seed(0)
+    m = M.ResnetFeatureExtractor()
+    O.resnet_randomise_bn(m.resnet, 29)
+    m = m.to(dev)
+    x = torch.rand((1, 3, 3, 48, 64), generator=torch.Generator().manual_seed(63)).to(dev)
+    with torch.no_grad():
+        y = m(x)
+    want = torch.from_numpy(G["y"])
+    err = ((y.cpu() - want).norm() / want.norm()).item()
+    print(f"train-mode trunk vs reference golden: feature map l2-rel {err:.3e}")
+    assert err < 5e-2, err
+    bns = [b for b in m.resnet.modules() if isinstance(b, torch.nn.BatchNorm2d)]
+    assert [int(b.num_batches_tracked) for b in bns] == list(G["nbt"])
+    for tag, b in (("first", bns[0]), ("last", bns[-1])):
+        for name in ("running_mean", "running_var"):
+            ref = torch.from_numpy(G[f"{tag}/{name}"])
+            e = ((getattr(b, name).cpu() - ref).norm() / ref.norm()).item()
+            print(f"train-mode trunk vs reference golden: {tag} BatchNorm {name} l2-rel {e:.3e}")
+            assert e < 5e-2, (tag, name, e)
 
 
 def test_video_processor_restatement_and_il_step():
